@@ -1,0 +1,418 @@
+#!/usr/bin/env python3
+"""bench.py -- coordNum pair-evaluations / second (value + gradient) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+A "step" is one pass of the hot path over one batch of synthetic coordinates:
+read_data (gather + COM) -> calc_value (all-pairs sweep, value + gradients [+ NCCL
+all-reduce when sharded]) -> value() -> apply_force (scatter).  Workload (BASELINE.json):
+
+    c5 (default)  coordNum 100 k x 1 M atoms, iso r0 = 4 A, n = 6, m = 12  (1e11 pairs; the case the
+                  metric and the >= 50 % FP64-peak target are quoted on; the SAME problem is
+                  sharded over N GPUs -> "scaling": "strong")
+    c2            coordNum 1 k x 100 k (1e8 pairs)
+    c3            selfCoordNum 50 k, tolerance 1e-3, pairListFrequency 10
+    c4            coordNum 10 k x 500 k, anisotropic cutoff3 (3, 6, 4)
+
+One JSON line is printed by rank 0.  `value` times device-resident inputs; `e2e` goes
+through the host-buffer C-ABI step (H2D of the proxy positions and D2H of value +
+gradients inside the timed region).  roofline: FP64-compute bound:
+achieved = pair-evals/s x 39 algorithmic flop, peak = DFMA microbenchmark run live here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from colvars_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    "c2": dict(kind="coordNum", n1=1000, n2=100000, cutoff3=(4.0, 4.0, 4.0), tol=0.0, freq=100,
+               name="coordNum 1k x 100k iso r0=4 n=6 m=12"),
+    "c3": dict(kind="selfCoordNum", n1=50000, n2=0, cutoff3=(4.0, 4.0, 4.0), tol=1e-3, freq=10,
+               name="selfCoordNum 50k tolerance=1e-3 pairListFrequency=10"),
+    "c4": dict(kind="coordNum", n1=10000, n2=500000, cutoff3=(3.0, 6.0, 4.0), tol=0.0, freq=100,
+               name="coordNum 10k x 500k aniso cutoff3=(3,6,4)"),
+    "c5": dict(kind="coordNum", n1=100000, n2=1000000, cutoff3=(4.0, 4.0, 4.0), tol=0.0,
+               freq=100, name="coordNum 100k x 1M iso r0=4 n=6 m=12"),
+}
+METRIC = "coordNum pair-evals/sec (value+grad)"
+UNIT = "pair-evals/s"
+
+
+def make_inputs(w):
+    if w["kind"] == "selfCoordNum":
+        proxy, i1, L = synth.selfcoordnum_case(w["n1"], seed=1234)
+        return proxy, i1, None
+    proxy, i1, i2, L = synth.coordnum_case(w["n1"], w["n2"], seed=1234)
+    return proxy, i1, i2
+
+
+def pairs_of(w):
+    return synth.num_pairs(w["kind"], w["n1"], w["n2"])
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref/ref_driver) when it was built,
+# else the plain-C port (oracle/liboracle.so); all host threads, bounded sample.
+# ---------------------------------------------------------------------------------------------
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_run(w, proxy, i1, i2, budget_s=12.0, threads=None):
+    """Time the CPU path on a slab of group1 rows against all of group2 and scale linearly.
+    Returns dict(value=pairs/s, cores, kind, sample)."""
+    threads = threads or host_cores()
+    ref_driver = ROOT / "oracle" / "_ref" / "ref_driver"
+    n1 = w["n1"]
+    n2 = w["n2"] if w["kind"] != "selfCoordNum" else w["n1"]
+    if ref_driver.exists():
+        try:
+            return cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver)
+        except Exception as e:  # fall through to the port, say why
+            sys.stderr.write(f"[bench] oracle/_ref/ref_driver failed ({e}); using the C port\n")
+    from tests import oracle_lib as O
+    p = O.make_params(w["cutoff3"], 6, 12, 0.0)
+    pos2 = proxy[i2] if i2 is not None else proxy[i1]
+
+    def slab(rows):
+        t0 = time.perf_counter()
+        O.coordnum(p, proxy[i1][:rows], pos2, omp=threads)
+        return time.perf_counter() - t0
+
+    rows = max(min(n1, (2 * 10 ** 8) // max(n2, 1)), 1)  # calibration: ~2e8 pairs
+    t = slab(rows)
+    rate = rows * n2 / t
+    rows2 = int(max(min(n1, budget_s * rate / n2), rows))
+    t2 = slab(rows2)
+    return dict(value=rows2 * n2 / t2, unit=UNIT, cores=threads, kind="port",
+                sample=f"{rows2} rows of group1 x all {n2} atoms of group2 "
+                       f"({rows2 * n2:.3g} pair-evals, {t2:.1f} s), OpenMP over rows, "
+                       "scaled linearly")
+
+
+def cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver):
+    """oracle/_ref/ref_driver: the unmodified reference library driven through
+    colvarmodule::calc() with group1 split into `threads` coordNum components under
+    `smp cvcs` (the reference's documented way to use several cores)."""
+    n1 = w["n1"]
+    n2 = w["n2"] if w["kind"] != "selfCoordNum" else w["n1"]
+    rate_guess = 6.0e7 * threads
+    rows = int(max(min(n1, budget_s * rate_guess / n2), threads))
+    if w["kind"] == "selfCoordNum":
+        rows = min(n1, int((2 * budget_s * rate_guess) ** 0.5))
+    with tempfile.TemporaryDirectory() as td:
+        inp = Path(td) / "in.bin"
+        if w["kind"] == "selfCoordNum":
+            pos1, pos2 = proxy[i1][:rows], np.zeros((0, 3))
+        else:
+            pos1, pos2 = proxy[i1][:rows], proxy[i2]
+        write_driver_input(inp, w, pos1, pos2)
+        out = subprocess.run([str(ref_driver), "--in", str(inp), "--threads", str(threads),
+                              "--steps", "3", "--time"], capture_output=True, text=True,
+                             timeout=600, env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+        if out.returncode != 0:
+            raise RuntimeError(out.stderr[-500:])
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+    npairs = rows * (rows - 1) // 2 if w["kind"] == "selfCoordNum" else rows * n2
+    sec = res["seconds_per_step"]
+    return dict(value=npairs / sec, unit=UNIT, cores=threads, kind="reference",
+                sample=f"unmodified Colvars library (oracle/_ref), colvarmodule::calc() on "
+                       f"{rows} rows of group1 x {n2 if w['kind'] != 'selfCoordNum' else rows} "
+                       f"atoms ({npairs:.3g} pair-evals, {sec:.2f} s/step), group1 split into "
+                       f"{threads} components under smp cvcs, scaled linearly")
+
+
+def write_driver_input(path, w, pos1, pos2):
+    """Binary case file of oracle/ref_driver.cpp."""
+    kind = {"coordNum": 0, "selfCoordNum": 1, "groupCoord": 2}[w["kind"]]
+    hdr = np.array([kind, len(pos1), len(pos2), 6, 12, w.get("freq", 100), 0, 0], dtype=np.int32)
+    dbl = np.array(list(w["cutoff3"]) + [w.get("tol", 0.0)], dtype=np.float64)
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes())
+        f.write(dbl.tobytes())
+        f.write(np.ascontiguousarray(pos1, dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(pos2, dtype=np.float64).tobytes())
+
+
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1]))
+                mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm),
+                       sm_mhz_min=float(min(sm)))
+        return out
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    proxy, i1, i2 = make_inputs(w)
+    steps = max(args.steps, 1)
+    per = max(4.0, min(30.0, 90.0 / (steps + args.warmup)))
+    vals = []
+    info = None
+    for k in range(args.warmup + steps):
+        info = cpu_run(w, proxy, i1, i2, budget_s=per)
+        if k >= args.warmup:
+            vals.append(info["value"])
+    value = float(np.mean(vals))
+    npairs = pairs_of(w)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * npairs / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "pairs_per_step": npairs,
+                   "note": "CPU path timed on a bounded sample and scaled linearly to the "
+                           "full step; ms_per_step is the extrapolated full-step time"},
+        "cpu_baseline": dict(info, value=value),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+
+    import torch
+    import torch.distributed as dist
+    import colvars_b200 as cb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the b200 arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    proxy, i1, i2 = make_inputs(w)
+    P = proxy.shape[0]
+    npairs = pairs_of(w)
+    cv = cb.CoordNum(w["kind"], i1, i2, cutoff3=w["cutoff3"], tolerance=w["tol"],
+                     pairlist_freq=w["freq"], device=local_rank)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(cb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        cv.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    d_pos = torch.tensor(np.ascontiguousarray(proxy.T), device=dev)  # SoA planes, stride P
+    d_force = torch.zeros_like(d_pos)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    k_force = -0.004
+
+    def step(s):
+        cv.read_data(d_pos, stream)
+        cv.calc_value(step=s, gradients=True, stream=stream)
+        v = cv.value()
+        cv.apply_force(k_force * (v - 0.1), d_force, stream)
+        return v
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP64 roofline denominator, measured live (sustained, ~250 ms of pure DFMA)
+    fp64_tflops, _ = cb.fp64_peak(local_rank, 250.0)
+
+    for s in range(args.warmup):
+        step(s)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(True), torch.cuda.Event(True), torch.cuda.Event(True),
+           torch.cuda.Event(True)) for _ in range(args.steps)]
+    launches = 0
+    value = 0.0
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)  # evict L2 between timed iterations (outside the events)
+        e0, ek0, ek1, e1 = ev[s]
+        e0.record(stream)
+        cv.read_data(d_pos, stream)
+        ek0.record(stream)
+        cv.calc_value(step=args.warmup + s, gradients=True, stream=stream)
+        ek1.record(stream)
+        value = cv.value()
+        cv.apply_force(k_force * (value - 0.1), d_force, stream)
+        e1.record(stream)
+        ng = 1 if w["kind"] == "selfCoordNum" else 2
+        launches += 2 * ng + cv.last_stats()[0] + ng  # gather+COM per group, calc, scatter
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else {}
+    step_ms = [a.elapsed_time(d) for a, _, _, d in ev]
+    kern_ms = [b.elapsed_time(c) for _, b, c, _ in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    kern_tot = torch.tensor([sum(kern_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_tot, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    kern_ms_avg = float(kern_tot.item()) / args.steps
+    # rebuild / list-walk split for pair-list workloads
+    split = None
+    if w["tol"] > 0:
+        reb = [m for s, m in enumerate(kern_ms) if (args.warmup + s) % w["freq"] == 0]
+        lst = [m for s, m in enumerate(kern_ms) if (args.warmup + s) % w["freq"] != 0]
+        split = {"rebuild_ms": float(np.mean(reb)) if reb else None,
+                 "list_ms": float(np.mean(lst)) if lst else None}
+
+    # ---- end-to-end through the host-buffer C-ABI step -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_pos = torch.tensor(proxy).pin_memory()
+        h_force = torch.zeros_like(h_pos).pin_memory()
+        hf = h_force.numpy()
+        for s in range(2):
+            v = cv.calc_host(h_pos, step=s)
+            cv.apply_force_host(k_force * (v - 0.1), h_force)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            v = cv.calc_host(h_pos, step=args.warmup + s)
+            cv.apply_force_host(k_force * (v - 0.1), h_force)
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        n_grad = 3 * (len(i1) + (len(i2) if i2 is not None else 0))
+        e2e = {"value": npairs * args.steps / float(t_e2e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(P * 24), "d2h_bytes_per_step": int(n_grad * 8 + 8),
+               "ms_per_step": 1e3 * float(t_e2e.item()) / args.steps,
+               "timing": "host wall clock around calc_host + apply_force_host (each call "
+                         "synchronises), max over ranks"}
+        assert hf is not None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pairs_per_s = npairs * args.steps / (total_ms * 1e-3)
+    kern_pairs_per_s = npairs / (kern_ms_avg * 1e-3)
+    achieved_tflops = kern_pairs_per_s * synth.FLOP_PER_PAIR_VALUE_GRAD / 1e12
+    peak = fp64_tflops * world
+    line = {
+        "metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": w["name"], "pairs_per_step": npairs, "proxy_atoms": int(P),
+                   "sharding": f"group1 blocks over {world} GPU(s), group2 replicated, "
+                               "ncclAllReduce of [value|grad1|grad2]" if world > 1 else "none",
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+                   "timing": "CUDA events on the launching stream per step, summed; max over "
+                             "ranks", "last_value": value},
+        "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved_tflops / peak, "traffic": None,
+                     "kernel": "sweep_kernel (+ exact/finalize) = calc_value",
+                     "kernel_ms": kern_ms_avg,
+                     "flop_per_pair": synth.FLOP_PER_PAIR_VALUE_GRAD,
+                     "peak_source": "DFMA microbenchmark run live in this process "
+                                    "(b200cv_fp64_peak, 250 ms sustained) x n_gpus; "
+                                    "MEASURED_PEAKS.json has no FP64 entry"},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "wall_s": t_wall,
+    }
+    if split:
+        line["pairlist"] = split
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_run(w, proxy, i1, i2, budget_s=12.0)
+        except Exception as e:
+            line["cpu_baseline"] = {"error": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

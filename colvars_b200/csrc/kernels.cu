@@ -1,0 +1,479 @@
+// kernels.cu -- kernels around the tile sweep: exact (reference-order) pair queue,
+// pair-list walk, dense fallback, centre-of-mass variants, finalize, atom-group
+// gather / COM / rotate / scatter, and the measurement helpers.
+#include "kernels.cuh"
+
+namespace b200cv {
+
+// ============================ block reduction helper =======================================
+
+template <int THREADS> __device__ __forceinline__ double block_sum(double v, double *red)
+{
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < THREADS / 32; w++) s += red[w];
+  }
+  __syncthreads();
+  return s;  // valid on thread 0
+}
+
+// ============================ exact pair queue / pair-list walk ================================
+
+__global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_constant__ ExactArgs A)
+{
+  __shared__ double red[EXACT_THREADS / 32];
+  unsigned long long n = A.count32 ? (unsigned long long)*A.count32 : *A.count64;
+  if (n > A.cap) n = A.cap;
+  bool const grad = A.flags & EF_GRADIENTS;
+  bool const rebuild = (A.flags & EF_REBUILD_PAIRLIST) && A.pl;
+  double fsum = 0.0;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * EXACT_THREADS + threadIdx.x; e < n;
+       e += (unsigned long long)gridDim.x * EXACT_THREADS) {
+    unsigned long long const ent = A.list[e];
+    int const i = (int)(ent >> 32), j = (int)(ent & 0xffffffffu);
+    double Gx, Gy, Gz;
+    double const F = pair_exact(A.P, A.x1[i], A.y1[i], A.z1[i], A.x2[j], A.y2[j], A.z2[j],
+                                A.flags, Gx, Gy, Gz);
+    fsum += F;
+    if (grad && F > 0.0) {
+      atomicAdd(&A.g1x[i], -Gx);
+      atomicAdd(&A.g1y[i], -Gy);
+      atomicAdd(&A.g1z[i], -Gz);
+      atomicAdd(&A.g2x[j], Gx);
+      atomicAdd(&A.g2y[j], Gy);
+      atomicAdd(&A.g2z[j], Gz);
+    }
+    if (rebuild && F > 0.0) {
+      unsigned long long const slot = atomicAdd(A.pl_count, 1ull);
+      if (slot < A.pl_cap) A.pl[slot] = ent;
+    }
+  }
+  double const s = block_sum<EXACT_THREADS>(fsum, red);
+  if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+}
+
+int launch_exact(const ExactArgs &args, cudaStream_t stream)
+{
+  exact_kernel<<<EXACT_BLOCKS, EXACT_THREADS, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+// ============================ dense fallback ==================================================
+
+__global__ void __launch_bounds__(EXACT_THREADS) dense_kernel(const __grid_constant__ DenseArgs A)
+{
+  __shared__ double red[EXACT_THREADS / 32];
+  bool const grad = A.flags & EF_GRADIENTS;
+  bool const rebuild = (A.flags & EF_REBUILD_PAIRLIST) && A.pl;
+  double fsum = 0.0;
+  unsigned long long const rows = (unsigned long long)(A.i_end - A.i_begin);
+  unsigned long long const total = rows * (unsigned long long)A.n2;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * EXACT_THREADS + threadIdx.x;
+       e < total; e += (unsigned long long)gridDim.x * EXACT_THREADS) {
+    int const i = A.i_begin + (int)(e / (unsigned long long)A.n2);
+    int const j = (int)(e % (unsigned long long)A.n2);
+    if (A.self && j <= i) continue;
+    double Gx, Gy, Gz;
+    double const F = pair_exact(A.P, A.x1[i], A.y1[i], A.z1[i], A.x2[j], A.y2[j], A.z2[j],
+                                A.flags, Gx, Gy, Gz);
+    fsum += F;
+    if (grad && F > 0.0) {
+      atomicAdd(&A.g1x[i], -Gx);
+      atomicAdd(&A.g1y[i], -Gy);
+      atomicAdd(&A.g1z[i], -Gz);
+      atomicAdd(&A.g2x[j], Gx);
+      atomicAdd(&A.g2y[j], Gy);
+      atomicAdd(&A.g2z[j], Gz);
+    }
+    if (rebuild && F > 0.0) {
+      unsigned long long const slot = atomicAdd(A.pl_count, 1ull);
+      if (slot < A.pl_cap) A.pl[slot] = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
+    }
+  }
+  double const s = block_sum<EXACT_THREADS>(fsum, red);
+  if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+}
+
+int launch_dense(const DenseArgs &args, cudaStream_t stream)
+{
+  dense_kernel<<<EXACT_BLOCKS, EXACT_THREADS, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+// ============================ centre-of-mass variants ===========================================
+
+__global__ void __launch_bounds__(EXACT_THREADS) center_kernel(const __grid_constant__ CenterArgs A)
+{
+  __shared__ double red[EXACT_THREADS / 32];
+  bool const grad = A.flags & EF_GRADIENTS;
+  bool const use_pl = A.flags & EF_USE_PAIRLIST;
+  bool const rebuild = A.flags & EF_REBUILD_PAIRLIST;
+  double const cx = A.center[0], cy = A.center[1], cz = A.center[2];
+  double fsum = 0.0, sgx = 0.0, sgy = 0.0, sgz = 0.0;
+  if (A.n == 0) {
+    // both sides are centres: one pair (groupCoord)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      double Gx, Gy, Gz;
+      double const F = pair_exact(A.P, cx, cy, cz, A.center2[0], A.center2[1], A.center2[2],
+                                  A.flags, Gx, Gy, Gz);
+      fsum = F;
+      if (grad && F > 0.0) {
+        A.center_grad[0] += -Gx;
+        A.center_grad[1] += -Gy;
+        A.center_grad[2] += -Gz;
+        A.center2_grad[0] += Gx;
+        A.center2_grad[1] += Gy;
+        A.center2_grad[2] += Gz;
+      }
+    }
+  } else {
+    for (int a = blockIdx.x * EXACT_THREADS + threadIdx.x; a < A.n;
+         a += gridDim.x * EXACT_THREADS) {
+      bool const within = !use_pl || rebuild || A.pairlist[a];
+      double F = 0.0, Gx = 0.0, Gy = 0.0, Gz = 0.0;
+      if (within) {
+        if (A.center_is_group1) {
+          F = pair_exact(A.P, cx, cy, cz, A.x[a], A.y[a], A.z[a], A.flags, Gx, Gy, Gz);
+        } else {
+          F = pair_exact(A.P, A.x[a], A.y[a], A.z[a], cx, cy, cz, A.flags, Gx, Gy, Gz);
+        }
+      }
+      if (use_pl && rebuild) A.pairlist[a] = F > 0.0 ? 1 : 0;
+      fsum += F;
+      if (grad && F > 0.0) {
+        // G is the gradient w.r.t. the second position of the pair
+        double const s = A.center_is_group1 ? 1.0 : -1.0;
+        atomicAdd(&A.gx[a], s * Gx);
+        atomicAdd(&A.gy[a], s * Gy);
+        atomicAdd(&A.gz[a], s * Gz);
+        sgx -= s * Gx;
+        sgy -= s * Gy;
+        sgz -= s * Gz;
+      }
+    }
+  }
+  double const s = block_sum<EXACT_THREADS>(fsum, red);
+  if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+  if (A.n != 0 && grad) {
+    double const tx = block_sum<EXACT_THREADS>(sgx, red);
+    double const ty = block_sum<EXACT_THREADS>(sgy, red);
+    double const tz = block_sum<EXACT_THREADS>(sgz, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(&A.center_grad[0], tx);
+      atomicAdd(&A.center_grad[1], ty);
+      atomicAdd(&A.center_grad[2], tz);
+    }
+  }
+}
+
+int launch_center(const CenterArgs &args, cudaStream_t stream)
+{
+  int blocks = args.n == 0 ? 1 : (args.n + EXACT_THREADS - 1) / EXACT_THREADS;
+  if (blocks > EXACT_BLOCKS) blocks = EXACT_BLOCKS;
+  center_kernel<<<blocks, EXACT_THREADS, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+// ============================ finalize ===========================================================
+
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs A)
+{
+  __shared__ double red[256];
+  // fixed summation order: thread t takes partials t, t+256, ...; then a binary tree
+  double s = 0.0;
+  for (int k = threadIdx.x; k < A.n; k += 256) s += A.partials[k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *A.d_value = red[0];
+    if (A.h_counters) {
+      A.h_counters[0] = A.rare_count ? (unsigned long long)*A.rare_count : 0ull;
+      A.h_counters[1] = A.pl_count ? *A.pl_count : 0ull;
+    }
+    if (A.h_value) {
+      __threadfence_system();
+      *A.h_value = red[0];
+    }
+  }
+}
+
+int launch_finalize(const FinalizeArgs &args, cudaStream_t stream)
+{
+  finalize_kernel<<<1, 256, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+// ============================ atom-group kernels ================================================
+
+__global__ void gather_kernel(const double *__restrict__ proxy, size_t pstride, int aos,
+                              const int *__restrict__ idx, int n, double *__restrict__ pos,
+                              size_t stride)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t const p = (size_t)idx[i];
+  if (aos) {
+    pos[i] = proxy[3 * p];
+    pos[stride + i] = proxy[3 * p + 1];
+    pos[2 * stride + i] = proxy[3 * p + 2];
+  } else {
+    pos[i] = proxy[p];
+    pos[stride + i] = proxy[pstride + p];
+    pos[2 * stride + i] = proxy[2 * pstride + p];
+  }
+}
+
+int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, int n,
+                  double *pos, size_t stride, cudaStream_t stream)
+{
+  if (n <= 0) return 0;
+  gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(proxy, pstride, aos, idx, n, pos, stride);
+  return (int)cudaGetLastError();
+}
+
+// calc_center_of_mass / calc_center_of_geometry (src/colvaratoms.cpp:1354-1395).  One CTA,
+// fixed order: thread t sums atoms t, t+1024, ...; binary tree across threads.
+__global__ void __launch_bounds__(1024) com_cog_kernel(const double *__restrict__ pos,
+                                                       size_t stride,
+                                                       const double *__restrict__ mass,
+                                                       double total_mass, int n, double *com,
+                                                       double *cog)
+{
+  __shared__ double red[6][1024 / 32];
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    double const m = mass[i];
+    double const x = pos[i], y = pos[stride + i], z = pos[2 * stride + i];
+    s[0] = fma(m, x, s[0]);
+    s[1] = fma(m, y, s[1]);
+    s[2] = fma(m, z, s[2]);
+    s[3] += x;
+    s[4] += y;
+    s[5] += z;
+  }
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], d);
+    if (lane == 0) red[c][warp] = s[c];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double v = red[c][lane];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) {
+        if (c < 3) com[c] = v / total_mass;
+        else cog[c - 3] = v / (double)n;
+      }
+    }
+  }
+}
+
+int launch_com_cog(const double *pos, size_t stride, const double *mass, double total_mass,
+                   int n, double *com, double *cog, cudaStream_t stream)
+{
+  com_cog_kernel<<<1, 1024, 0, stream>>>(pos, stride, mass, total_mass, n, com, cog);
+  return (int)cudaGetLastError();
+}
+
+__global__ void translate_kernel(double *pos, size_t stride, int n, const double *t, double s)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos[i] += s * t[0];
+  pos[stride + i] += s * t[1];
+  pos[2 * stride + i] += s * t[2];
+}
+
+int launch_translate(double *pos, size_t stride, int n, const double *t_dev, double s,
+                     cudaStream_t stream)
+{
+  if (n <= 0) return 0;
+  translate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pos, stride, n, t_dev, s);
+  return (int)cudaGetLastError();
+}
+
+// cvm::quaternion::rotation_matrix (src/colvartypes.h)
+__device__ __forceinline__ void quat_to_matrix(const double *q, double R[3][3])
+{
+  double const q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+  R[0][0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3;
+  R[1][1] = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3;
+  R[2][2] = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+  R[0][1] = 2.0 * (q1 * q2 - q0 * q3);
+  R[0][2] = 2.0 * (q0 * q2 + q1 * q3);
+  R[1][0] = 2.0 * (q0 * q3 + q1 * q2);
+  R[1][2] = 2.0 * (q2 * q3 - q0 * q1);
+  R[2][0] = 2.0 * (q1 * q3 - q0 * q2);
+  R[2][1] = 2.0 * (q0 * q1 + q2 * q3);
+}
+
+__global__ void rotate_kernel(double *pos, size_t stride, int n, const double *q)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double R[3][3];
+  quat_to_matrix(q, R);
+  double const x = pos[i], y = pos[stride + i], z = pos[2 * stride + i];
+  pos[i] = R[0][0] * x + R[0][1] * y + R[0][2] * z;
+  pos[stride + i] = R[1][0] * x + R[1][1] * y + R[1][2] * z;
+  pos[2 * stride + i] = R[2][0] * x + R[2][1] * y + R[2][2] * z;
+}
+
+int launch_rotate(double *pos, size_t stride, int n, const double *q_dev, cudaStream_t stream)
+{
+  if (n <= 0) return 0;
+  rotate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pos, stride, n, q_dev);
+  return (int)cudaGetLastError();
+}
+
+__global__ void weighted_gradient_kernel(const double *__restrict__ w, const double *g, int n,
+                                         double *grad, size_t stride)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  grad[i] = w[i] * g[0];
+  grad[stride + i] = w[i] * g[1];
+  grad[2 * stride + i] = w[i] * g[2];
+}
+
+int launch_weighted_gradient(const double *w, const double *g_dev, int n, double *grad,
+                             size_t stride, cudaStream_t stream)
+{
+  if (n <= 0) return 0;
+  weighted_gradient_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, g_dev, n, grad, stride);
+  return (int)cudaGetLastError();
+}
+
+// atom_group::apply_colvar_force (src/colvaratoms.cpp:1637-1689): atomics because several
+// groups / components may push on the same proxy atom.
+__global__ void scatter_force_kernel(const double *__restrict__ grad, size_t stride,
+                                     const int *__restrict__ idx, int n, double f,
+                                     const double *q, double *proxy_force, size_t pstride,
+                                     int aos)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double gx = grad[i], gy = grad[stride + i], gz = grad[2 * stride + i];
+  if (q) {
+    // rot.inverse().matrix() = transpose of R(q)
+    double R[3][3];
+    quat_to_matrix(q, R);
+    double const tx = R[0][0] * gx + R[1][0] * gy + R[2][0] * gz;
+    double const ty = R[0][1] * gx + R[1][1] * gy + R[2][1] * gz;
+    double const tz = R[0][2] * gx + R[1][2] * gy + R[2][2] * gz;
+    gx = tx;
+    gy = ty;
+    gz = tz;
+  }
+  size_t const p = (size_t)idx[i];
+  if (aos) {
+    atomicAdd(&proxy_force[3 * p], f * gx);
+    atomicAdd(&proxy_force[3 * p + 1], f * gy);
+    atomicAdd(&proxy_force[3 * p + 2], f * gz);
+  } else {
+    atomicAdd(&proxy_force[p], f * gx);
+    atomicAdd(&proxy_force[pstride + p], f * gy);
+    atomicAdd(&proxy_force[2 * pstride + p], f * gz);
+  }
+}
+
+int launch_scatter_force(const double *grad, size_t stride, const int *idx, int n, double f,
+                         const double *q_dev, double *proxy_force, size_t pstride, int aos,
+                         cudaStream_t stream)
+{
+  if (n <= 0) return 0;
+  scatter_force_kernel<<<(n + 255) / 256, 256, 0, stream>>>(grad, stride, idx, n, f, q_dev,
+                                                            proxy_force, pstride, aos);
+  return (int)cudaGetLastError();
+}
+
+__global__ void repack_kernel(const double *__restrict__ src, size_t sstride, double *dst,
+                              size_t dstride, int n, int accumulate)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double const v = src[d * sstride + i];
+    if (accumulate) dst[d * dstride + i] += v;
+    else dst[d * dstride + i] = v;
+  }
+}
+
+int launch_repack(const double *src, size_t sstride, double *dst, size_t dstride, int n,
+                  int accumulate, cudaStream_t stream)
+{
+  if (n <= 0) return 0;
+  repack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, sstride, dst, dstride, n, accumulate);
+  return (int)cudaGetLastError();
+}
+
+// ============================ measurement helpers =================================================
+
+// FP64 roofline denominator: 16 independent DFMA chains per thread, 256 DFMA per loop trip.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
+{
+  double a[16];
+  double const b = 1.0000001, c = 1e-9;
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = (double)(threadIdx.x + k) * 1e-3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 16; rep++) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) a[k] = fma(a[k], b, c);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s += a[k];
+  if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+int launch_fp64_peak(double *d_out, int iters, int blocks, cudaStream_t stream)
+{
+  fp64_peak_kernel<<<blocks, 256, 0, stream>>>(d_out, iters);
+  return (int)cudaGetLastError();
+}
+
+__global__ void rcp_selftest_kernel(const double *x, int n, double *maxulp)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  double err = 0.0;
+  if (i < n) {
+    double const q = x[i];
+    double const y = fast_rcp(q);
+    double const yref = __ddiv_rn(1.0, q);
+    // distance in units of the last place of the correctly rounded result
+    long long const a = __double_as_longlong(y), b = __double_as_longlong(yref);
+    err = (double)(a > b ? a - b : b - a);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, d));
+  if ((threadIdx.x & 31) == 0) {
+    // non-negative doubles order like their bit patterns
+    atomicMax((unsigned long long *)maxulp, (unsigned long long)__double_as_longlong(err));
+  }
+}
+
+int launch_rcp_selftest(const double *d_x, int n, double *d_maxulp, cudaStream_t stream)
+{
+  rcp_selftest_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_x, n, d_maxulp);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b200cv

@@ -1,0 +1,118 @@
+// kernels.cuh -- launch interface between the C-ABI layer (api.cu) and the kernels.
+#pragma once
+#include "sweep.cuh"
+
+namespace b200cv {
+
+// sweep geometry (compile-time): R register atoms per lane, W warps per CTA
+constexpr int SWEEP_R = 8;
+constexpr int SWEEP_W = 4;
+constexpr int SWEEP_IB = SWEEP_W * 32 * SWEEP_R;  // group1 atoms per work item (1024)
+
+// Launch the tile sweep over `nitems` work items.  exp_special = n' when ed == 2*en and a
+// specialised instantiation exists (currently n' = 3, i.e. 6/12), else 0 (runtime exponents).
+// pbc: BC_NONE or BC_ORTHO.  Returns a cudaError_t.
+int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso, int pbc,
+                 bool pairlist, cudaStream_t stream);
+bool sweep_has_special(int en, int ed);
+
+// Pairs queued by the sweep (or every listed pair on non-rebuild steps, or every pair for
+// the general-PBC fallback) evaluated in the reference's operation order.
+struct ExactArgs {
+  const double *x1, *y1, *z1;
+  const double *x2, *y2, *z2;
+  double *g1x, *g1y, *g1z;
+  double *g2x, *g2y, *g2z;
+  const unsigned long long *list;      // packed (i << 32 | j)
+  const unsigned int *count32;         // number of entries (device), or NULL
+  const unsigned long long *count64;   // ... 64-bit variant (pair list), or NULL
+  unsigned long long cap;              // entries beyond cap were never written
+  double *partials;                    // [EXACT_BLOCKS]
+  unsigned long long *pl;              // pair list to append to on rebuild (or NULL)
+  unsigned long long pl_cap;
+  unsigned long long *pl_count;
+  int flags;                           // EF_*
+  PairParams P;
+};
+constexpr int EXACT_BLOCKS = 296;
+constexpr int EXACT_THREADS = 128;
+int launch_exact(const ExactArgs &args, cudaStream_t stream);
+
+// Dense fallback for boundary conditions the tile sweep does not specialise (mixed /
+// triclinic): every pair through pair_exact, gradients by atomics.  self: i < j only.
+struct DenseArgs {
+  const double *x1, *y1, *z1;
+  const double *x2, *y2, *z2;
+  double *g1x, *g1y, *g1z;
+  double *g2x, *g2y, *g2z;
+  int n1, n2, self;
+  int i_begin, i_end;  // rows of this shard
+  double *partials;    // [EXACT_BLOCKS]
+  unsigned long long *pl;
+  unsigned long long pl_cap;
+  unsigned long long *pl_count;
+  int flags;
+  PairParams P;
+};
+int launch_dense(const DenseArgs &args, cudaStream_t stream);
+
+// One pseudo-atom (a centre of mass held in device memory) against a group of n atoms:
+// coordNum with group{1,2}CenterOnly and groupCoord (src/colvarcomp_coordnums.cpp:190-247).
+struct CenterArgs {
+  const double *center;     // device double[3]: the COM pseudo-atom
+  const double *x, *y, *z;  // the other side: n atoms (or another centre when n == 0)
+  const double *center2;    // used when both sides are centres
+  double *gx, *gy, *gz;     // gradients of the n atoms (accumulated)
+  double *center_grad;      // device double[3] += gradient of `center`
+  double *center2_grad;     // when both are centres
+  int n;
+  int center_is_group1;     // diff = p2 - p1: which side the centre is on
+  unsigned char *pairlist;  // dense bool per pair (n entries) or NULL
+  double *partials;         // [EXACT_BLOCKS]
+  int flags;
+  PairParams P;
+};
+int launch_center(const CenterArgs &args, cudaStream_t stream);
+
+// value = sum(partials[0..n)) in a fixed order -> device scalar + mapped pinned host copy;
+// also publishes the queue counters to the host.
+struct FinalizeArgs {
+  const double *partials;
+  int n;
+  double *d_value;
+  double *h_value;  // mapped pinned
+  const unsigned int *rare_count;
+  const unsigned long long *pl_count;
+  unsigned long long *h_counters;  // mapped pinned [2]: rare_count, pl_count
+};
+int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
+
+// ---- atom-group kernels (src/colvaratoms.cpp, src/cuda/colvaratoms_kernel.cu) -----------
+// gather: pos[d*stride + i] = proxy[d*pstride + idx[i]]  (aos != 0: proxy[3*idx[i] + d])
+int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, int n,
+                  double *pos, size_t stride, cudaStream_t stream);
+// COM = sum m x / M and COG = sum x / n in one pass (single CTA, fixed order)
+int launch_com_cog(const double *pos, size_t stride, const double *mass, double total_mass,
+                   int n, double *com, double *cog, cudaStream_t stream);
+// pos += s * t (t in device memory, plus optional constant shift c)
+int launch_translate(double *pos, size_t stride, int n, const double *t_dev, double s,
+                     cudaStream_t stream);
+// pos = R pos, R = rotation matrix of device quaternion q (inverse != 0: R^T)
+int launch_rotate(double *pos, size_t stride, int n, const double *q_dev, cudaStream_t stream);
+// grad[i] = w[i] * g (assignment; set_weighted_gradient)
+int launch_weighted_gradient(const double *w, const double *g_dev, int n, double *grad,
+                             size_t stride, cudaStream_t stream);
+// F_proxy[idx[i]] += f * (Rinv grad_i); q_dev == NULL: no rotation
+int launch_scatter_force(const double *grad, size_t stride, const int *idx, int n, double f,
+                         const double *q_dev, double *proxy_force, size_t pstride, int aos,
+                         cudaStream_t stream);
+// copy n atoms between SoA layouts with different strides (dst += src when accumulate)
+int launch_repack(const double *src, size_t sstride, double *dst, size_t dstride, int n,
+                  int accumulate, cudaStream_t stream);
+
+// ---- fitting kernels (src/colvartypes.cpp:231-489, src/colvar_rotation_derivative.h) ----
+struct FitBuffers;  // defined in fit.cuh
+int launch_fp64_peak(double *d_out, int iters, int blocks, cudaStream_t stream);
+int launch_rcp_selftest(const double *d_x, int n, double *d_maxulp, cudaStream_t stream);
+
+}  // namespace b200cv

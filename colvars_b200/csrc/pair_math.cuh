@@ -1,0 +1,302 @@
+// pair_math.cuh -- per-pair arithmetic of the coordination-number switching function.
+//
+// Two evaluators:
+//
+//  * pair_fast<>: the hot path.  FMA-contracted, one reciprocal per pair, integer
+//    exponents by repeated multiplication, constants folded out of the loop.  It
+//    returns (F, gq) with the pair gradient G_d = C_d * gq * diff_d; the per-axis
+//    constants C_d are applied once per atom when accumulators are flushed.
+//    It also returns `rare`: the pair lies so close to a decision threshold
+//    (l2 ~ 1 where the reference switches to its Taylor branch and the quotient
+//    form loses digits; or, with a pair list, l2 ~ l2_max or f0 ~ tolerance) that
+//    only arithmetic in the reference's own operation order reproduces the
+//    reference.  Rare pairs contribute nothing here; they are queued and
+//    evaluated by pair_exact.
+//
+//  * pair_exact: restates colvar::coordnum::compute_pair_coordnum
+//    (src/colvarcomp_coordnums.h:227-281) and switching_function (:168-224) in the
+//    reference's operation order with round-to-nearest intrinsics (no FMA
+//    contraction), so its l2, F and pair-list decision are bit-identical to the
+//    reference CPU path for bit-identical inputs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200cv {
+
+enum : int { EF_GRADIENTS = 1, EF_USE_PAIRLIST = 1 << 9, EF_REBUILD_PAIRLIST = 1 << 10 };
+enum : int { BC_NONE = 0, BC_ORTHO = 1, BC_GENERAL = 2 };
+
+// Everything the pair functions need; lives in kernel parameter (constant) space.
+struct PairParams {
+  double inv_r0[3];
+  double inv_r0sq[3];
+  double c_grad[3];  // C_d of the fast path (see pair_fast)
+  double tol;        // pairlist tolerance (0 without pair list)
+  double inv1mt;     // 1 / (1 - tol)
+  double ntol;       // -tol * inv1mt
+  double l2_max;     // tolerance_l2_max (1e20 without pair list)
+  int en2, ed2;      // en/2, ed/2
+  int l2max_hi;      // high word of l2_max
+  int tol_hi;        // high word of tol
+  // boundary conditions (src/colvars_system.h)
+  int bc_type;       // reference enum: 0 non-periodic, 1 mixed, 2 orthogonal, 3 triclinic
+  int periodic[3];
+  double cell[3][3];   // unit_cell_x/y/z
+  double recip[3][3];  // reciprocal_cell_x/y/z
+};
+
+// ---- reciprocal --------------------------------------------------------------------
+// MUFU.RCP64H seed (>= 20 good bits, PTX rcp.approx.ftz.f64) + one cubic
+// (Halley-type) step: e = 1 - q*y0; y = y0 + y0*(e + e*e).  3 DFMA, error ~0.5 ulp
+// + e^3 (2^-60).  q is always in [1, 1e300] here, so no special-case handling.
+__device__ __forceinline__ double rcp_seed(double q)
+{
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+  return y;
+}
+
+__device__ __forceinline__ double fast_rcp(double q)
+{
+  double const y0 = rcp_seed(q);
+  double const e = fma(-q, y0, 1.0);
+#if defined(B200CV_RCP_NEWTON2)
+  double const y1 = fma(y0, e, y0);
+  double const e1 = fma(-q, y1, 1.0);
+  return fma(y1, e1, y1);
+#else
+  double const t = fma(e, e, e);
+  return fma(y0, t, y0);
+#endif
+}
+
+// x^n for a compile-time n by the shortest multiplication chain the compiler finds
+template <int N> __device__ __forceinline__ double ipow(double x)
+{
+  if constexpr (N == 0) return 1.0;
+  else if constexpr (N == 1) return x;
+  else if constexpr (N % 2 == 0) { double const h = ipow<N / 2>(x); return h * h; }
+  else return x * ipow<N - 1>(x);
+}
+
+// runtime integer power, same square-and-multiply order as cvm::integer_power
+// (src/colvarmodule.h:105-116) but contracted; used by the runtime-exponent fast path
+__device__ __forceinline__ double ipow_rt(double x, int n)
+{
+  double yy = 1.0, ww = x;
+  for (int nn = n; nn != 0; nn >>= 1, ww *= ww) {
+    if (nn & 1) yy *= ww;
+  }
+  return yy;
+}
+
+// reciprocal for the general quotient form: the argument b^2*l2 is positive but can be
+// tiny (l2 -> 0) or huge; fall back to IEEE division outside the seed's comfortable range.
+__device__ __forceinline__ double fast_rcp_wide(double x)
+{
+  if (x > 1e-290 && x < 1e290) return fast_rcp(x);
+  return 1.0 / x;
+}
+
+// "|l2 - 1| < 2^-10" on the high word only (integer pipe, not the FP64 pipe)
+__device__ __forceinline__ bool near_one(double u)
+{
+  return (unsigned)(__double2hiint(u) - 0x3FEFF800) < 0xC00u;
+}
+
+// high words within +-1 of each other (relative distance < ~2e-6); both positive
+__device__ __forceinline__ bool hi_near(double a, int b_hi)
+{
+  return (unsigned)(__double2hiint(a) - b_hi + 1) <= 2u;
+}
+
+// EXP = 0: runtime exponents (en2, ed2 from params), general quotient form.
+// EXP = n' > 0: compile-time en/2 = n' with ed = 2*en, for which
+//   (1 - x^n') / (1 - x^2n') = 1 / (1 + x^n'),  dF/dl2 = -n' x^(n'-1) / (1 + x^n')^2
+// (no singularity at l2 = 1, one FMA chain, one reciprocal).
+//
+// Output convention: G_d = c_grad[d] * gq * diff_d, F >= 0.
+//   EXP > 0 : gq = u^(n'-1) r^2,          c_grad[d] = -2 n' inv1mt inv_r0sq[d]
+//   EXP = 0 : gq = dF/dl2 (incl. inv1mt), c_grad[d] = 2 inv_r0sq[d]
+template <int EXP, bool PL>
+__device__ __forceinline__ void switching_fast(double u, PairParams const &P, double &F,
+                                               double &gq, bool &rare)
+{
+  rare = near_one(u);
+  double f0;
+  if constexpr (EXP > 0) {
+    double const um1 = ipow<EXP - 1>(u);
+    double const q = fma(um1, u, 1.0);
+    double const r = fast_rcp(q);
+    f0 = r;
+    gq = um1 * (r * r);
+  } else {
+    double const xn = ipow_rt(u, P.en2);
+    double const xd = ipow_rt(u, P.ed2);
+    double const a = 1.0 - xn;
+    double const b = 1.0 - xd;
+    // one reciprocal: rinv = 1 / (b^2 l2);  F = a b l2 rinv,
+    // dF/dl2 = (m' xd a - n' xn b) rinv
+    double const bl = b * u;
+    double const rinv = fast_rcp_wide(b * bl);
+    double const en2_r = (double)P.en2, ed2_r = (double)P.ed2;
+    f0 = (a * bl) * rinv;
+    gq = (ed2_r * (xd * a) - en2_r * (xn * b)) * rinv;
+    if (u < 1e-280) {  // coincident atoms: F -> 1, dF/dl2 -> 0 (the reference yields NaN here)
+      f0 = 1.0;
+      gq = 0.0;
+    }
+  }
+  if constexpr (PL) {
+    rare = rare || hi_near(u, P.l2max_hi) || hi_near(f0, P.tol_hi);
+    F = fma(f0, P.inv1mt, P.ntol);
+    bool const out = (u > P.l2_max) || (F < 0.0);
+    if constexpr (EXP == 0) gq *= P.inv1mt;
+    if (out) { F = 0.0; gq = 0.0; }
+  } else {
+    F = f0;
+  }
+}
+
+// ---- exact (reference-order) path -------------------------------------------------------
+
+// cvm::integer_power (src/colvarmodule.h:105-116), no contraction
+__device__ __forceinline__ double integer_power_exact(double x, int n)
+{
+  if (x == 0.0) return 0.0;
+  double yy = 1.0, ww = x;
+  for (int nn = n; nn != 0; nn >>= 1, ww = __dmul_rn(ww, ww)) {
+    if (nn & 1) yy = __dmul_rn(yy, ww);
+  }
+  return yy;
+}
+
+__device__ __forceinline__ double dot3_exact(const double a[3], double bx, double by, double bz)
+{
+  return __dadd_rn(__dadd_rn(__dmul_rn(a[0], bx), __dmul_rn(a[1], by)), __dmul_rn(a[2], bz));
+}
+
+// system_boundary_conditions::position_distance (src/colvars_system.h:161-219)
+__device__ inline void position_distance_exact(PairParams const &P, double x1, double y1,
+                                               double z1, double x2, double y2, double z2,
+                                               double &dx, double &dy, double &dz)
+{
+  dx = __dsub_rn(x2, x1);
+  dy = __dsub_rn(y2, y1);
+  dz = __dsub_rn(z2, z1);
+  if (P.bc_type == 0 || P.bc_type == 4) return;
+  double const xs = floor(__dadd_rn(dot3_exact(P.recip[0], dx, dy, dz), 0.5));
+  double const ys = floor(__dadd_rn(dot3_exact(P.recip[1], dx, dy, dz), 0.5));
+  double const zs = floor(__dadd_rn(dot3_exact(P.recip[2], dx, dy, dz), 0.5));
+  dx = __dsub_rn(dx, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][0]), __dmul_rn(ys, P.cell[1][0])),
+                               __dmul_rn(zs, P.cell[2][0])));
+  dy = __dsub_rn(dy, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][1]), __dmul_rn(ys, P.cell[1][1])),
+                               __dmul_rn(zs, P.cell[2][1])));
+  dz = __dsub_rn(dz, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][2]), __dmul_rn(ys, P.cell[1][2])),
+                               __dmul_rn(zs, P.cell[2][2])));
+  if (P.bc_type != 2) {
+    // get_triclinic_shift: search the neighbouring images for a shorter vector
+    double min_d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    int const nx = P.periodic[0] ? 1 : 0, ny = P.periodic[1] ? 1 : 0, nz = P.periodic[2] ? 1 : 0;
+    for (int ix = -nx; ix <= nx; ix++) {
+      for (int iy = -ny; iy <= ny; iy++) {
+        for (int iz = -nz; iz <= nz; iz++) {
+          double const sx = __dadd_rn(__dadd_rn(__dmul_rn((double)ix, P.cell[0][0]),
+                                                __dmul_rn((double)iy, P.cell[1][0])),
+                                      __dmul_rn((double)iz, P.cell[2][0]));
+          double const sy = __dadd_rn(__dadd_rn(__dmul_rn((double)ix, P.cell[0][1]),
+                                                __dmul_rn((double)iy, P.cell[1][1])),
+                                      __dmul_rn((double)iz, P.cell[2][1]));
+          double const sz = __dadd_rn(__dadd_rn(__dmul_rn((double)ix, P.cell[0][2]),
+                                                __dmul_rn((double)iy, P.cell[1][2])),
+                                      __dmul_rn((double)iz, P.cell[2][2]));
+          double const tx = __dadd_rn(dx, sx), ty = __dadd_rn(dy, sy), tz = __dadd_rn(dz, sz);
+          double const d2 =
+              __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+          if (d2 < min_d2) { rx = sx; ry = sy; rz = sz; min_d2 = d2; }
+        }
+      }
+    }
+    dx = __dadd_rn(dx, rx);
+    dy = __dadd_rn(dy, ry);
+    dz = __dadd_rn(dz, rz);
+  }
+}
+
+// switching_function<flags> (src/colvarcomp_coordnums.h:168-224)
+__device__ inline double switching_exact(double l2, double &dFdl2, PairParams const &P,
+                                         int flags)
+{
+  double const xn = integer_power_exact(l2, P.en2);
+  double const xd = integer_power_exact(l2, P.ed2);
+  double const eps_l2 = 1.0e-7;
+  double const h = __dsub_rn(l2, 1.0);
+  double const en2_r = (double)P.en2, ed2_r = (double)P.ed2;
+  bool const taylor = fabs(h) < eps_l2;
+  double f0;
+  if (taylor) {
+    double const c0 = __ddiv_rn(en2_r, ed2_r);
+    double const c1 = __ddiv_rn(__dmul_rn(en2_r, __dsub_rn(en2_r, ed2_r)), __dmul_rn(2.0, ed2_r));
+    double const c2 =
+        __ddiv_rn(__dmul_rn(__dmul_rn(en2_r, __dsub_rn(en2_r, ed2_r)),
+                            __dsub_rn(__dsub_rn(__dmul_rn(2.0, en2_r), ed2_r), 3.0)),
+                  __dmul_rn(12.0, ed2_r));
+    f0 = __dadd_rn(c0, __dmul_rn(h, __dadd_rn(c1, __dmul_rn(h, c2))));
+  } else {
+    f0 = __ddiv_rn(__dsub_rn(1.0, xn), __dsub_rn(1.0, xd));
+  }
+  double func, inv1mt = 0.0;
+  if (flags & EF_USE_PAIRLIST) {
+    inv1mt = __ddiv_rn(1.0, __dsub_rn(1.0, P.tol));
+    func = __dmul_rn(__dsub_rn(f0, P.tol), inv1mt);
+  } else {
+    func = f0;
+  }
+  if (func < 0) return 0.0;
+  if (flags & EF_GRADIENTS) {
+    double log_deriv;
+    if (taylor) {
+      double const g0 = __dmul_rn(0.5, __dsub_rn(en2_r, ed2_r));
+      double const g1 = __ddiv_rn(
+          __dmul_rn(__dsub_rn(en2_r, ed2_r), __dsub_rn(__dadd_rn(en2_r, ed2_r), 6.0)), 12.0);
+      log_deriv = __dadd_rn(g0, __dmul_rn(h, g1));
+    } else {
+      double const t1 = __ddiv_rn(__dmul_rn(ed2_r, xd), __dmul_rn(__dsub_rn(1.0, xd), l2));
+      double const t2 = __ddiv_rn(__dmul_rn(en2_r, xn), __dmul_rn(__dsub_rn(1.0, xn), l2));
+      log_deriv = __dsub_rn(t1, t2);
+    }
+    dFdl2 = (flags & EF_USE_PAIRLIST) ? __dmul_rn(__dmul_rn(f0, inv1mt), log_deriv)
+                                      : __dmul_rn(func, log_deriv);
+  }
+  return func;
+}
+
+// compute_pair_coordnum<flags> (src/colvarcomp_coordnums.h:227-281); returns F and the
+// gradient vector G (group1 gets -G, group2 +G); G = 0 when F == 0 or gradients are off
+__device__ inline double pair_exact(PairParams const &P, double x1, double y1, double z1,
+                                    double x2, double y2, double z2, int flags, double &Gx,
+                                    double &Gy, double &Gz)
+{
+  double dx, dy, dz;
+  position_distance_exact(P, x1, y1, z1, x2, y2, z2, dx, dy, dz);
+  double const sx = __dmul_rn(dx, P.inv_r0[0]);
+  double const sy = __dmul_rn(dy, P.inv_r0[1]);
+  double const sz = __dmul_rn(dz, P.inv_r0[2]);
+  double const l2 = __dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz));
+  Gx = Gy = Gz = 0.0;
+  if (flags & EF_USE_PAIRLIST) {
+    if (l2 > P.l2_max) return 0.0;
+  }
+  double dFdl2 = 0.0;
+  double const F = switching_exact(l2, dFdl2, P, flags);
+  if ((flags & EF_GRADIENTS) && (F > 0.0)) {
+    Gx = __dmul_rn(dFdl2, __dmul_rn(__dmul_rn(2.0, P.inv_r0sq[0]), dx));
+    Gy = __dmul_rn(dFdl2, __dmul_rn(__dmul_rn(2.0, P.inv_r0sq[1]), dy));
+    Gz = __dmul_rn(dFdl2, __dmul_rn(__dmul_rn(2.0, P.inv_r0sq[2]), dz));
+  }
+  return F;
+}
+
+}  // namespace b200cv

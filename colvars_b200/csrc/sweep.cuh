@@ -1,0 +1,340 @@
+// sweep.cuh -- the all-pairs tile kernel of coordNum / selfCoordNum (sm_100a).
+//
+// Replaces the O(N1*N2) double loop colvar::coordnum::main_loop
+// (src/colvarcomp_coordnums.cpp:187-248) and selfcoordnum_sequential_loop (:478-523).
+//
+// Decomposition
+//   work item   = (block of IB = W*32*R group1 atoms) x (chunk of <= JCMAX group2 atoms);
+//                 one CTA of W warps per item, items listed in a device table so that
+//                 the same kernel serves coordNum, the upper triangle of selfCoordNum and
+//                 any multi-GPU shard of rows.
+//   group1 side : each lane keeps R atoms (coordinates + 3 gradient accumulators) in
+//                 registers for the whole item.
+//   group2 side : the chunk's SoA coordinates are staged into shared memory once per CTA
+//                 with three TMA bulk copies (cp.async.bulk, mbarrier complete_tx).
+//   tile        : 32 group2 atoms.  At step t lane l works on atom (l+t)%32 of the tile,
+//                 read conflict-free from shared memory; its 3 group2 gradient
+//                 accumulators travel with the atom by one SHFL rotation per step, so
+//                 after 32 steps lane l owns the complete warp-level sum for atom l with
+//                 no FP64 work spent on reductions.
+//   group2 grads: warps walk the chunk's tiles in a staggered order and add their
+//                 per-tile sums into block-private shared-memory accumulators; one
+//                 RED.ADD.F64 per (CTA, atom, axis) goes to global memory at the end.
+//   value       : per-lane sum -> warp shuffle tree -> one partial per CTA (summed in a
+//                 fixed order by finalize_kernel: no atomics on the scalar).
+//   pair list   : on rebuild sweeps each lane records one 32-bit mask per register atom
+//                 and tile; masks are compacted into a global (i,j) list by a warp
+//                 prefix sum and one atomicAdd per warp and tile (stream compaction).
+//   rare pairs  : pairs within 2^-10 of l2 = 1 (or next to a pair-list threshold) are
+//                 appended to a queue and evaluated in the reference's operation order by
+//                 exact_kernel; they contribute nothing here.
+//
+// FP64-pipe cost of the specialised n=6/m=12 isotropic pair: 3 (diff) + 3 (d2) + 1 (l2)
+// + 2 (l2^2, 1+l2^3) + 3 (reciprocal refinement) + 2 (r^2, gq) + 1 (F sum) + 6 (two
+// gradient FMAs per axis) = 21 DFMA-class instructions, vs 39 algorithmic flops.
+#pragma once
+#include "pair_math.cuh"
+
+namespace b200cv {
+
+constexpr int JCMAX = 1024;  // group2 atoms per chunk (24 KB coordinates + 24 KB accumulators)
+
+struct SweepItem {
+  int i0;    // first group1 atom of the block
+  int j0;    // first group2 atom of the chunk (multiple of 32)
+  int jn;    // atoms in the chunk (<= JCMAX)
+  int diag;  // selfCoordNum only: chunk overlaps the block's rows -> apply j > i
+};
+
+struct SweepArgs {
+  const double *x1, *y1, *z1;  // group1 planes
+  const double *x2, *y2, *z2;  // group2 planes, readable up to the next multiple of 32
+  double *g1x, *g1y, *g1z;
+  double *g2x, *g2y, *g2z;
+  const SweepItem *items;
+  double *partials;  // one per CTA
+  unsigned long long *rare;
+  unsigned int rare_cap;
+  unsigned int *rare_count;
+  unsigned long long *pl;
+  unsigned long long pl_cap;
+  unsigned long long *pl_count;
+  int i_end;      // group1 atoms with index >= i_end do not exist
+  int want_grad;  // 0: value only (no gradient flush)
+  PairParams P;
+};
+
+// ---- TMA bulk copy + mbarrier (PTX) --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- one 32-atom tile ---------------------------------------------------------------------
+template <int EXP, bool ANISO, int PBC, bool PL, int R, bool MASKED>
+__device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &item, int tile,
+                                           int lane, int ibase, const double *__restrict__ sx,
+                                           const double *__restrict__ sy,
+                                           const double *__restrict__ sz, double *ax, double *ay,
+                                           double *az, const double (&xi)[R], const double (&yi)[R],
+                                           const double (&zi)[R], double (&a1x)[R],
+                                           double (&a1y)[R], double (&a1z)[R], double &fsum)
+{
+  PairParams const &P = A.P;
+  double b2x = 0.0, b2y = 0.0, b2z = 0.0;
+  unsigned plm[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) plm[k] = 0u;
+  int const tbase = tile * 32;
+
+#pragma unroll 1
+  for (int t = 0; t < 32; t++) {
+    int const jj = (lane + t) & 31;
+    double const xj = sx[tbase + jj];
+    double const yj = sy[tbase + jj];
+    double const zj = sz[tbase + jj];
+    int const jloc = tbase + jj;
+    int const jglob = item.j0 + jloc;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      double dx = xj - xi[k];
+      double dy = yj - yi[k];
+      double dz = zj - zi[k];
+      if constexpr (PBC == BC_ORTHO) {
+        // position_distance, orthogonal cell (src/colvars_system.h:176-184): the image
+        // index is computed in the reference's operation order so that ties break
+        // identically
+        double const shx = floor(__dadd_rn(__dmul_rn(P.recip[0][0], dx), 0.5));
+        double const shy = floor(__dadd_rn(__dmul_rn(P.recip[1][1], dy), 0.5));
+        double const shz = floor(__dadd_rn(__dmul_rn(P.recip[2][2], dz), 0.5));
+        dx = fma(-shx, P.cell[0][0], dx);
+        dy = fma(-shy, P.cell[1][1], dy);
+        dz = fma(-shz, P.cell[2][2], dz);
+      }
+      double u;
+      if constexpr (ANISO) {
+        double const sx_ = dx * P.inv_r0[0];
+        double const sy_ = dy * P.inv_r0[1];
+        double const sz_ = dz * P.inv_r0[2];
+        u = fma(sz_, sz_, fma(sy_, sy_, sx_ * sx_));
+      } else {
+        u = fma(dz, dz, fma(dy, dy, dx * dx)) * P.inv_r0sq[0];
+      }
+      double F, gq;
+      bool rare;
+      switching_fast<EXP, PL>(u, P, F, gq, rare);
+      if constexpr (MASKED) {
+        int const iglob = ibase + k * 32;
+        bool const valid =
+            (iglob < A.i_end) && (jloc < item.jn) && (!item.diag || (jglob > iglob));
+        F = valid ? F : 0.0;
+        gq = valid ? gq : 0.0;
+        rare = rare && valid;
+      }
+      if (rare) {
+        unsigned const slot = atomicAdd(A.rare_count, 1u);
+        if (slot < A.rare_cap) {
+          A.rare[slot] = ((unsigned long long)(unsigned)(ibase + k * 32) << 32) |
+                         (unsigned long long)(unsigned)jglob;
+        }
+        F = 0.0;
+        gq = 0.0;
+      }
+      if constexpr (PL) {
+        plm[k] |= (F > 0.0 ? 1u : 0u) << t;
+      }
+      fsum += F;
+      a1x[k] = fma(gq, dx, a1x[k]);
+      a1y[k] = fma(gq, dy, a1y[k]);
+      a1z[k] = fma(gq, dz, a1z[k]);
+      b2x = fma(gq, dx, b2x);
+      b2y = fma(gq, dy, b2y);
+      b2z = fma(gq, dz, b2z);
+    }
+    // the accumulators follow their atom: lane l takes over the atom lane l+1 just did
+    int const src = (lane + 1) & 31;
+    b2x = __shfl_sync(0xffffffffu, b2x, src);
+    b2y = __shfl_sync(0xffffffffu, b2y, src);
+    b2z = __shfl_sync(0xffffffffu, b2z, src);
+  }
+  // lane l now holds the warp's sum for atom tbase + l: add to the block-private copy
+  atomicAdd(&ax[tbase + lane], b2x);
+  atomicAdd(&ay[tbase + lane], b2y);
+  atomicAdd(&az[tbase + lane], b2z);
+
+  if constexpr (PL) {
+    // stream compaction of this warp-tile's listed pairs into the global (i,j) list
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < R; k++) cnt += __popc(plm[k]);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int const v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int const total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total > 0) {
+      unsigned long long base = 0;
+      if (lane == 31) base = atomicAdd(A.pl_count, (unsigned long long)total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      unsigned long long off = base + (unsigned long long)(incl - cnt);
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        unsigned m = plm[k];
+        unsigned long long const hi = (unsigned long long)(unsigned)(ibase + k * 32) << 32;
+        while (m) {
+          int const t = __ffs(m) - 1;
+          m &= m - 1;
+          if (off < A.pl_cap) {
+            A.pl[off] = hi | (unsigned long long)(unsigned)(item.j0 + tbase + ((lane + t) & 31));
+          }
+          off++;
+        }
+      }
+    }
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+template <int EXP, bool ANISO, int PBC, bool PL, int R, int W>
+__global__ void __launch_bounds__(W * 32) sweep_kernel(const __grid_constant__ SweepArgs A)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + JCMAX;
+  double *sz = sy + JCMAX;
+  double *ax = sz + JCMAX;
+  double *ay = ax + JCMAX;
+  double *az = ay + JCMAX;
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ double red[W];
+
+  SweepItem const item = A.items[blockIdx.x];
+  int const lane = threadIdx.x & 31;
+  int const warp = threadIdx.x >> 5;
+  int const jn_pad = (item.jn + 31) & ~31;
+  int const ntiles = jn_pad >> 5;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t const bytes = (uint32_t)jn_pad * 8u;
+    mbar_arrive_expect_tx(&mbar, 3u * bytes);
+    bulk_g2s(sx, A.x2 + item.j0, bytes, &mbar);
+    bulk_g2s(sy, A.y2 + item.j0, bytes, &mbar);
+    bulk_g2s(sz, A.z2 + item.j0, bytes, &mbar);
+  }
+  for (int t = threadIdx.x; t < jn_pad; t += W * 32) {
+    ax[t] = 0.0;
+    ay[t] = 0.0;
+    az[t] = 0.0;
+  }
+
+  // group1 atoms of this lane: i = ibase + 32 k
+  int const ibase = item.i0 + warp * (32 * R) + lane;
+  double xi[R], yi[R], zi[R], a1x[R], a1y[R], a1z[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    int const i = ibase + k * 32;
+    bool const ok = i < A.i_end;
+    xi[k] = ok ? A.x1[i] : 0.0;
+    yi[k] = ok ? A.y1[i] : 0.0;
+    zi[k] = ok ? A.z1[i] : 0.0;
+    a1x[k] = a1y[k] = a1z[k] = 0.0;
+  }
+  double fsum = 0.0;
+
+  __syncthreads();  // accumulators zeroed
+  mbar_wait(&mbar, 0);
+
+  bool const masked_item = item.diag || (item.i0 + W * 32 * R > A.i_end);
+  int const tile0 = (warp * ntiles) / W;  // staggered start: warps touch different tiles
+#pragma unroll 1
+  for (int tt = 0; tt < ntiles; tt++) {
+    int tile = tile0 + tt;
+    if (tile >= ntiles) tile -= ntiles;
+    bool const masked = masked_item || ((tile + 1) * 32 > item.jn);
+    if (masked) {
+      sweep_tile<EXP, ANISO, PBC, PL, R, true>(A, item, tile, lane, ibase, sx, sy, sz, ax, ay, az,
+                                                xi, yi, zi, a1x, a1y, a1z, fsum);
+    } else {
+      sweep_tile<EXP, ANISO, PBC, PL, R, false>(A, item, tile, lane, ibase, sx, sy, sz, ax, ay,
+                                                 az, xi, yi, zi, a1x, a1y, a1z, fsum);
+    }
+  }
+
+  // value: warp tree, then one partial per CTA in a fixed order
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+  if (lane == 0) red[warp] = fsum;
+  __syncthreads();  // also: all warps are done adding into ax/ay/az
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < W; w++) s += red[w];
+    A.partials[blockIdx.x] = s;
+  }
+
+  if (A.want_grad) {
+    // G_d = c_grad[d] * gq * diff_d ; group1 gets -G, group2 +G
+    double const cx = A.P.c_grad[0], cy = A.P.c_grad[1], cz = A.P.c_grad[2];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      int const i = ibase + k * 32;
+      if (i < A.i_end) {
+        atomicAdd(&A.g1x[i], -cx * a1x[k]);
+        atomicAdd(&A.g1y[i], -cy * a1y[k]);
+        atomicAdd(&A.g1z[i], -cz * a1z[k]);
+      }
+    }
+    for (int t = threadIdx.x; t < item.jn; t += W * 32) {
+      atomicAdd(&A.g2x[item.j0 + t], cx * ax[t]);
+      atomicAdd(&A.g2y[item.j0 + t], cy * ay[t]);
+      atomicAdd(&A.g2z[item.j0 + t], cz * az[t]);
+    }
+  }
+}
+
+constexpr size_t sweep_smem_bytes() { return 6 * JCMAX * sizeof(double); }
+
+}  // namespace b200cv

@@ -1,0 +1,48 @@
+// sweep_inst.cu -- instantiations and dispatch of the tile sweep (sweep.cuh).
+#include "kernels.cuh"
+
+namespace b200cv {
+
+// ============================ sweep dispatch =================================================
+
+bool sweep_has_special(int en, int ed) { return en == 6 && ed == 12; }
+
+template <int EXP, bool ANISO, int PBC, bool PL>
+static int launch_sweep_t(const SweepArgs &args, int nitems, cudaStream_t stream)
+{
+  auto kern = sweep_kernel<EXP, ANISO, PBC, PL, SWEEP_R, SWEEP_W>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sweep_smem_bytes());
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  kern<<<nitems, SWEEP_W * 32, sweep_smem_bytes(), stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+template <int EXP, bool ANISO>
+static int launch_sweep_ea(const SweepArgs &a, int n, int pbc, bool pl, cudaStream_t s)
+{
+  if (pbc == BC_NONE) {
+    return pl ? launch_sweep_t<EXP, ANISO, BC_NONE, true>(a, n, s)
+              : launch_sweep_t<EXP, ANISO, BC_NONE, false>(a, n, s);
+  }
+  return pl ? launch_sweep_t<EXP, ANISO, BC_ORTHO, true>(a, n, s)
+            : launch_sweep_t<EXP, ANISO, BC_ORTHO, false>(a, n, s);
+}
+
+int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso, int pbc,
+                 bool pairlist, cudaStream_t stream)
+{
+  if (nitems <= 0) return 0;
+  if (exp_special == 3) {
+    return aniso ? launch_sweep_ea<3, true>(args, nitems, pbc, pairlist, stream)
+                 : launch_sweep_ea<3, false>(args, nitems, pbc, pairlist, stream);
+  }
+  return aniso ? launch_sweep_ea<0, true>(args, nitems, pbc, pairlist, stream)
+               : launch_sweep_ea<0, false>(args, nitems, pbc, pairlist, stream);
+}
+
+}  // namespace b200cv

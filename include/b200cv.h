@@ -1,0 +1,189 @@
+/*
+ * b200cv.h -- C ABI of the B200-native coordination-number engine.
+ *
+ * This is the drop-in boundary for the Colvars coordination-number hot path
+ * (coordNum / selfCoordNum / groupCoord): everything a `colvar::cvc` subclass
+ * needs to implement init / read_data / calc_value / calc_gradients /
+ * apply_force on top of hand-written sm_100a kernels.  Plain C types only; no
+ * torch, no C++ in the signatures.  Device pointers are raw `double*` in the
+ * layouts the reference already uses; streams are passed as `void*`
+ * (a `cudaStream_t`).
+ *
+ * Reference interfaces replaced (paths relative to the Colvars tree):
+ *   b200cv_create / destroy        colvar::coordnum::coordnum + init        src/colvarcomp_coordnums.cpp:18-156
+ *                                  selfcoordnum / groupcoordnum ctors        src/colvarcomp_coordnums.cpp:472-475,564
+ *   b200cv_set_group               cvc::parse_group + atom_group arrays      src/colvarcomp.cpp:178-240, src/colvaratoms.h:770-815
+ *   b200cv_set_fitting             atom_group::parse_fitting_options         src/colvaratoms.cpp:815-934
+ *   b200cv_set_boundaries          system_boundary_conditions::set_boundaries src/colvars_system.h:80-158 (copied in cvc::read_data, src/colvarcomp.cpp:461)
+ *   b200cv_read_data               cvc::read_data                            src/colvarcomp.cpp:457-476
+ *                                  (reset_atoms_data + read_positions +      src/colvaratoms.cpp:1731,1107-1125,1325-1352;
+ *                                  calc_required_properties; GPU twin:       src/colvaratoms_gpu.cpp:176-465,
+ *                                  atoms_pos_from_proxy / cog_com kernels)   src/cuda/colvaratoms_kernel.cu:18-243
+ *   b200cv_calc_value              coordnum/selfcoordnum/groupcoordnum::calc_value  src/colvarcomp_coordnums.cpp:274-313,547-555,567-577
+ *                                  (= cvc::add_calc_value_node in smp gpu)   src/colvarcomp.h:170-173
+ *   b200cv_value                   cvc::calc_value_after_gpu                 src/colvarcomp.h:176
+ *   b200cv_calc_fit_gradients      cvc::calc_fit_gradients                   src/colvarcomp.cpp:558-565, src/colvaratoms.cpp:1433-1527
+ *   b200cv_apply_force             cvc::apply_force -> apply_colvar_force    src/colvarcomp.cpp:568-577, src/colvaratoms.cpp:1637-1704;
+ *                                  apply_colvar_force_to_proxy_kernel        src/cuda/colvaratoms_kernel.cu:434-570
+ *   b200cv_eval                    coordnum::main_loop on bare arrays        src/colvarcomp_coordnums.cpp:187-248, :478-523
+ *   b200cv_calc_host / b200cv_apply_force_host
+ *                                  the same step for a CPU proxy
+ *                                  (AoS atoms_positions / atoms_new_colvar_forces)  src/colvarproxy.h:139-142,275-300
+ *
+ * Error convention: every call returns the Colvars error bitmask
+ * (src/colvarmodule.h:986-995); b200cv_last_error() gives the message.
+ * No exceptions cross this boundary.  Calls on one handle must be serialised by
+ * the caller; different handles may be used from different host threads
+ * (`smp cvcs`, src/colvarproxy.cpp:299-315).
+ *
+ * There is no CPU fallback: creating a handle without a usable CUDA device
+ * fails with B200CV_ERROR.
+ */
+#ifndef B200CV_H
+#define B200CV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Colvars error bitmask (src/colvarmodule.h:986-995) */
+#define B200CV_OK 0
+#define B200CV_ERROR 1
+#define B200CV_NOT_IMPLEMENTED (1 << 1)
+#define B200CV_INPUT_ERROR (1 << 2)
+#define B200CV_BUG_ERROR (1 << 3)
+#define B200CV_FILE_ERROR (1 << 4)
+#define B200CV_MEMORY_ERROR (1 << 5)
+
+/* component kinds = function_type() strings "coordNum" / "selfCoordNum" / "groupCoord" */
+#define B200CV_COORDNUM 0
+#define B200CV_SELFCOORDNUM 1
+#define B200CV_GROUPCOORD 2
+
+/* evaluation flags, same values as colvar::coordnum::ef_* (src/colvarcomp_coordnums.h:32-37) */
+#define B200CV_EF_NULL 0
+#define B200CV_EF_GRADIENTS 1
+#define B200CV_EF_USE_PAIRLIST (1 << 9)
+#define B200CV_EF_REBUILD_PAIRLIST (1 << 10)
+
+typedef struct b200cv_cvc b200cv_cvc;
+
+/* Keywords of a coordNum / selfCoordNum / groupCoord block
+ * (src/colvarcomp_coordnums.cpp:73-153; doc/colvars-refman-main.tex:1913-2016). */
+typedef struct {
+  int kind;               /* B200CV_COORDNUM | _SELFCOORDNUM | _GROUPCOORD */
+  int n1;                 /* atoms in group1 */
+  int n2;                 /* atoms in group2 (ignored for selfCoordNum) */
+  double cutoff3[3];      /* r0 per axis ("cutoff" = all three equal); default 4 A */
+  int exp_numer;          /* expNumer, even > 0; default 6 */
+  int exp_denom;          /* expDenom, even > 0; default 12 */
+  int group1_center_only; /* group1CenterOnly (forced on for groupCoord) */
+  int group2_center_only; /* group2CenterOnly (forced on for groupCoord) */
+  double tolerance;       /* > 0 enables the pair list */
+  int pairlist_freq;      /* pairListFrequency; default 100 */
+  int device;             /* CUDA device ordinal */
+} b200cv_config;
+
+/* Fill a config with the reference defaults (r0 = 4, n = 6, m = 12, tolerance 0, freq 100). */
+void b200cv_config_defaults(b200cv_config *cfg);
+
+/* coordnum::init.  Validates like the reference: odd / non-positive exponents, n < 1,
+ * non-positive pairListFrequency -> B200CV_INPUT_ERROR.  With tolerance > 0 runs the
+ * reference's Newton solve for tolerance_l2_max on the host
+ * (src/colvarcomp_coordnums.cpp:162-184). */
+int b200cv_create(const b200cv_config *cfg, b200cv_cvc **out);
+int b200cv_destroy(b200cv_cvc *h);
+/* Message of the last failing call on this handle (or of the last failed create when
+ * h == NULL).  Never NULL. */
+const char *b200cv_last_error(const b200cv_cvc *h);
+
+/* Atom group `which` (1 or 2): proxy slot of every atom (atoms_index), masses (NULL = 1.0).
+ * Overlapping group1 / group2 -> B200CV_INPUT_ERROR (src/colvarcomp_coordnums.cpp:67-71). */
+int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const double *mass,
+                     int n);
+
+/* Fitting options of group `which` (centerToReference / rotateToReference / fittingGroup /
+ * refPositions / enableFitGradients).  fit_proxy_index == NULL: the group is fitted on
+ * itself.  ref_pos is SoA x..x y..y z..z of nref = (nfit or n) atoms, not yet centred. */
+int b200cv_set_fitting(b200cv_cvc *h, int which, int center, int rotate,
+                       const int *fit_proxy_index, int nfit, const double *ref_pos_soa,
+                       int enable_fit_gradients);
+
+/* Periodic flags and Bravais vectors; all-zero flags = non-periodic. */
+int b200cv_set_boundaries(b200cv_cvc *h, int periodic_x, int periodic_y, int periodic_z,
+                          const double A[3], const double B[3], const double C[3]);
+
+/* ---- device-resident step (colvarproxy_gpu layout) ---------------------------------
+ * d_proxy_pos / d_proxy_force: device double[3 * proxy_stride], SoA planes x|y|z with
+ * stride = number of proxy atoms (src/colvaratoms_gpu.cpp:210-214,
+ * src/cuda/colvaratoms_kernel.cu:47-52).  All work is enqueued on `stream`
+ * (proxy->get_default_stream()); nothing synchronises except b200cv_value(). */
+int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
+                     void *stream);
+int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, void *stream);
+int b200cv_calc_fit_gradients(b200cv_cvc *h, void *stream);
+/* Waits for the stream used by the last calc_value and returns x.real_value. */
+int b200cv_value(b200cv_cvc *h, double *value);
+/* F_proxy[idx_i] += force * (R^-1 grad_i) for both groups (+ fit gradients). */
+int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_t proxy_stride,
+                       void *stream);
+
+/* ---- bare-array entry (what add_calc_value_node wraps) ------------------------------
+ * d_pos1/d_pos2: device SoA double[3*n] exactly as colvaratoms_gpu_buffer_t::d_atoms_pos
+ * (src/colvaratoms_gpu.h:19-64); d_grad1/d_grad2: d_atoms_grad, ACCUMULATED into (the
+ * reference zeroes them every step, src/colvaratoms_gpu.cpp:192).  For selfCoordNum pass
+ * d_pos2 = d_grad2 = NULL.  `flags` = B200CV_EF_*; rebuild is the caller's decision here.
+ * The value is retrieved with b200cv_value(). */
+int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
+                double *d_grad1, double *d_grad2, void *stream);
+
+/* ---- host-buffer step (CPU proxy arrays; host<->device copies included) ---------------
+ * h_proxy_pos: AoS rvector array double[3*n_proxy] (src/colvarproxy.h:275).
+ * b200cv_calc_host = read_data + calc_value (+ fit gradients) and returns the value;
+ * b200cv_apply_force_host adds force * gradients into h_proxy_force (AoS). */
+int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
+                     long long step_relative, int gradients, double *value);
+int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, size_t n_proxy);
+
+/* ---- inspection (tests, debug_gradients, host shim) ----------------------------------- */
+/* Copy a group's current positions / gradients / fit gradients to host SoA arrays. */
+int b200cv_get_positions(b200cv_cvc *h, int which, double *h_pos_soa);
+int b200cv_get_gradients(b200cv_cvc *h, int which, double *h_grad_soa);
+int b200cv_get_fit_gradients(b200cv_cvc *h, int which, double *h_fit_grad_soa, int nfit);
+int b200cv_get_centers(b200cv_cvc *h, int which, double com[3], double cog[3]);
+/* Rotation quaternion (q0..q3) of a fitted group after read_data. */
+int b200cv_get_rotation(b200cv_cvc *h, int which, double q[4]);
+/* tolerance_l2_max found by the Newton solve at create time (1e20 without pair list). */
+int b200cv_get_tolerance_l2_max(const b200cv_cvc *h, double *l2_max);
+/* Number of listed pairs after the last rebuild, and their canonical indices
+ * (ip = i*N2 + j, or the row-major upper triangle for selfCoordNum; sorted ascending). */
+int b200cv_pairlist_count(b200cv_cvc *h, size_t *count);
+int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *h_indices, size_t capacity);
+/* Counters of the last calc_value: kernels launched, pairs sent to the exact
+ * (reference-order) path. */
+int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs);
+
+/* ---- multi-GPU (one process per GPU; group1 rows sharded, group2 replicated) ---------- */
+/* NCCL unique id (128 bytes) created on rank 0 and handed to every rank by the caller. */
+int b200cv_comm_unique_id(unsigned char id[128]);
+/* Join the communicator; afterwards calc_value evaluates only this rank's rows of
+ * group1 (cyclic tiles for selfCoordNum) and all-reduces [value | grad1 | grad2] with
+ * ncclAllReduce(ncclDouble, ncclSum) on the compute stream. */
+int b200cv_comm_init(b200cv_cvc *h, const unsigned char id[128], int rank, int world);
+/* Shard without a communicator (the caller reduces): for tests and external plumbing. */
+int b200cv_set_shard(b200cv_cvc *h, int rank, int world);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* Sustained DFMA throughput of the device (the FP64 roofline denominator):
+ * runs a pure dependent-chain DFMA kernel for about `target_ms` and reports TFLOP/s. */
+int b200cv_fp64_peak(int device, double target_ms, double *tflops, double *elapsed_ms);
+/* Max relative error (in ulps) of the in-kernel reciprocal over n samples in [lo, hi]. */
+int b200cv_selftest_rcp(int device, int n, double lo, double hi, double *max_ulp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CV_H */

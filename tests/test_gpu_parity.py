@@ -1,0 +1,370 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bar (BASELINE.json north_star): pair-list indices bit-exact; values,
+gradients and forces within 1e-12 relative in FP64.
+
+Metric for arrays (SURVEY.md section 7 "hard parts"): per-atom gradients are sums of many
+signed pair terms; summation order differs from the CPU loop, so the error of an element is
+bounded relative to the largest element of the array:  max|a - b| <= RTOL * max|b|.
+"""
+import numpy as np
+import pytest
+
+from . import oracle_lib as O
+from . import regression as R
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _cb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import colvars_b200 as cb
+    cb.load()
+    return cb
+
+
+def close_arr(a, b, rtol=RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(np.max(np.abs(b)), 1e-300) if b.size else 1.0
+    err = np.max(np.abs(a - b)) if b.size else 0.0
+    assert err <= rtol * scale, f"max abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
+
+
+def close_val(a, b, rtol=RTOL):
+    assert abs(a - b) <= rtol * max(abs(b), 1e-300), f"{a!r} vs {b!r} rel {abs(a - b) / abs(b):.3e}"
+
+
+def rand_case(n1, n2, seed, L=30.0):
+    rng = np.random.default_rng(seed)
+    p1 = rng.random((n1, 3)) * L
+    p2 = rng.random((n2, 3)) * L
+    proxy = np.ascontiguousarray(np.concatenate([p1, p2]))
+    return proxy, np.arange(n1, dtype=np.int32), np.arange(n1, n1 + n2, dtype=np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+
+def test_reciprocal_is_within_two_ulp():
+    cb = _cb()
+    for lo, hi in ((1.0, 2.0), (1.0, 1e6), (1.0, 1e40), (1e-200, 1e200)):
+        assert cb.selftest_rcp(0, 1 << 20, lo, hi) <= 2.0
+
+
+@pytest.mark.parametrize("case", R.CASES)
+def test_reference_regression_cases(case):
+    """The reference's own coordnum regression inputs (5 frames of deca-alanine) through
+    the host-buffer C-ABI step, against the golden traj/forces (the reference comparer's
+    tolerance) AND against the oracle (1e-12)."""
+    cb = _cb()
+    cfg, frames, traj, forces = R.load_case(case)
+    natoms = frames[0].shape[0]
+    idx1, idx2 = R.stub_slots(cfg, natoms)
+    cv = cb.CoordNum(cfg.function_type, idx1, idx2 if cfg.kind != 1 else None,
+                     cutoff3=cfg.cutoff3, exp_numer=cfg.exp_numer, exp_denom=cfg.exp_denom,
+                     group1_center_only=cfg.group1_center_only,
+                     group2_center_only=cfg.group2_center_only, tolerance=cfg.tolerance,
+                     pairlist_freq=cfg.pairlist_freq)
+    oracle = R.run_oracle_case(cfg, frames)
+    results = []
+    for step, xyz in enumerate(frames):
+        pos = np.ascontiguousarray(xyz, dtype=np.float64)
+        v = cv.calc_host(pos, step=step, gradients=True)
+        fa = R.harmonic_force(cfg, v)
+        pf = np.zeros((natoms, 3))
+        cv.apply_force_host(fa, pf)
+        results.append((v, fa, pf))
+        ov, ofa, opf = oracle[step]
+        close_val(v, ov)
+        close_val(fa, ofa)
+        close_arr(pf, opf)
+    assert not R.check_against_golden(results, traj, forces)
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 33), (5, 7), (31, 32), (33, 65), (257, 1000),
+                                   (1030, 2100)])
+def test_coordnum_random_sizes(n1, n2):
+    cb = _cb()
+    proxy, i1, i2 = rand_case(n1, n2, seed=n1 * 1000 + n2, L=12.0 + 0.01 * n2)
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
+    v = cv.calc_host(proxy)
+    p = O.make_params((4.0, 4.0, 4.0))
+    ov, og1, og2 = O.coordnum(p, proxy[i1], proxy[i2])
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
+    close_arr(cv.gradients(2), og2)
+    # Newton's third law: the gradients of the two groups cancel
+    tot = cv.gradients(1).sum(0) + cv.gradients(2).sum(0)
+    assert np.max(np.abs(tot)) <= 1e-11 * max(np.max(np.abs(og1)), 1e-300) * (n1 + n2)
+
+
+@pytest.mark.parametrize("n", [2, 3, 32, 33, 100, 1025, 2500])
+def test_selfcoordnum_random_sizes(n):
+    cb = _cb()
+    proxy, i1, _ = rand_case(n, 0, seed=77 + n, L=10.0 + 0.005 * n)
+    cv = cb.CoordNum("selfCoordNum", i1, cutoff=3.5)
+    v = cv.calc_host(proxy)
+    p = O.make_params((3.5, 3.5, 3.5))
+    ov, og = O.selfcoordnum(p, proxy)
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og)
+
+
+def test_anisotropic_cutoff3_and_general_exponents():
+    cb = _cb()
+    proxy, i1, i2 = rand_case(300, 1500, seed=5, L=25.0)
+    for cutoff3, en, ed in (((3.0, 6.0, 4.0), 6, 12), ((4.0, 4.0, 4.0), 8, 10),
+                            ((2.5, 3.5, 5.0), 4, 8), ((4.0, 4.0, 4.0), 2, 4),
+                            ((3.3, 3.3, 3.3), 6, 8), ((5.0, 4.0, 3.0), 12, 6)):
+        cv = cb.CoordNum("coordNum", i1, i2, cutoff3=cutoff3, exp_numer=en, exp_denom=ed)
+        v = cv.calc_host(proxy)
+        p = O.make_params(cutoff3, en, ed)
+        ov, og1, og2 = O.coordnum(p, proxy[i1], proxy[i2])
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        close_arr(cv.gradients(2), og2)
+        cv.close()
+
+
+def test_value_only_leaves_gradients_untouched():
+    cb = _cb()
+    proxy, i1, i2 = rand_case(100, 300, seed=9)
+    cv = cb.CoordNum("coordNum", i1, i2)
+    v = cv.calc_host(proxy, gradients=False)
+    p = O.make_params()
+    ov, _, _ = O.coordnum(p, proxy[i1], proxy[i2], gradients=False)
+    close_val(v, ov)
+    assert not cv.gradients(1).any() and not cv.gradients(2).any()
+
+
+def test_pairs_at_the_taylor_window_and_coincident_thresholds():
+    """Pairs placed exactly at / next to l2 = 1 (the reference's Taylor branch,
+    |l2 - 1| < 1e-7) must come out as the reference computes them."""
+    cb = _cb()
+    r0 = 4.0
+    offs = [0.0, 1e-9, -1e-9, 4e-8, -4e-8, 6e-8, 1e-6, -1e-6, 1e-4, -1e-4, 4e-4, -4e-4, 1e-3,
+            -1e-3]
+    p1 = np.zeros((len(offs), 3))
+    p2 = np.zeros((len(offs), 3))
+    for k, o in enumerate(offs):
+        p1[k] = (100.0 * k, 0.0, 0.0)          # far apart rows: only pair (k,k) is near l2 = 1
+        d = np.array([1.0, 2.0, 2.0]) / 3.0    # unit vector
+        p2[k] = p1[k] + d * r0 * np.sqrt(1.0 + o)
+    proxy = np.ascontiguousarray(np.concatenate([p1, p2]))
+    i1 = np.arange(len(offs), dtype=np.int32)
+    i2 = i1 + len(offs)
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=r0)
+    v = cv.calc_host(proxy)
+    ov, og1, og2 = O.coordnum(O.make_params((r0,) * 3), p1, p2)
+    close_val(v, ov, 1e-13)
+    close_arr(cv.gradients(1), og1, 1e-13)
+    close_arr(cv.gradients(2), og2, 1e-13)
+    launches, exact = cv.last_stats()
+    assert exact >= 10  # those pairs went through the reference-order path
+
+
+@pytest.mark.parametrize("kind", ["coordNum", "selfCoordNum"])
+@pytest.mark.parametrize("aniso", [False, True])
+def test_pairlist_indices_bit_exact_and_values(kind, aniso):
+    """Rebuild on steps 0, 3, 6; list walk in between (pairListFrequency 3).  The listed
+    set has to equal the reference's dense bool array bit for bit on every rebuild."""
+    cb = _cb()
+    n1, n2 = (700, 1800) if kind == "coordNum" else (1500, 0)
+    proxy, i1, i2 = rand_case(n1, n2, seed=21 + n1, L=22.0)
+    cutoff3 = (3.0, 5.0, 4.0) if aniso else (4.0, 4.0, 4.0)
+    tol = 0.02
+    cv = cb.CoordNum(kind, i1, i2 if kind == "coordNum" else None, cutoff3=cutoff3,
+                     tolerance=tol, pairlist_freq=3)
+    p = O.make_params(cutoff3, 6, 12, tol)
+    assert cv.tolerance_l2_max() == p.tolerance_l2_max
+    npairs = n1 * n2 if kind == "coordNum" else n1 * (n1 - 1) // 2
+    pl = np.ones(npairs, dtype=np.uint8)
+    rng = np.random.default_rng(3)
+    pos = proxy.copy()
+    for step in range(8):
+        rebuild = step % 3 == 0
+        v = cv.calc_host(pos, step=step)
+        if kind == "coordNum":
+            ov, og1, og2 = O.coordnum(p, pos[i1], pos[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(cv.gradients(2), og2)
+        else:
+            ov, og1 = O.selfcoordnum(p, pos, pairlist=pl, rebuild=rebuild)
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        if rebuild:
+            mine = cv.pairlist()
+            ref = np.flatnonzero(pl).astype(np.uint64)
+            assert mine.shape == ref.shape and np.array_equal(mine, ref)
+        pos = pos + rng.normal(0.0, 0.05, pos.shape)
+
+
+def test_pairlist_before_first_rebuild_is_all_true():
+    """step_relative = 1 on the first call: the reference walks an all-true list."""
+    cb = _cb()
+    proxy, i1, i2 = rand_case(90, 200, seed=4, L=14.0)
+    cv = cb.CoordNum("coordNum", i1, i2, tolerance=0.01, pairlist_freq=5)
+    p = O.make_params((4.0,) * 3, 6, 12, 0.01)
+    pl = np.ones(90 * 200, dtype=np.uint8)
+    v = cv.calc_host(proxy, step=1)
+    ov, og1, og2 = O.coordnum(p, proxy[i1], proxy[i2], pairlist=pl, rebuild=False)
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
+    assert len(cv.pairlist()) == 90 * 200
+
+
+def test_pairlist_thresholds_are_decided_like_the_reference():
+    """Pairs straddling l2_max by a few ulp: membership must match the oracle exactly."""
+    cb = _cb()
+    tol, r0 = 0.01, 4.0
+    p = O.make_params((r0,) * 3, 6, 12, tol)
+    l2max = p.tolerance_l2_max
+    n = 64
+    p1 = np.zeros((n, 3))
+    p2 = np.zeros((n, 3))
+    for k in range(n):
+        p1[k] = (200.0 * k, 0.0, 0.0)
+        scale = 1.0 + (k - n // 2) * 2.0 ** -52
+        p2[k] = p1[k] + np.array([0.0, 0.0, 1.0]) * r0 * np.sqrt(l2max) * scale
+    proxy = np.ascontiguousarray(np.concatenate([p1, p2]))
+    i1 = np.arange(n, dtype=np.int32)
+    i2 = i1 + n
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=r0, tolerance=tol, pairlist_freq=1)
+    v = cv.calc_host(proxy, step=0)
+    pl = np.ones(n * n, dtype=np.uint8)
+    ov, og1, og2 = O.coordnum(p, p1, p2, pairlist=pl, rebuild=True)
+    assert np.array_equal(cv.pairlist(), np.flatnonzero(pl).astype(np.uint64))
+    assert abs(v - ov) <= 1e-12 * max(abs(ov), 1e-6)
+
+
+@pytest.mark.parametrize("bc", ["ortho", "triclinic", "mixed"])
+@pytest.mark.parametrize("kind", ["coordNum", "selfCoordNum"])
+def test_periodic_boundaries(bc, kind):
+    cb = _cb()
+    L = 18.0
+    n1, n2 = (200, 900) if kind == "coordNum" else (700, 0)
+    rng = np.random.default_rng(11)
+    proxy = np.ascontiguousarray((rng.random((n1 + n2, 3)) * 3.0 - 1.0) * L)  # outside the cell too
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    if bc == "ortho":
+        per, A, B, Cc = (1, 1, 1), (L, 0, 0), (0, 1.1 * L, 0), (0, 0, 0.9 * L)
+    elif bc == "triclinic":
+        per, A, B, Cc = (1, 1, 1), (L, 0, 0), (0.3 * L, L, 0), (0.1 * L, -0.2 * L, L)
+    else:
+        per, A, B, Cc = (1, 1, 0), (L, 0, 0), (0, L, 0), (0, 0, L)
+    cv = cb.CoordNum(kind, i1, i2 if kind == "coordNum" else None, cutoff=4.0)
+    cv.set_boundaries(per, A, B, Cc)
+    v = cv.calc_host(proxy)
+    p = O.make_params((4.0,) * 3, boundaries=(per, A, B, Cc))
+    if kind == "coordNum":
+        ov, og1, og2 = O.coordnum(p, proxy[i1], proxy[i2])
+        close_arr(cv.gradients(2), og2)
+    else:
+        ov, og1 = O.selfcoordnum(p, proxy)
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
+
+
+@pytest.mark.parametrize("g1c,g2c,kind", [(True, False, "coordNum"), (False, True, "coordNum"),
+                                          (True, True, "coordNum"), (True, True, "groupCoord")])
+def test_center_only_variants_and_groupcoord(g1c, g2c, kind):
+    cb = _cb()
+    proxy, i1, i2 = rand_case(150, 400, seed=8, L=9.0)
+    rng = np.random.default_rng(2)
+    m1, m2 = rng.random(150) * 15 + 1, rng.random(400) * 15 + 1
+    cv = cb.CoordNum(kind, i1, i2, cutoff3=(3.0, 6.0, 4.0), group1_center_only=g1c,
+                     group2_center_only=g2c, mass1=m1, mass2=m2)
+    v = cv.calc_host(proxy)
+    p = O.make_params((3.0, 6.0, 4.0))
+    ov, og1, og2 = O.coordnum(p, proxy[i1], proxy[i2], g1_center_only=g1c, g2_center_only=g2c,
+                              mass1=m1, mass2=m2)
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
+    close_arr(cv.gradients(2), og2)
+
+
+def test_device_resident_step_and_force_scatter():
+    """colvarproxy_gpu layout: SoA planes with stride = #proxy atoms, shuffled indices,
+    shared proxy atoms untouched, forces accumulated on top of existing ones."""
+    import torch
+    cb = _cb()
+    rng = np.random.default_rng(31)
+    P = 5000
+    allpos = rng.random((P, 3)) * 30.0
+    perm = rng.permutation(P)
+    i1, i2 = perm[:400].astype(np.int32), perm[400:2400].astype(np.int32)
+    cv = cb.CoordNum("coordNum", i1, i2)
+    d_pos = torch.tensor(np.ascontiguousarray(allpos.T), device="cuda")
+    f0 = rng.random((3, P))
+    d_force = torch.tensor(f0, device="cuda")
+    cv.read_data(d_pos)
+    cv.calc_value(step=0)
+    v = cv.value()
+    cv.apply_force(-0.37, d_force)
+    torch.cuda.synchronize()
+    p = O.make_params()
+    ov, og1, og2 = O.coordnum(p, allpos[i1], allpos[i2])
+    close_val(v, ov)
+    expect = f0.T.copy()
+    expect[i1] += -0.37 * og1
+    expect[i2] += -0.37 * og2
+    close_arr(d_force.cpu().numpy().T, expect)
+    com, cog = cv.centers(2)
+    close_arr(cog, allpos[i2].mean(0), 1e-13)
+
+
+def test_bare_array_eval_accumulates_into_callers_gradients():
+    import torch
+    cb = _cb()
+    proxy, i1, i2 = rand_case(333, 777, seed=12, L=15.0)
+    cv = cb.CoordNum("coordNum", i1, i2)
+    pos1 = torch.tensor(np.ascontiguousarray(proxy[i1].T), device="cuda")
+    pos2 = torch.tensor(np.ascontiguousarray(proxy[i2].T), device="cuda")
+    g1 = torch.ones((3, 333), dtype=torch.float64, device="cuda")
+    g2 = torch.zeros((3, 777), dtype=torch.float64, device="cuda")
+    cv.eval(pos1, pos2, cb.EF_GRADIENTS, g1, g2)
+    v = cv.value()
+    torch.cuda.synchronize()
+    ov, og1, og2 = O.coordnum(O.make_params(), proxy[i1], proxy[i2])
+    close_val(v, ov)
+    close_arr(g1.cpu().numpy().T, og1 + 1.0)
+    close_arr(g2.cpu().numpy().T, og2)
+
+
+def test_input_errors_follow_the_reference():
+    cb = _cb()
+    with pytest.raises(cb.B200cvError, match="odd exponent"):
+        cb.CoordNum("coordNum", [0], [1], exp_numer=5)
+    with pytest.raises(cb.B200cvError, match="negative exponent"):
+        cb.CoordNum("coordNum", [0], [1], exp_numer=-2)
+    with pytest.raises(cb.B200cvError, match="share a common atom"):
+        cb.CoordNum("coordNum", [0, 1, 2], [5, 2])
+    with pytest.raises(cb.B200cvError, match="pairlistfrequency"):
+        cb.CoordNum("coordNum", [0], [1], tolerance=0.1, pairlist_freq=0)
+    with pytest.raises(cb.B200cvError, match="cutoff"):
+        cb.CoordNum("coordNum", [0], [1], cutoff=3.0, cutoff3=(1, 2, 3))
+
+
+def test_config2_full_size_against_parallel_oracle():
+    """BASELINE config 2 at full size (1 k x 100 k, 1e8 pairs): value and gradients
+    against the OpenMP oracle, plus size-independent properties."""
+    cb = _cb()
+    from colvars_b200 import synth
+    proxy, i1, i2, L = synth.coordnum_case(1000, 100000, seed=1234)
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
+    v = cv.calc_host(proxy)
+    g1, g2 = cv.gradients(1), cv.gradients(2)
+    ov, og1, og2 = O.coordnum(O.make_params(), proxy[i1], proxy[i2], omp=8)
+    close_val(v, ov)
+    close_arr(g1, og1)
+    close_arr(g2, og2)
+    # translation invariance and Newton's third law
+    assert np.max(np.abs(g1.sum(0) + g2.sum(0))) <= 1e-9
+    v2 = cv.calc_host(proxy + np.array([3.0, -7.0, 11.0]))
+    close_val(v2, v, 1e-11)
+    # a rigid rotation of everything leaves the isotropic value unchanged
+    Rm = synth.random_rotation(5)
+    v3 = cv.calc_host(np.ascontiguousarray(proxy @ Rm.T))
+    close_val(v3, v, 1e-11)
