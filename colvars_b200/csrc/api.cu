@@ -280,6 +280,16 @@ int alloc_group(b200cv_cvc *h, Group &G, int n)
   return B200CV_OK;
 }
 
+int ensure_partials(b200cv_cvc *h, int need)
+{
+  if (need > h->partial_cap) {
+    free_dev(h->d_partials);
+    CUDA_OK(h, cudaMalloc(&h->d_partials, sizeof(double) * need));
+    h->partial_cap = need;
+  }
+  return B200CV_OK;
+}
+
 // Work items of the tile sweep for this rank: (group1 block) x (group2 chunk)
 int build_items(b200cv_cvc *h)
 {
@@ -336,12 +346,8 @@ int build_items(b200cv_cvc *h)
     CUDA_OK(h, cudaMemcpy(h->d_items, mine.data(), sizeof(SweepItem) * mine.size(),
                           cudaMemcpyHostToDevice));
   }
-  int const need = std::max(h->nitems, 1) + 2 * EXACT_BLOCKS;
-  if (need > h->partial_cap) {
-    free_dev(h->d_partials);
-    CUDA_OK(h, cudaMalloc(&h->d_partials, sizeof(double) * need));
-    h->partial_cap = need;
-  }
+  int rc = ensure_partials(h, std::max(h->nitems, 1) + 2 * EXACT_BLOCKS);
+  if (rc) return rc;
   h->items_dirty = false;
   return B200CV_OK;
 }
@@ -400,6 +406,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
 
   if (h->center1() || h->center2()) {
     // COM variants (src/colvarcomp_coordnums.cpp:190-247): O(N) work, reference-order pairs
+    int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
+    if (rc) return rc;
     CenterArgs A{};
     A.P = h->P;
     A.flags = flags;

@@ -7,8 +7,8 @@
 //    returns (F, gq) with the pair gradient G_d = C_d * gq * diff_d; the per-axis
 //    constants C_d are applied once per atom when accumulators are flushed.
 //    It also returns `rare`: the pair lies so close to a decision threshold
-//    (l2 ~ 1 where the reference switches to its Taylor branch and the quotient
-//    form loses digits; or, with a pair list, l2 ~ l2_max or f0 ~ tolerance) that
+//    (|l2 - 1| < 2^-4, where the reference's quotient form and its Taylor branch
+//    carry rounding errors of their own that parity has to reproduce; or, with a pair list, l2 ~ l2_max or f0 ~ tolerance) that
 //    only arithmetic in the reference's own operation order reproduces the
 //    reference.  Rare pairs contribute nothing here; they are queued and
 //    evaluated by pair_exact.
@@ -99,10 +99,16 @@ __device__ __forceinline__ double fast_rcp_wide(double x)
   return 1.0 / x;
 }
 
-// "|l2 - 1| < 2^-10" on the high word only (integer pipe, not the FP64 pipe)
+// "|l2 - 1| < 2^-4" on the high word only (integer pipe, not the FP64 pipe).
+// Why so wide: the reference's log-derivative m' xd / ((1-xd) l2) - n' xn / ((1-xn) l2)
+// subtracts two O(1/h) terms (h = l2 - 1), so ITS rounding error is ~5e-17 / h^2 relative:
+// 3e-11 at h = 1e-3, 1e-14 at h = 2^-4.  Any better-conditioned formula disagrees with the
+// reference by that much, so parity at 1e-12 needs the reference's own operation order for
+// every pair in this window (about 2 pairs per group1 atom at water density -- ~1e-6 of all
+// pairs at the benchmark sizes).
 __device__ __forceinline__ bool near_one(double u)
 {
-  return (unsigned)(__double2hiint(u) - 0x3FEFF800) < 0xC00u;
+  return (unsigned)(__double2hiint(u) - 0x3FEE0000) < 0x30000u;
 }
 
 // high words within +-1 of each other (relative distance < ~2e-6); both positive

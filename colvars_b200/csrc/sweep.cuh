@@ -25,7 +25,7 @@
 //   pair list   : on rebuild sweeps each lane records one 32-bit mask per register atom
 //                 and tile; masks are compacted into a global (i,j) list by a warp
 //                 prefix sum and one atomicAdd per warp and tile (stream compaction).
-//   rare pairs  : pairs within 2^-10 of l2 = 1 (or next to a pair-list threshold) are
+//   rare pairs  : pairs within 2^-4 of l2 = 1 (or next to a pair-list threshold) are
 //                 appended to a queue and evaluated in the reference's operation order by
 //                 exact_kernel; they contribute nothing here.
 //

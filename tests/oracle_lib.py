@@ -143,10 +143,15 @@ def coordnum(p, pos1, pos2, *, gradients=True, pairlist=None, rebuild=False,
     m1 = np.ones(n1) if mass1 is None else np.asarray(mass1, dtype=np.float64)
     m2 = np.ones(n2) if mass2 is None else np.asarray(mass2, dtype=np.float64)
     com1, com2 = np.zeros(3), np.zeros(3)
-    L.cvo_center_of_mass(n1, _ptr(p1), _ptr(m1), float(m1.sum()), _ptr(com1))
-    L.cvo_center_of_mass(n2, _ptr(p2), _ptr(m2), float(m2.sum()), _ptr(com2))
-    w1 = m1 / m1.sum()
-    w2 = m2 / m2.sum()
+    # atom_group::update_total_mass: std::accumulate, strictly left to right
+    # (src/colvaratoms.cpp:1001).  np.add.accumulate is sequential; Python's sum() is not
+    # (compensated summation since 3.12) and numpy's sum() is pairwise.
+    tm1 = float(np.add.accumulate(m1)[-1])
+    tm2 = float(np.add.accumulate(m2)[-1])
+    L.cvo_center_of_mass(n1, _ptr(p1), _ptr(m1), tm1, _ptr(com1))
+    L.cvo_center_of_mass(n2, _ptr(p2), _ptr(m2), tm2, _ptr(com2))
+    w1 = m1 / tm1
+    w2 = m2 / tm2
     v = L.cvo_coordnum(C.byref(p), n1, _ptr(p1), n2, _ptr(p2), int(g1_center_only),
                        int(g2_center_only), _ptr(com1), _ptr(com2), _ptr(w1), _ptr(w2),
                        _ptr(g1), _ptr(g2), plp, flags)
