@@ -64,7 +64,7 @@ SYMBOLS = [
     "b200cv_config_defaults", "b200cv_create", "b200cv_destroy", "b200cv_last_error",
     "b200cv_set_group", "b200cv_set_fitting", "b200cv_set_boundaries", "b200cv_read_data",
     "b200cv_calc_value", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
-    "b200cv_eval", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
+    "b200cv_eval", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
     "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_comm_unique_id",
@@ -99,6 +99,7 @@ def load():
     L.b200cv_value.argtypes = [H, _dp]
     L.b200cv_apply_force.argtypes = [H, C.c_double, vp, sz, vp]
     L.b200cv_eval.argtypes = [H, vp, vp, C.c_int, vp, vp, vp]
+    L.b200cv_eval_host.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
     L.b200cv_calc_host.argtypes = [H, vp, sz, ll, C.c_int, _dp]
     L.b200cv_apply_force_host.argtypes = [H, C.c_double, vp, sz]
     L.b200cv_get_positions.argtypes = [H, C.c_int, _dp]
@@ -264,6 +265,13 @@ class CoordNum:
         g2 = C.c_void_p(grad2.data_ptr()) if grad2 is not None else None
         self._check(self._L.b200cv_eval(self._h, C.c_void_p(pos1.data_ptr()), p2, int(flags), g1,
                                         g2, _stream_ptr(stream)))
+
+    def eval_host(self, pos1, pos2=None, flags=EF_GRADIENTS, grad1=None, grad2=None):
+        """pos*/grad*: numpy SoA arrays (3, n) float64 in host memory; returns the value."""
+        v = C.c_double()
+        self._check(self._L.b200cv_eval_host(self._h, _as_dp(pos1), _as_dp(pos2), int(flags),
+                                             _as_dp(grad1), _as_dp(grad2), C.byref(v)))
+        return v.value
 
     # -- host-buffer step (CPU proxy arrays, AoS) ---------------------------------------------
     def calc_host(self, proxy_pos_aos, step=0, gradients=True):

@@ -250,7 +250,23 @@ void fill_pair_params(b200cv_cvc *h)
   P.ntol = -P.tol * P.inv1mt;
   P.l2_max = h->l2_max;
   P.l2max_hi = hi_word(P.l2_max);
-  P.tol_hi = hi_word(P.tol > 0 ? P.tol : 1e-300);
+  // l2 at which the unshifted switching function equals the tolerance (bisection; the
+  // function is monotonic on [1, 1e12] whenever such a root exists)
+  P.utol_hi = P.l2max_hi;
+  if (P.tol > 0) {
+    auto f0 = [&](double u) {
+      double d = 0.0;
+      return switching_host(u, d, c.exp_numer, c.exp_denom, 0.0) - P.tol;
+    };
+    double lo = 1.0 + 1e-6, hi = 1e12;
+    if (f0(lo) * f0(hi) < 0) {
+      for (int it = 0; it < 200; it++) {
+        double const mid = 0.5 * (lo + hi);
+        if (f0(lo) * f0(mid) <= 0) hi = mid; else lo = mid;
+      }
+      P.utol_hi = hi_word(0.5 * (lo + hi));
+    }
+  }
   h->exp_special = sweep_has_special(c.exp_numer, c.exp_denom) ? P.en2 : 0;
   for (int d = 0; d < 3; d++) {
     P.c_grad[d] = h->exp_special ? -2.0 * (double)P.en2 * P.inv1mt * P.inv_r0sq[d]
@@ -1042,6 +1058,63 @@ int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int f
     if (!h->self() && d_grad2) {
       Group &G2 = h->g[1];
       CUDA_OK(h, launch_repack(G2.d_grad, G2.stride, d_grad2, (size_t)G2.n, G2.n, 1, s));
+    }
+  }
+  return B200CV_OK;
+}
+
+int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, int flags,
+                     double *h_grad1, double *h_grad2, double *value)
+{
+  if (!h || !value) return B200CV_BUG_ERROR;
+  if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
+  if (!h_pos1 || (!h->self() && !h_pos2)) return fail(h, B200CV_BUG_ERROR, "null positions");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->own_stream;
+  int const ng = h->self() ? 1 : 2;
+  const double *hp[2] = {h_pos1, h_pos2};
+  double *hg[2] = {h_grad1, h_grad2};
+  int rc = reset_gradients(h, s);
+  if (rc) return rc;
+  for (int k = 0; k < ng; k++) {
+    Group &G = h->g[k];
+    // SoA planes of n atoms -> padded planes of the device buffers
+    CUDA_OK(h, cudaMemcpy2DAsync(G.d_pos, sizeof(double) * G.stride, hp[k],
+                                 sizeof(double) * G.n, sizeof(double) * G.n, 3,
+                                 cudaMemcpyHostToDevice, s));
+    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(),
+                              s));
+  }
+  if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
+    flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
+  }
+  h->last_stream = s;
+  h->last_flags = flags;
+  h->have_calc = true;
+  h->data_read = true;
+  rc = enqueue_calc(h, flags, s);
+  if (rc) return rc;
+  rc = sync_and_check(h);
+  if (rc) return rc;
+  *value = *h->h_value;
+  if (flags & B200CV_EF_GRADIENTS) {
+    if (h->h_stage_count < h->reduce_count) {
+      if (h->h_stage_grad) cudaFreeHost(h->h_stage_grad);
+      h->h_stage_grad = nullptr;
+      CUDA_OK(h, cudaHostAlloc(&h->h_stage_grad, sizeof(double) * h->reduce_count,
+                               cudaHostAllocDefault));
+      h->h_stage_count = h->reduce_count;
+    }
+    CUDA_OK(h, cudaMemcpyAsync(h->h_stage_grad, h->d_reduce, sizeof(double) * h->reduce_count,
+                               cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    for (int k = 0; k < ng; k++) {
+      if (!hg[k]) continue;
+      Group &G = h->g[k];
+      const double *g = h->h_stage_grad + (G.d_grad - h->d_reduce);
+      for (int d = 0; d < 3; d++) {
+        for (int i = 0; i < G.n; i++) hg[k][(size_t)d * G.n + i] += g[(size_t)d * G.stride + i];
+      }
     }
   }
   return B200CV_OK;

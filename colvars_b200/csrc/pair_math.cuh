@@ -38,7 +38,7 @@ struct PairParams {
   double l2_max;     // tolerance_l2_max (1e20 without pair list)
   int en2, ed2;      // en/2, ed/2
   int l2max_hi;      // high word of l2_max
-  int tol_hi;        // high word of tol
+  int utol_hi;       // high word of the l2 at which f0(l2) = tol
   // boundary conditions (src/colvars_system.h)
   int bc_type;       // reference enum: 0 non-periodic, 1 mixed, 2 orthogonal, 3 triclinic
   int periodic[3];
@@ -117,6 +117,21 @@ __device__ __forceinline__ bool hi_near(double a, int b_hi)
   return (unsigned)(__double2hiint(a) - b_hi + 1) <= 2u;
 }
 
+// Is this pair one that only reference-order arithmetic reproduces?  A function of l2 alone,
+// evaluated on its high word (integer pipe): |l2 - 1| < 2^-4, or -- with a pair list -- l2
+// within ~2e-6 (relative) of l2_max or of the root of f0(l2) = tolerance, the two places
+// where the reference takes a yes/no decision (src/colvarcomp_coordnums.h:203-206,256-261).
+template <bool PL> __device__ __forceinline__ bool pair_is_rare(double u, PairParams const &P)
+{
+  bool rare = near_one(u);
+  if constexpr (PL) rare = rare || hi_near(u, P.l2max_hi) || hi_near(u, P.utol_hi);
+  return rare;
+}
+
+// l2 value that switches a pair off in the specialised path: F = 2^-300, gq = 2^-400, i.e.
+// nothing at any physical scale, and exactly zero with a pair list (l2 > l2_max).
+#define B200CV_L2_OFF 1.2676506002282294e30 /* 2^100 */
+
 // EXP = 0: runtime exponents (en2, ed2 from params), general quotient form.
 // EXP = n' > 0: compile-time en/2 = n' with ed = 2*en, for which
 //   (1 - x^n') / (1 - x^2n') = 1 / (1 + x^n'),  dF/dl2 = -n' x^(n'-1) / (1 + x^n')^2
@@ -125,13 +140,17 @@ __device__ __forceinline__ bool hi_near(double a, int b_hi)
 // Output convention: G_d = c_grad[d] * gq * diff_d, F >= 0.
 //   EXP > 0 : gq = u^(n'-1) r^2,          c_grad[d] = -2 n' inv1mt inv_r0sq[d]
 //   EXP = 0 : gq = dF/dl2 (incl. inv1mt), c_grad[d] = 2 inv_r0sq[d]
+// `off` (pair is padding, masked, or queued for the exact path) must contribute nothing:
+// EXP > 0 replaces l2 by B200CV_L2_OFF up front (one select instead of two),
+// EXP = 0 zeroes F and gq at the end (its F does not decay for every exponent choice).
 template <int EXP, bool PL>
-__device__ __forceinline__ void switching_fast(double u, PairParams const &P, double &F,
-                                               double &gq, bool &rare)
+__device__ __forceinline__ void switching_fast(double u, bool off, PairParams const &P, double &F,
+                                               double &gq)
 {
-  rare = near_one(u);
   double f0;
   if constexpr (EXP > 0) {
+    static_assert(EXP <= 10, "B200CV_L2_OFF^EXP must stay finite");
+    u = off ? B200CV_L2_OFF : u;
     double const um1 = ipow<EXP - 1>(u);
     double const q = fma(um1, u, 1.0);
     double const r = fast_rcp(q);
@@ -155,13 +174,20 @@ __device__ __forceinline__ void switching_fast(double u, PairParams const &P, do
     }
   }
   if constexpr (PL) {
-    rare = rare || hi_near(u, P.l2max_hi) || hi_near(f0, P.tol_hi);
     F = fma(f0, P.inv1mt, P.ntol);
-    bool const out = (u > P.l2_max) || (F < 0.0);
-    if constexpr (EXP == 0) gq *= P.inv1mt;
+    // l2 > l2_max and F < 0 on bit patterns (both sides positive / sign bit): integer pipe
+    bool out = (__double_as_longlong(u) > __double_as_longlong(P.l2_max)) ||
+               (__double2hiint(F) < 0);
+    if constexpr (EXP == 0) {
+      gq *= P.inv1mt;
+      out = out || off;
+    }
     if (out) { F = 0.0; gq = 0.0; }
   } else {
     F = f0;
+    if constexpr (EXP == 0) {
+      if (off) { F = 0.0; gq = 0.0; }
+    }
   }
 }
 

@@ -131,6 +131,7 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
     double const zj = sz[tbase + jj];
     int const jloc = tbase + jj;
     int const jglob = item.j0 + jloc;
+    unsigned rmask = 0u;
 #pragma unroll
     for (int k = 0; k < R; k++) {
       double dx = xj - xi[k];
@@ -156,28 +157,23 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
       } else {
         u = fma(dz, dz, fma(dy, dy, dx * dx)) * P.inv_r0sq[0];
       }
-      double F, gq;
-      bool rare;
-      switching_fast<EXP, PL>(u, P, F, gq, rare);
+      // branch-free: a rare pair contributes nothing here and is remembered in a mask, so
+      // that the R pairs of this step stay one basic block for the instruction scheduler
+      bool rare = pair_is_rare<PL>(u, P);
+      bool off = rare;
       if constexpr (MASKED) {
         int const iglob = ibase + k * 32;
         bool const valid =
             (iglob < A.i_end) && (jloc < item.jn) && (!item.diag || (jglob > iglob));
-        F = valid ? F : 0.0;
-        gq = valid ? gq : 0.0;
         rare = rare && valid;
+        off = off || !valid;
       }
-      if (rare) {
-        unsigned const slot = atomicAdd(A.rare_count, 1u);
-        if (slot < A.rare_cap) {
-          A.rare[slot] = ((unsigned long long)(unsigned)(ibase + k * 32) << 32) |
-                         (unsigned long long)(unsigned)jglob;
-        }
-        F = 0.0;
-        gq = 0.0;
-      }
+      rmask |= (rare ? 1u : 0u) << k;
+      double F, gq;
+      switching_fast<EXP, PL>(u, off, P, F, gq);
       if constexpr (PL) {
-        plm[k] |= (F > 0.0 ? 1u : 0u) << t;
+        // F is +0 or positive: test the bit pattern on the integer pipe
+        plm[k] |= (__double_as_longlong(F) != 0ll ? 1u : 0u) << t;
       }
       fsum += F;
       a1x[k] = fma(gq, dx, a1x[k]);
@@ -186,6 +182,18 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
       b2x = fma(gq, dx, b2x);
       b2y = fma(gq, dy, b2y);
       b2z = fma(gq, dz, b2z);
+    }
+    if (rmask) {
+      // queue the rare pairs of this step for exact_kernel (cold path)
+      do {
+        int const k = __ffs(rmask) - 1;
+        rmask &= rmask - 1;
+        unsigned const slot = atomicAdd(A.rare_count, 1u);
+        if (slot < A.rare_cap) {
+          A.rare[slot] = ((unsigned long long)(unsigned)(ibase + k * 32) << 32) |
+                         (unsigned long long)(unsigned)jglob;
+        }
+      } while (rmask);
     }
     // the accumulators follow their atom: lane l takes over the atom lane l+1 just did
     int const src = (lane + 1) & 31;

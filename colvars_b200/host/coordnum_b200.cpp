@@ -1,0 +1,181 @@
+// coordnum_b200.cpp -- see coordnum_b200.h.  Host side of the drop-in: keyword parsing with
+// the reference's own parser, then one C-ABI call per calc_value().
+#include "coordnum_b200.h"
+
+#include <vector>
+
+#include "colvaratoms.h"
+#include "colvarproxy.h"
+#include "colvars_system.h"
+
+namespace {
+
+// read access to the cell the base class copied into cvc::boundary_conditions
+// (src/colvarcomp.cpp:461); the fields are protected in the reference
+struct boundaries_view : public cvm::system_boundary_conditions {
+  void push(b200cv_cvc *h) const
+  {
+    double const A[3] = {unit_cell_x.x, unit_cell_x.y, unit_cell_x.z};
+    double const B[3] = {unit_cell_y.x, unit_cell_y.y, unit_cell_y.z};
+    double const C[3] = {unit_cell_z.x, unit_cell_z.y, unit_cell_z.z};
+    b200cv_set_boundaries(h, periodic_x, periodic_y, periodic_z, A, B, C);
+  }
+};
+
+// the component map is a protected static of colvar
+struct component_registry : public colvar {
+  explicit component_registry(colvarmodule *m) : colvar(m) {}
+  void replace()
+  {
+    if (global_cvc_map.empty()) define_component_types();
+    global_cvc_map["coordNum"] = []() -> colvar::cvc * { return new coordnum_b200(); };
+    global_cvc_map["selfCoordNum"] = []() -> colvar::cvc * { return new selfcoordnum_b200(); };
+    global_cvc_map["groupCoord"] = []() -> colvar::cvc * { return new groupcoordnum_b200(); };
+  }
+};
+
+int set_engine_group(b200cv_cvc *h, int which, cvm::atom_group *g)
+{
+  size_t const n = g->size();
+  std::vector<int> ids(n);
+  std::vector<double> m(n);
+  for (size_t i = 0; i < n; i++) {
+    ids[i] = g->id(i);
+    m[i] = g->mass(i);
+  }
+  return b200cv_set_group(h, which, ids.data(), m.data(), (int)n);
+}
+
+}  // namespace
+
+void coordnum_b200::install(colvarmodule *cvmodule)
+{
+  component_registry reg(cvmodule);
+  reg.replace();
+}
+
+coordnum_b200::coordnum_b200() : coordnum_b200("coordNum") {}
+
+coordnum_b200::coordnum_b200(char const *function_type_in)
+{
+  set_function_type(function_type_in);
+  x.type(colvarvalue::type_scalar);
+  cvm::real const r0 = cvmodule->proxy->angstrom_to_internal(4.0);
+  r0_vec = cvm::rvector(r0, r0, r0);
+}
+
+coordnum_b200::~coordnum_b200()
+{
+  if (engine) b200cv_destroy(engine);
+}
+
+int coordnum_b200::b200_error(int code)
+{
+  return cvmodule->error(std::string(b200cv_last_error(engine)) + "\n", code);
+}
+
+int coordnum_b200::init(std::string const &conf)
+{
+  int error_code = cvc::init(conf);
+  std::string const ftype = function_type();
+  bool const is_self = (ftype == "selfCoordNum");
+  bool const is_group = (ftype == "groupCoord");
+
+  group1 = parse_group(conf, "group1");
+  if (!group1) return error_code | COLVARS_INPUT_ERROR;
+  if (group1->b_dummy) {
+    error_code |= cvmodule->error("Error: group1 may not be a dummy atom\n", COLVARS_INPUT_ERROR);
+  }
+  if (!is_self) {
+    group2 = parse_group(conf, "group2");
+    if (!group2) return error_code | COLVARS_INPUT_ERROR;
+    if (!is_group) {
+      get_keyval(conf, "group1CenterOnly", b_group1_center_only, group2->b_dummy);
+      get_keyval(conf, "group2CenterOnly", b_group2_center_only, group2->b_dummy);
+    } else {
+      b_group1_center_only = b_group2_center_only = true;
+    }
+    size_t const c1 = b_group1_center_only ? 1 : group1->size();
+    size_t const c2 = b_group2_center_only ? 1 : group2->size();
+    num_pairs = c1 * c2;
+  } else {
+    num_pairs = (group1->size() * (group1->size() - 1)) / 2;
+  }
+  init_scalar_boundaries(0.0, num_pairs);
+
+  cvm::real r0 = r0_vec[0];
+  bool const have_cutoff = get_keyval(conf, "cutoff", r0, r0);
+  if (get_keyval(conf, "cutoff3", r0_vec, r0_vec)) {
+    if (have_cutoff) {
+      error_code |= cvmodule->error(
+          "Error: cannot specify \"cutoff\" and \"cutoff3\" at the same time.\n",
+          COLVARS_INPUT_ERROR);
+    }
+  } else if (have_cutoff) {
+    r0_vec = cvm::rvector(r0, r0, r0);
+  }
+  get_keyval(conf, "expNumer", en, en);
+  get_keyval(conf, "expDenom", ed, ed);
+  if (!is_group) {
+    get_keyval(conf, "tolerance", tolerance, tolerance);
+    if (tolerance > 0) {
+      cvmodule->cite_feature("coordNum pairlist");
+      get_keyval(conf, "pairListFrequency", pairlist_freq, pairlist_freq);
+    }
+  }
+  if (error_code != COLVARS_OK) return error_code;
+
+  // everything else (exponent / frequency validation, the Newton solve for
+  // tolerance_l2_max, overlap check) happens behind the C ABI with the reference's messages
+  b200cv_config cfg;
+  b200cv_config_defaults(&cfg);
+  cfg.kind = is_self ? B200CV_SELFCOORDNUM : (is_group ? B200CV_GROUPCOORD : B200CV_COORDNUM);
+  cfg.n1 = (int)group1->size();
+  cfg.n2 = is_self ? 0 : (int)group2->size();
+  cfg.cutoff3[0] = r0_vec.x;
+  cfg.cutoff3[1] = r0_vec.y;
+  cfg.cutoff3[2] = r0_vec.z;
+  cfg.exp_numer = en;
+  cfg.exp_denom = ed;
+  cfg.group1_center_only = b_group1_center_only;
+  cfg.group2_center_only = b_group2_center_only;
+  cfg.tolerance = tolerance;
+  cfg.pairlist_freq = pairlist_freq;
+  cfg.device = 0;
+  int rc = b200cv_create(&cfg, &engine);
+  if (rc != B200CV_OK) {
+    return error_code | cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
+  }
+  if (!is_self && group2->b_dummy) {
+    return error_code | cvmodule->error("Error: dummy atoms are not supported by the B200 "
+                                        "coordination-number engine.\n", COLVARS_NOT_IMPLEMENTED);
+  }
+  rc = set_engine_group(engine, 1, group1);
+  if (rc == B200CV_OK && !is_self) rc = set_engine_group(engine, 2, group2);
+  if (rc != B200CV_OK) return error_code | b200_error(rc);
+  return error_code;
+}
+
+void coordnum_b200::calc_value()
+{
+  // compute_coordnum (src/colvarcomp_coordnums.cpp:251-271): flags for this step
+  int flags = is_enabled(f_cvc_gradient) ? B200CV_EF_GRADIENTS : B200CV_EF_NULL;
+  if (tolerance > 0 && function_type() != "groupCoord") {
+    flags |= B200CV_EF_USE_PAIRLIST;
+    if (cvmodule->step_relative() % pairlist_freq == 0) flags |= B200CV_EF_REBUILD_PAIRLIST;
+  }
+  static_cast<boundaries_view const &>(boundary_conditions).push(engine);
+  // group arrays are SoA x..x y..y z..z (src/colvaratoms.h:556-584); read_data() has
+  // already gathered (and fitted) them, gradients accumulate on top of its zeros
+  const double *p2 = group2 ? &group2->pos_x(0) : nullptr;
+  double *g2 = group2 ? &group2->grad_x(0) : nullptr;
+  x.real_value = 0.0;
+  int const rc = b200cv_eval_host(engine, &group1->pos_x(0), p2, flags, &group1->grad_x(0), g2,
+                                  &x.real_value);
+  if (rc != B200CV_OK) b200_error(rc);
+}
+
+void coordnum_b200::calc_gradients()
+{
+  // produced by calc_value(), as in the reference (src/colvarcomp_coordnums.cpp:316-319)
+}

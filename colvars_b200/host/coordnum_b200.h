@@ -1,0 +1,61 @@
+// coordnum_b200.h -- `colvar::cvc` components that run the coordination-number hot path on a
+// B200 through the C ABI of include/b200cv.h.
+//
+// Drop-in for colvar::coordnum / selfcoordnum / groupcoordnum
+// (src/colvarcomp_coordnums.h:23-141 of the Colvars tree): same configuration keywords, same
+// error messages, same `cvc` virtuals (init / calc_value / calc_gradients; read_data,
+// calc_fit_gradients, debug_gradients and apply_force are the base-class ones and keep
+// working because group positions are read from, and gradients written to, the reference's own
+// cvm::atom_group arrays).  Compiles only against the unmodified Colvars headers.
+#ifndef COORDNUM_B200_H
+#define COORDNUM_B200_H
+
+#include <string>
+
+#include "colvarmodule.h"
+#include "colvar.h"
+#include "colvarcomp.h"
+
+#include "b200cv.h"
+
+class coordnum_b200 : public colvar::cvc {
+public:
+  coordnum_b200();
+  ~coordnum_b200() override;
+  int init(std::string const &conf) override;
+  void calc_value() override;
+  void calc_gradients() override;
+
+  /// Replace the factories of "coordNum", "selfCoordNum" and "groupCoord" in
+  /// colvar::global_cvc_map (src/colvar.cpp:822-830, :908-910).  Call once after the
+  /// colvarmodule exists and before the first configuration is parsed.
+  static void install(colvarmodule *cvmodule);
+
+protected:
+  explicit coordnum_b200(char const *function_type_in);
+  int b200_error(int code);
+
+  cvm::atom_group *group1 = nullptr;
+  cvm::atom_group *group2 = nullptr;
+  cvm::rvector r0_vec;
+  int en = 6;
+  int ed = 12;
+  bool b_group1_center_only = false;
+  bool b_group2_center_only = false;
+  cvm::real tolerance = 0.0;
+  int pairlist_freq = 100;
+  size_t num_pairs = 0;
+  b200cv_cvc *engine = nullptr;
+};
+
+class selfcoordnum_b200 : public coordnum_b200 {
+public:
+  selfcoordnum_b200() : coordnum_b200("selfCoordNum") {}
+};
+
+class groupcoordnum_b200 : public coordnum_b200 {
+public:
+  groupcoordnum_b200() : coordnum_b200("groupCoord") {}
+};
+
+#endif

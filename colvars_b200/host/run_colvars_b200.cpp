@@ -1,0 +1,57 @@
+// run_colvars_b200.cpp -- functional-test runner: the unmodified Colvars library + stub proxy
+// with the three coordination-number components replaced by the B200 ones.  Same command
+// line and same output files as the reference's tests/functional/run_colvars_test
+// (-c config -t trajectory.xyz -o prefix [--force]), so the reference's golden files apply.
+#include <fstream>
+#include <iostream>
+#include <string>
+
+#include "colvarmodule.h"
+#include "colvarproxy.h"
+#include "colvarproxy_stub.h"
+
+#include "coordnum_b200.h"
+
+int main(int argc, char **argv)
+{
+  std::string config, traj, prefix;
+  bool forces = false;
+  for (int a = 1; a < argc; a++) {
+    std::string const s = argv[a];
+    if ((s == "-c" || s == "--configuration_file") && a + 1 < argc) config = argv[++a];
+    else if ((s == "-t" || s == "--trajectory_file") && a + 1 < argc) traj = argv[++a];
+    else if ((s == "-o" || s == "--output_prefix") && a + 1 < argc) prefix = argv[++a];
+    else if (s == "--force") forces = true;
+  }
+  if (config.empty() || traj.empty()) {
+    std::cerr << "usage: run_colvars_b200 -c test.in -t trajectory.xyz [-o prefix [--force]]\n";
+    return 2;
+  }
+  colvarproxy_stub *proxy = new colvarproxy_stub();
+  colvarmodule *cvmodule = proxy->cvmodule;
+  int err = proxy->set_unit_system("real", false);
+  if (!prefix.empty()) err |= proxy->set_output_prefix(prefix);
+  err |= cvmodule->setup_input();
+  err |= cvmodule->setup_output();
+  coordnum_b200::install(cvmodule);  // <-- the only difference from the reference runner
+  err |= cvmodule->read_config_file(config.c_str());
+
+  std::ifstream ifs(traj);
+  int natoms = 0;
+  ifs >> natoms;
+  ifs.close();
+  for (int ai = 0; ai < natoms; ai++) proxy->init_atom(ai + 1);
+  int io_err = 0;
+  while (!io_err) {
+    io_err = proxy->read_frame_xyz(traj.c_str(), forces && !prefix.empty());
+  }
+  proxy->post_run();
+  double const max_gradient_error = cvmodule->get_max_gradient_error();
+  if (max_gradient_error > 0.) {
+    std::cout << "Max gradient error (debugGradients): " << max_gradient_error << "\n";
+    if (max_gradient_error > 1e-3) err = 1;
+  }
+  if (cvmodule->get_error()) err |= 1;
+  delete proxy;
+  return err;
+}

@@ -26,6 +26,7 @@
  *   b200cv_apply_force             cvc::apply_force -> apply_colvar_force    src/colvarcomp.cpp:568-577, src/colvaratoms.cpp:1637-1704;
  *                                  apply_colvar_force_to_proxy_kernel        src/cuda/colvaratoms_kernel.cu:434-570
  *   b200cv_eval                    coordnum::main_loop on bare arrays        src/colvarcomp_coordnums.cpp:187-248, :478-523
+ *   b200cv_eval_host               the same, atom_group host arrays (CPU proxy)     src/colvaratoms.h:556-584
  *   b200cv_calc_host / b200cv_apply_force_host
  *                                  the same step for a CPU proxy
  *                                  (AoS atoms_positions / atoms_new_colvar_forces)  src/colvarproxy.h:139-142,275-300
@@ -139,6 +140,14 @@ int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_
  * The value is retrieved with b200cv_value(). */
 int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
                 double *d_grad1, double *d_grad2, void *stream);
+
+/* Same evaluation for group arrays that live in HOST memory: atom_group::atoms_pos /
+ * atoms_grad of a CPU-proxy run (SoA double[3*n], src/colvaratoms.h:770-815), i.e. after the
+ * reference's own read_data() has gathered (and fitted) the groups.  Positions go up,
+ * gradients are ACCUMULATED into h_grad1/h_grad2 (may be NULL), the value is returned.
+ * This is the entry the `colvar::cvc` shim of colvars_b200/host calls from calc_value(). */
+int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1_soa, const double *h_pos2_soa,
+                     int flags, double *h_grad1_soa, double *h_grad2_soa, double *value);
 
 /* ---- host-buffer step (CPU proxy arrays; host<->device copies included) ---------------
  * h_proxy_pos: AoS rvector array double[3*n_proxy] (src/colvarproxy.h:275).

@@ -1,0 +1,61 @@
+"""The drop-in test: the UNMODIFIED Colvars library (parser, colvar, atom groups, harmonic
+bias, stub proxy, trajectory writer) with only the three coordination-number components
+replaced by colvars_b200/host/coordnum_b200 (-> C ABI -> CUDA).  Same command line, same
+output files and the same golden files as the reference's own functional tests
+(tests/input_files/<case>/AutoDiff, run through tests/functional/run_colvars_test); tolerance
+of the reference's comparer (tests/input_files/compare_test.sh: relative 1e-6, absolute
+1e-12).  debugGradients is on in most of these inputs, so the reference's own finite-difference
+check of our analytical gradients also has to stay below its 1e-3 threshold.
+
+The runner binary is built in the build container (it needs the reference headers) and
+travels to the GPU box prebuilt."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from . import regression as R
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+RUNNER = ROOT / "colvars_b200" / "host" / "_build" / "run_colvars_b200"
+
+
+def _close(a, b):
+    return np.all(np.abs(a - b) <= np.maximum(1e-6 * np.abs(b), 1e-12))
+
+
+@pytest.mark.parametrize("case", R.CASES)
+def test_reference_host_with_b200_components(case, tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not RUNNER.exists():
+        pytest.fail(f"{RUNNER} missing: build it with __graft_entry__.build() where "
+                    "/root/reference exists")
+    for f in ("trajectory.xyz", "index.ndx"):
+        shutil.copy(R.GOLDEN / f, tmp_path / f)
+    d = tmp_path / f"{case}_harmonic-fixed"
+    d.mkdir()
+    shutil.copy(R.GOLDEN / f"{case}_harmonic-fixed" / "test.in", d / "test.in")
+    r = subprocess.run([str(RUNNER), "-c", f"{d.name}/test.in", "-t", "trajectory.xyz", "-o",
+                        f"{d.name}/test_out", "--force"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    gold = R.GOLDEN / f"{case}_harmonic-fixed" / "AutoDiff"
+    traj = np.loadtxt(d / "test_out.colvars.traj", comments="#")
+    gtraj = np.loadtxt(gold / "test_out.colvars.traj", comments="#")
+    assert traj.shape == gtraj.shape and _close(traj, gtraj), (traj, gtraj)
+    for k in range(5):
+        f = np.loadtxt(d / f"test_out_forces_{k}.dat")
+        g = np.loadtxt(gold / f"test_out_forces_{k}.dat")
+        assert f.shape == g.shape and _close(f, g)
+    # the printed text itself should agree on (nearly) every number
+    same = sum(a == b for a, b in zip((d / "test_out.colvars.traj").read_text().split(),
+                                      (gold / "test_out.colvars.traj").read_text().split()))
+    total = len((gold / "test_out.colvars.traj").read_text().split())
+    assert same >= total - 2, (same, total)
+    if "debugGradients" in (d / "test.in").read_text():
+        assert "Max gradient error" in r.stdout
