@@ -14,7 +14,8 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb200cv.so"
+# B200CV_LIB selects another build of the same library (kernel-geometry experiments)
+LIB_PATH = Path(os.environ.get("B200CV_LIB", _HERE / "libb200cv.so"))
 
 OK = 0
 ERROR = 1

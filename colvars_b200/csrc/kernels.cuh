@@ -5,8 +5,18 @@
 namespace b200cv {
 
 // sweep geometry (compile-time): R register atoms per lane, W warps per CTA
-constexpr int SWEEP_R = 8;
-constexpr int SWEEP_W = 4;
+#ifndef B200CV_SWEEP_R
+#define B200CV_SWEEP_R 8
+#endif
+#ifndef B200CV_SWEEP_W
+#define B200CV_SWEEP_W 4
+#endif
+#ifndef B200CV_SWEEP_MINB
+#define B200CV_SWEEP_MINB 1
+#endif
+constexpr int SWEEP_R = B200CV_SWEEP_R;
+constexpr int SWEEP_W = B200CV_SWEEP_W;
+constexpr int SWEEP_MINB = B200CV_SWEEP_MINB;  // CTAs per SM the register allocation targets
 constexpr int SWEEP_IB = SWEEP_W * 32 * SWEEP_R;  // group1 atoms per work item (1024)
 
 // Launch the tile sweep over `nitems` work items.  exp_special = n' when ed == 2*en and a

@@ -37,7 +37,10 @@
 
 namespace b200cv {
 
-constexpr int JCMAX = 1024;  // group2 atoms per chunk (24 KB coordinates + 24 KB accumulators)
+#ifndef B200CV_JCMAX
+#define B200CV_JCMAX 1024
+#endif
+constexpr int JCMAX = B200CV_JCMAX;  // group2 atoms per chunk (24 B coordinates + 24 B accumulators each)
 
 struct SweepItem {
   int i0;    // first group1 atom of the block
@@ -106,7 +109,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
       : "memory");
 }
 
+// ---- pair geometry -------------------------------------------------------------------------
+template <bool ANISO, int PBC>
+__device__ __forceinline__ double pair_l2(PairParams const &P, double &dx, double &dy, double &dz)
+{
+  if constexpr (PBC == BC_ORTHO) {
+    // position_distance, orthogonal cell (src/colvars_system.h:176-184): the image index is
+    // computed in the reference's operation order so that ties break identically
+    double const shx = floor(__dadd_rn(__dmul_rn(P.recip[0][0], dx), 0.5));
+    double const shy = floor(__dadd_rn(__dmul_rn(P.recip[1][1], dy), 0.5));
+    double const shz = floor(__dadd_rn(__dmul_rn(P.recip[2][2], dz), 0.5));
+    dx = fma(-shx, P.cell[0][0], dx);
+    dy = fma(-shy, P.cell[1][1], dy);
+    dz = fma(-shz, P.cell[2][2], dz);
+  }
+  if constexpr (ANISO) {
+    double const sx_ = dx * P.inv_r0[0];
+    double const sy_ = dy * P.inv_r0[1];
+    double const sz_ = dz * P.inv_r0[2];
+    return fma(sz_, sz_, fma(sy_, sy_, sx_ * sx_));
+  } else {
+    return fma(dz, dz, fma(dy, dy, dx * dx)) * P.inv_r0sq[0];
+  }
+}
+
 // ---- one 32-atom tile ---------------------------------------------------------------------
+// Two ways of keeping rare pairs out of the fast sums:
+//  * SELECT (masked tiles, pair-list sweeps, runtime exponents): per pair, test l2 and switch
+//    the pair off before it is evaluated;
+//  * UNDO (specialised exponents, no pair list, interior tiles -- the benchmark path): per pair
+//    only fold the high word of l2 into a running minimum (2 integer instructions);
+//    evaluate and accumulate every pair; if the step saw a rare pair (about 1 step in 5000 at
+//    water density) a cold block re-evaluates it, subtracts it again and queues it.  The
+//    specialised form 1/(1+l2^n') is finite and smooth at l2 = 1, so adding and removing a
+//    pair costs one rounding of the running sums and nothing else.  The FP64 pipe holds the
+//    issue port for 2-3 cycles per instruction and nothing co-issues with it on sm_100
+//    (tools/ubench_fp64.cu), so every integer instruction removed from the pair is time.
 template <int EXP, bool ANISO, int PBC, bool PL, int R, bool MASKED>
 __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &item, int tile,
                                            int lane, int ibase, const double *__restrict__ sx,
@@ -116,74 +154,102 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
                                            const double (&zi)[R], double (&a1x)[R],
                                            double (&a1y)[R], double (&a1z)[R], double &fsum)
 {
+  constexpr bool UNDO = (EXP > 0) && !PL && !MASKED;
   PairParams const &P = A.P;
   double b2x = 0.0, b2y = 0.0, b2z = 0.0;
   unsigned plm[R];
 #pragma unroll
   for (int k = 0; k < R; k++) plm[k] = 0u;
   int const tbase = tile * 32;
+  const double *__restrict__ px = sx + tbase;
+  const double *__restrict__ py = sy + tbase;
+  const double *__restrict__ pz = sz + tbase;
 
 #pragma unroll 1
   for (int t = 0; t < 32; t++) {
     int const jj = (lane + t) & 31;
-    double const xj = sx[tbase + jj];
-    double const yj = sy[tbase + jj];
-    double const zj = sz[tbase + jj];
+    double const xj = px[jj];
+    double const yj = py[jj];
+    double const zj = pz[jj];
     int const jloc = tbase + jj;
     int const jglob = item.j0 + jloc;
     unsigned rmask = 0u;
+    if constexpr (UNDO) {
+      unsigned nearest = 0xffffffffu;  // min over the step of (hi(l2) - hi(1 - 2^-4)), unsigned
 #pragma unroll
-    for (int k = 0; k < R; k++) {
-      double dx = xj - xi[k];
-      double dy = yj - yi[k];
-      double dz = zj - zi[k];
-      if constexpr (PBC == BC_ORTHO) {
-        // position_distance, orthogonal cell (src/colvars_system.h:176-184): the image
-        // index is computed in the reference's operation order so that ties break
-        // identically
-        double const shx = floor(__dadd_rn(__dmul_rn(P.recip[0][0], dx), 0.5));
-        double const shy = floor(__dadd_rn(__dmul_rn(P.recip[1][1], dy), 0.5));
-        double const shz = floor(__dadd_rn(__dmul_rn(P.recip[2][2], dz), 0.5));
-        dx = fma(-shx, P.cell[0][0], dx);
-        dy = fma(-shy, P.cell[1][1], dy);
-        dz = fma(-shz, P.cell[2][2], dz);
+      for (int k = 0; k < R; k++) {
+        double dx = xj - xi[k];
+        double dy = yj - yi[k];
+        double dz = zj - zi[k];
+        double const u = pair_l2<ANISO, PBC>(P, dx, dy, dz);
+        nearest = min(nearest, (unsigned)(__double2hiint(u) - 0x3FEE0000));
+        double F, gq;
+        switching_fast<EXP, false>(u, false, P, F, gq);
+        fsum += F;
+        a1x[k] = fma(gq, dx, a1x[k]);
+        b2x = fma(gq, dx, b2x);
+        a1y[k] = fma(gq, dy, a1y[k]);
+        b2y = fma(gq, dy, b2y);
+        a1z[k] = fma(gq, dz, a1z[k]);
+        b2z = fma(gq, dz, b2z);
       }
-      double u;
-      if constexpr (ANISO) {
-        double const sx_ = dx * P.inv_r0[0];
-        double const sy_ = dy * P.inv_r0[1];
-        double const sz_ = dz * P.inv_r0[2];
-        u = fma(sz_, sz_, fma(sy_, sy_, sx_ * sx_));
-      } else {
-        u = fma(dz, dz, fma(dy, dy, dx * dx)) * P.inv_r0sq[0];
+      if (__builtin_expect(nearest < 0x30000u, 0)) {
+        // cold: some pair of this step has |l2 - 1| < 2^-4.  Take it out again.
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          double dx = xj - xi[k];
+          double dy = yj - yi[k];
+          double dz = zj - zi[k];
+          double const u = pair_l2<ANISO, PBC>(P, dx, dy, dz);
+          if (near_one(u)) {
+            double F, gq;
+            switching_fast<EXP, false>(u, false, P, F, gq);
+            fsum -= F;
+            a1x[k] = fma(-gq, dx, a1x[k]);
+            b2x = fma(-gq, dx, b2x);
+            a1y[k] = fma(-gq, dy, a1y[k]);
+            b2y = fma(-gq, dy, b2y);
+            a1z[k] = fma(-gq, dz, a1z[k]);
+            b2z = fma(-gq, dz, b2z);
+            rmask |= 1u << k;
+          }
+        }
       }
-      // branch-free: a rare pair contributes nothing here and is remembered in a mask, so
-      // that the R pairs of this step stay one basic block for the instruction scheduler
-      bool rare = pair_is_rare<PL>(u, P);
-      bool off = rare;
-      if constexpr (MASKED) {
-        int const iglob = ibase + k * 32;
-        bool const valid =
-            (iglob < A.i_end) && (jloc < item.jn) && (!item.diag || (jglob > iglob));
-        rare = rare && valid;
-        off = off || !valid;
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        double dx = xj - xi[k];
+        double dy = yj - yi[k];
+        double dz = zj - zi[k];
+        double const u = pair_l2<ANISO, PBC>(P, dx, dy, dz);
+        // branch-free: a rare pair contributes nothing here and is remembered in a mask, so
+        // that the R pairs of this step stay one basic block for the instruction scheduler
+        bool rare = pair_is_rare<PL>(u, P);
+        bool off = rare;
+        if constexpr (MASKED) {
+          int const iglob = ibase + k * 32;
+          bool const valid =
+              (iglob < A.i_end) && (jloc < item.jn) && (!item.diag || (jglob > iglob));
+          rare = rare && valid;
+          off = off || !valid;
+        }
+        rmask |= (rare ? 1u : 0u) << k;
+        double F, gq;
+        switching_fast<EXP, PL>(u, off, P, F, gq);
+        if constexpr (PL) {
+          // F is +0 or positive: test the bit pattern on the integer pipe
+          plm[k] |= (__double_as_longlong(F) != 0ll ? 1u : 0u) << t;
+        }
+        fsum += F;
+        a1x[k] = fma(gq, dx, a1x[k]);
+        b2x = fma(gq, dx, b2x);
+        a1y[k] = fma(gq, dy, a1y[k]);
+        b2y = fma(gq, dy, b2y);
+        a1z[k] = fma(gq, dz, a1z[k]);
+        b2z = fma(gq, dz, b2z);
       }
-      rmask |= (rare ? 1u : 0u) << k;
-      double F, gq;
-      switching_fast<EXP, PL>(u, off, P, F, gq);
-      if constexpr (PL) {
-        // F is +0 or positive: test the bit pattern on the integer pipe
-        plm[k] |= (__double_as_longlong(F) != 0ll ? 1u : 0u) << t;
-      }
-      fsum += F;
-      a1x[k] = fma(gq, dx, a1x[k]);
-      a1y[k] = fma(gq, dy, a1y[k]);
-      a1z[k] = fma(gq, dz, a1z[k]);
-      b2x = fma(gq, dx, b2x);
-      b2y = fma(gq, dy, b2y);
-      b2z = fma(gq, dz, b2z);
     }
-    if (rmask) {
+    if (__builtin_expect(rmask != 0u, 0)) {
       // queue the rare pairs of this step for exact_kernel (cold path)
       do {
         int const k = __ffs(rmask) - 1;
@@ -241,8 +307,8 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int EXP, bool ANISO, int PBC, bool PL, int R, int W>
-__global__ void __launch_bounds__(W * 32) sweep_kernel(const __grid_constant__ SweepArgs A)
+template <int EXP, bool ANISO, int PBC, bool PL, int R, int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_constant__ SweepArgs A)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);

@@ -10,7 +10,7 @@ bool sweep_has_special(int en, int ed) { return en == 6 && ed == 12; }
 template <int EXP, bool ANISO, int PBC, bool PL>
 static int launch_sweep_t(const SweepArgs &args, int nitems, cudaStream_t stream)
 {
-  auto kern = sweep_kernel<EXP, ANISO, PBC, PL, SWEEP_R, SWEEP_W>;
+  auto kern = sweep_kernel<EXP, ANISO, PBC, PL, SWEEP_R, SWEEP_W, SWEEP_MINB>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
