@@ -69,7 +69,7 @@ SYMBOLS = [
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
     "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_comm_unique_id",
-    "b200cv_comm_init", "b200cv_set_shard", "b200cv_fp64_peak", "b200cv_selftest_rcp",
+    "b200cv_comm_init", "b200cv_set_shard", "b200cv_plan_items", "b200cv_fp64_peak", "b200cv_selftest_rcp",
 ]
 
 
@@ -115,6 +115,8 @@ def load():
     L.b200cv_comm_unique_id.argtypes = [C.c_char_p]
     L.b200cv_comm_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     L.b200cv_set_shard.argtypes = [H, C.c_int, C.c_int]
+    L.b200cv_plan_items.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, sz,
+                                    C.POINTER(sz), _ip]
     L.b200cv_fp64_peak.argtypes = [C.c_int, C.c_double, _dp, _dp]
     L.b200cv_selftest_rcp.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, _dp]
     for name in SYMBOLS:
@@ -343,6 +345,23 @@ def _host_ptr(a):
     # torch CPU tensor (pinned or not)
     assert (not a.is_cuda) and a.is_contiguous() and a.dim() == 2 and a.shape[1] == 3
     return C.c_void_p(a.data_ptr()), a.shape[0]
+
+
+def plan_items(function_type, n1, n2, rank=0, world=1):
+    """Work items (i0, j0, jn, diag) this rank sweeps; pure host logic (no GPU needed)."""
+    L = load()
+    n = C.c_size_t()
+    ch = C.c_int()
+    kind = KIND_BY_NAME[function_type]
+    rc = L.b200cv_plan_items(kind, n1, n2, rank, world, None, 0, C.byref(n), C.byref(ch))
+    if rc != OK:
+        raise B200cvError(rc, "plan_items")
+    out = np.zeros((max(n.value, 1), 4), dtype=np.int32)
+    rc = L.b200cv_plan_items(kind, n1, n2, rank, world, out.ctypes.data_as(_ip), n.value,
+                             C.byref(n), C.byref(ch))
+    if rc != OK:
+        raise B200cvError(rc, "plan_items")
+    return out[:n.value], ch.value
 
 
 def comm_unique_id():

@@ -306,21 +306,22 @@ int ensure_partials(b200cv_cvc *h, int need)
   return B200CV_OK;
 }
 
-// Work items of the tile sweep for this rank: (group1 block) x (group2 chunk)
-int build_items(b200cv_cvc *h)
+// Work items of the tile sweep for one rank: (group1 block) x (group2 chunk).  Pure host
+// logic (no CUDA): also exported as b200cv_plan_items for the CPU-side sharding tests.
+void plan_items(bool self, int n1, int n2_in, int rank, int world, std::vector<SweepItem> &mine,
+                int &chunk_out)
 {
-  int const n1 = h->g[0].n;
-  int const n2 = h->self() ? n1 : h->g[1].n;
+  int const n2 = self ? n1 : n2_in;
   int const nb1 = (n1 + SWEEP_IB - 1) / SWEEP_IB;
   // chunk length: as long as possible (fewer flushes) while leaving >= ~6 CTAs per SM
-  long long const target = 148LL * 6 * h->world;
+  long long const target = 148LL * 6 * world;
   long long chunk = JCMAX;
   if ((long long)nb1 * ((n2 + JCMAX - 1) / JCMAX) < target) {
     long long const per_block = std::max(1LL, target / std::max(nb1, 1));
     chunk = (long long)round_up((size_t)((n2 + per_block - 1) / per_block), 32);
     chunk = std::min<long long>(std::max<long long>(chunk, 32LL * SWEEP_W), JCMAX);
   }
-  h->chunk = (int)chunk;
+  chunk_out = (int)chunk;
   int const nch = (n2 + (int)chunk - 1) / (int)chunk;
 
   std::vector<SweepItem> all;
@@ -331,30 +332,34 @@ int build_items(b200cv_cvc *h)
       int const j0 = c * (int)chunk;
       int const jn = std::min((int)chunk, n2 - j0);
       int diag = 0;
-      if (h->self()) {
+      if (self) {
         if (j0 + jn <= i0 + 1) continue;       // no j > i in this chunk
         diag = (j0 < i0 + SWEEP_IB) ? 1 : 0;   // overlaps the block's own rows
       }
       all.push_back(SweepItem{i0, j0, jn, diag});
     }
   }
-  std::vector<SweepItem> mine;
-  if (h->world == 1) {
+  mine.clear();
+  if (world == 1) {
     mine.swap(all);
-  } else if (!h->self() && nb1 >= h->world) {
-    // contiguous ranges of group1 blocks: this rank's group1 gradients are complete
-    int const b_lo = (int)((long long)nb1 * h->rank / h->world);
-    int const b_hi = (int)((long long)nb1 * (h->rank + 1) / h->world);
-    for (auto const &it : all) {
-      int const b = it.i0 / SWEEP_IB;
-      if (b >= b_lo && b < b_hi) mine.push_back(it);
-    }
+  } else if (!self) {
+    // equal contiguous ranges of the block-major item list: a rank owns whole group1 blocks
+    // except at the two ends of its range, and the load is balanced to one item
+    size_t const lo = all.size() * (size_t)rank / (size_t)world;
+    size_t const hi = all.size() * (size_t)(rank + 1) / (size_t)world;
+    mine.assign(all.begin() + lo, all.begin() + hi);
   } else {
-    // cyclic over the flat list (balances the selfCoordNum triangle and small group1)
+    // cyclic over the flat list (balances the selfCoordNum triangle)
     for (size_t k = 0; k < all.size(); k++) {
-      if ((int)(k % (size_t)h->world) == h->rank) mine.push_back(all[k]);
+      if ((int)(k % (size_t)world) == rank) mine.push_back(all[k]);
     }
   }
+}
+
+int build_items(b200cv_cvc *h)
+{
+  std::vector<SweepItem> mine;
+  plan_items(h->self(), h->g[0].n, h->g[1].n, h->rank, h->world, mine, h->chunk);
   free_dev(h->d_items);
   h->nitems = (int)mine.size();
   if (h->nitems > 0) {
@@ -1397,6 +1402,22 @@ int b200cv_comm_init(b200cv_cvc *h, const unsigned char id[128], int rank, int w
     return fail(h, B200CV_ERROR,
                 std::string("ncclCommInitRank: ") +
                     (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  }
+  return B200CV_OK;
+}
+
+int b200cv_plan_items(int kind, int n1, int n2, int rank, int world, int *items, size_t capacity,
+                      size_t *count, int *chunk)
+{
+  if (!count || world < 1 || rank < 0 || rank >= world || n1 < 1) return B200CV_INPUT_ERROR;
+  std::vector<SweepItem> mine;
+  int ch = 0;
+  plan_items(kind == B200CV_SELFCOORDNUM, n1, n2, rank, world, mine, ch);
+  *count = mine.size();
+  if (chunk) *chunk = ch;
+  if (items) {
+    if (capacity < mine.size()) return B200CV_MEMORY_ERROR;
+    std::memcpy(items, mine.data(), sizeof(SweepItem) * mine.size());
   }
   return B200CV_OK;
 }

@@ -185,6 +185,13 @@ int b200cv_comm_init(b200cv_cvc *h, const unsigned char id[128], int rank, int w
 /* Shard without a communicator (the caller reduces): for tests and external plumbing. */
 int b200cv_set_shard(b200cv_cvc *h, int rank, int world);
 
+/* The work-item table rank `rank` of `world` sweeps: `count` records of 4 ints
+ * {i0, j0, jn, diag} = 1024-row block of group1 x chunk [j0, j0+jn) of group2 (diag: the
+ * selfCoordNum chunk overlaps the block's own rows, so j > i is applied).  Pure host logic,
+ * needs no GPU; items == NULL only counts. */
+int b200cv_plan_items(int kind, int n1, int n2, int rank, int world, int *items,
+                      size_t capacity, size_t *count, int *chunk);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Sustained DFMA throughput of the device (the FP64 roofline denominator):
  * runs a pure dependent-chain DFMA kernel for about `target_ms` and reports TFLOP/s. */
