@@ -141,7 +141,8 @@ def cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver):
 def write_driver_input(path, w, pos1, pos2):
     """Binary case file of oracle/ref_driver.cpp."""
     kind = {"coordNum": 0, "selfCoordNum": 1, "groupCoord": 2}[w["kind"]]
-    hdr = np.array([kind, len(pos1), len(pos2), 6, 12, w.get("freq", 100), 0, 0], dtype=np.int32)
+    hdr = np.array([kind, len(pos1), len(pos2), 6, 12, w.get("freq", 100), 0, 0, 0, 0, 0, 0],
+                   dtype=np.int32)
     dbl = np.array(list(w["cutoff3"]) + [w.get("tol", 0.0)], dtype=np.float64)
     with open(path, "wb") as f:
         f.write(hdr.tobytes())

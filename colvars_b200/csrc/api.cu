@@ -938,8 +938,8 @@ int b200cv_set_fitting(b200cv_cvc *h, int which, int center, int rotate,
   if (!G.d_index) return fail(h, B200CV_INPUT_ERROR, "define the group before its fitting options");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   std::string err;
-  int rc = fit_setup(G.fit, center, rotate, fit_proxy_index, nfit, G.n, ref_pos_soa,
-                     enable_fit_gradients, err);
+  int rc = fit_setup(G.fit, center, rotate, fit_proxy_index, nfit, G.n, G.stride, G.d_index,
+                     G.h_index, ref_pos_soa, enable_fit_gradients, err);
   if (rc) return fail(h, rc, err);
   return B200CV_OK;
 }

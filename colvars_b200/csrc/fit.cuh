@@ -1,7 +1,8 @@
-// fit.cuh -- centerToReference / rotateToReference support of an atom group
-// (atom_group::calc_apply_roto_translation, calc_fit_gradients; src/colvaratoms.cpp:1127-1173,
-// 1433-1527; optimal rotation src/colvartypes.cpp:231-489; rotation derivative
-// src/colvar_rotation_derivative.h).
+// fit.cuh -- centerToReference / rotateToReference of an atom group on the device
+// (atom_group::calc_apply_roto_translation src/colvaratoms.cpp:1127-1173, calc_fit_gradients
+// :1433-1527; optimal rotation src/colvartypes.cpp:211-489; rotation derivative
+// src/colvar_rotation_derivative.h).  No host round trip: correlation matrix, 4x4
+// eigen-solve, rotation and the fit-gradient chain all run as kernels on the caller's stream.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -11,29 +12,33 @@
 namespace b200cv {
 
 struct FitState {
+  bool active = false;
   bool center = false;
   bool rotate = false;
   bool fit_gradients = false;
-  bool separate_group = false;  // fittingGroup given
-  int nfit = 0;                 // atoms in the group used for the fit
-  size_t fstride = 0;
+  bool separate = false;  // fittingGroup given
+  int nfit = 0;           // atoms of the group the fit is computed on
   int nmain = 0;
-  std::vector<int> h_fit_index;
-  int *d_fit_index = nullptr;
-  double *d_fit_pos = nullptr;       // fitting group positions (centred, rotated at the end)
-  double *d_fit_pos_unrot = nullptr; // centred, unrotated (input of the optimal rotation)
-  double *d_ref_pos = nullptr;       // centred reference positions
-  double *d_main_unrot = nullptr;    // atoms_pos_unrotated of the main group
-  double *d_fit_grad = nullptr;      // fit_gradients
-  double *d_small = nullptr;         // q[4], cog_fit[3], ref_cog[3], S/eig workspace ...
-  double *d_q = nullptr;             // alias into d_small
+  size_t mstride = 0;     // plane stride of the main group's buffers
+  size_t fstride = 0;     // plane stride of d_fit_pos / d_ref / d_fit_grad
+  std::vector<int> h_index;         // proxy slots of the fitted-on atoms (host copy)
+  int *d_fit_index = nullptr;       // separate fitting group only (owned)
+  const int *d_index = nullptr;     // slots of the fitted-on atoms on the device (owned or main's)
+  double *d_fit_pos = nullptr;      // separate fitting group positions (owned)
+  double *d_ref = nullptr;          // centred reference positions
+  double *d_main_unrot = nullptr;   // atoms_pos_unrotated of the main group
+  double *d_fit_grad = nullptr;     // fit_gradients
+  double *d_small = nullptr;        // see fit.cu for the layout
+  double *d_q = nullptr;            // = d_small (quaternion q0..q3)
   double ref_pos_cog[3] = {0, 0, 0};
-  double *h_pin = nullptr;           // pinned scratch for host-side application
+  std::vector<double> h_stage;
 };
 
 void fit_free(FitState &F);
 int fit_setup(FitState &F, int center, int rotate, const int *fit_proxy_index, int nfit,
-              int nmain, const double *ref_pos_soa, int enable_fit_gradients, std::string &err);
+              int nmain, size_t mstride, const int *d_main_index,
+              const std::vector<int> &h_main_index, const double *ref_pos_soa,
+              int enable_fit_gradients, std::string &err);
 // gather the fitting group (if separate), centre, rotate, translate: modifies d_pos
 int fit_read_and_apply(FitState &F, const double *proxy_pos, size_t pstride, int aos,
                        double *d_pos, size_t stride, int n, cudaStream_t s, std::string &err);

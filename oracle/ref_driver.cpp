@@ -15,18 +15,23 @@
 // pre-registered in atom-number order so slot k = atom k+1 = input row k.
 //
 // Input file (little endian):
-//   int32[8]  kind (0 coordNum, 1 selfCoordNum, 2 groupCoord), n1, n2, en, ed,
-//             pairListFrequency, flags, nframes (0 = 1)
+//   int32[12] kind (0 coordNum, 1 selfCoordNum, 2 groupCoord), n1, n2, en, ed,
+//             pairListFrequency, flags, nframes (0 = 1), nfit, reserved x3
 //               flags: 1 group1CenterOnly, 2 group2CenterOnly, 4 boundaries follow,
-//                      8 masses follow
+//                      8 masses follow, 16 group1 is fitted (32 centerToReference,
+//                      64 rotateToReference); nfit > 0: separate fittingGroup = the nfit
+//                      atoms after group2, nfit = 0: group1 is fitted on itself
 //   double[4] cutoff3 x, y, z, tolerance
-//   [flags&4] int32[4] periodic x y z + pad ; double[9] A, B, C
-//   [flags&8] double[n1+n2] masses
-//   nframes x double[(n1+n2)*3]   positions, AoS, group1 rows then group2 rows
+//   [flags&4]  int32[4] periodic x y z + pad ; double[9] A, B, C
+//   [flags&8]  double[P] masses            (P = n1 + n2 + nfit)
+//   [flags&16] double[nref*3] refPositions, AoS (nref = nfit or n1)
+//   nframes x double[P*3]   positions, AoS: group1 rows, group2 rows, fitting-group rows
 // Output file (--out):
 //   per frame: double value, double fa, double[n1*3] grad1 (AoS), double[n2*3] grad2,
-//              double[(n1+n2)*3] applied forces, int64 npl, uint64[npl] listed canonical
-//              indices (npl = -1 when there is no pair list or it is too large to dump)
+//              double[P*3] applied forces, int64 npl, uint64[npl] listed canonical
+//              indices (npl = -1 when there is no pair list or it is too large to dump),
+//              [flags&16] double[4] rotation quaternion, double[nref*3] fit gradients (AoS),
+//                         double[n1*3] fitted group1 positions (AoS)
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -116,7 +121,7 @@ int main(int argc, char **argv)
   }
   std::ifstream in(in_path, std::ios::binary);
   if (!in) { std::cerr << "cannot open " << in_path << "\n"; return 2; }
-  int32_t hdr[8];
+  int32_t hdr[12];
   double dbl[4];
   in.read((char *)hdr, sizeof(hdr));
   in.read((char *)dbl, sizeof(dbl));
@@ -124,7 +129,10 @@ int main(int argc, char **argv)
   size_t const n1 = hdr[1], n2 = hdr[2];
   int const en = hdr[3], ed = hdr[4], freq = hdr[5], flags = hdr[6];
   int const nframes = hdr[7] > 0 ? hdr[7] : 1;
-  size_t const P = n1 + n2;
+  size_t const nfit = hdr[8];
+  bool const fitted = flags & 16;
+  size_t const nref = fitted ? (nfit ? nfit : n1) : 0;
+  size_t const P = n1 + n2 + nfit;
   int32_t per[4] = {0, 0, 0, 0};
   double cell[9] = {0};
   if (flags & 4) {
@@ -136,6 +144,8 @@ int main(int argc, char **argv)
     masses.resize(P);
     in.read((char *)masses.data(), sizeof(double) * P);
   }
+  std::vector<double> refpos(3 * nref);
+  if (fitted) in.read((char *)refpos.data(), sizeof(double) * 3 * nref);
   std::vector<std::vector<double>> frames(nframes, std::vector<double>(3 * P));
   for (auto &f : frames) in.read((char *)f.data(), sizeof(double) * 3 * P);
   if (!in) { std::cerr << "short input file\n"; return 2; }
@@ -160,7 +170,22 @@ int main(int argc, char **argv)
     size_t const a = n1 * c / ncomp, b = n1 * (c + 1) / ncomp;
     cfg << "  " << key << " {\n";
     if (ncomp > 1) cfg << "    name c" << c << "\n";
-    cfg << "    group1 { atomNumbersRange " << range(a + 1, b) << " }\n";
+    cfg << "    group1 {\n      atomNumbersRange " << range(a + 1, b) << "\n";
+    if (fitted) {
+      cfg << "      centerToReference " << ((flags & 32) ? "yes" : "no") << "\n";
+      cfg << "      rotateToReference " << ((flags & 64) ? "yes" : "no") << "\n";
+      if (nfit) {
+        cfg << "      fittingGroup { atomNumbersRange " << range(n1 + n2 + 1, n1 + n2 + nfit)
+            << " }\n";
+      }
+      cfg << "      refPositions";
+      for (size_t r = 0; r < nref; r++) {
+        cfg << " (" << refpos[3 * r] << ", " << refpos[3 * r + 1] << ", " << refpos[3 * r + 2]
+            << ")";
+      }
+      cfg << "\n";
+    }
+    cfg << "    }\n";
     if (!self) cfg << "    group2 { atomNumbersRange " << range(n1 + 1, n1 + n2) << " }\n";
     if (dbl[0] == dbl[1] && dbl[0] == dbl[2]) cfg << "    cutoff " << dbl[0] << "\n";
     else cfg << "    cutoff3 (" << dbl[0] << ", " << dbl[1] << ", " << dbl[2] << ")\n";
@@ -255,6 +280,22 @@ int main(int argc, char **argv)
       }
       out.write((const char *)&npl, 8);
       if (npl > 0) out.write((const char *)idx.data(), 8 * idx.size());
+      if (fitted) {
+        cvm::atom_group *ag1 = cv->get_cvcs()[0]->atom_groups[0];
+        cvm::quaternion const qq = ag1->rot.q;
+        double const qv[4] = {qq.q0, qq.q1, qq.q2, qq.q3};
+        out.write((const char *)qv, 32);
+        cvm::atom_group *fg = ag1->fitting_group ? ag1->fitting_group : ag1;
+        for (size_t j = 0; j < fg->size(); j++) {
+          double const v[3] = {fg->fit_gradients_x(j), fg->fit_gradients_y(j),
+                               fg->fit_gradients_z(j)};
+          out.write((const char *)v, 24);
+        }
+        for (size_t i = 0; i < ag1->size(); i++) {
+          double const v[3] = {ag1->pos_x(i), ag1->pos_y(i), ag1->pos_z(i)};
+          out.write((const char *)v, 24);
+        }
+      }
     } else {
       std::printf("frame %d value %.17g fa %.17g\n", f, value, fa);
     }

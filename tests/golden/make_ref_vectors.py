@@ -30,8 +30,11 @@ def write_case(path, c, frames):
         flags |= 4
     if c.get("masses") is not None:
         flags |= 8
+    if c.get("fit"):
+        flags |= 16 | (32 if c["fit"]["center"] else 0) | (64 if c["fit"]["rotate"] else 0)
+    nfit = c.get("nfit", 0)
     hdr = np.array([KIND[c["kind"]], c["n1"], c["n2"], c["en"], c["ed"], c["freq"], flags,
-                    len(frames)], dtype=np.int32)
+                    len(frames), nfit, 0, 0, 0], dtype=np.int32)
     dbl = np.array(list(c["cutoff3"]) + [c["tol"]], dtype=np.float64)
     with open(path, "wb") as f:
         f.write(hdr.tobytes())
@@ -41,13 +44,17 @@ def write_case(path, c, frames):
             f.write(np.asarray(c["cell"], dtype=np.float64).tobytes())
         if flags & 8:
             f.write(np.asarray(c["masses"], dtype=np.float64).tobytes())
+        if flags & 16:
+            f.write(np.ascontiguousarray(c["fit"]["ref"], dtype=np.float64).tobytes())
         for fr in frames:
             f.write(np.ascontiguousarray(fr, dtype=np.float64).tobytes())
 
 
 def read_result(path, c, nframes):
     n1, n2 = c["n1"], c["n2"]
-    P = n1 + n2
+    nfit = c.get("nfit", 0)
+    P = n1 + n2 + nfit
+    nref = (nfit or n1) if c.get("fit") else 0
     raw = open(path, "rb").read()
     off = 0
     out = []
@@ -64,8 +71,16 @@ def read_result(path, c, nframes):
         off += 8
         idx = np.frombuffer(raw, np.uint64, max(npl, 0), off)
         off += 8 * max(npl, 0)
-        out.append(dict(value=v, fa=fa, grad1=g1.copy(), grad2=g2.copy(), forces=fo.copy(),
-                        npl=npl, pl=idx.copy()))
+        rec = dict(value=v, fa=fa, grad1=g1.copy(), grad2=g2.copy(), forces=fo.copy(),
+                   npl=npl, pl=idx.copy())
+        if nref:
+            rec["q"] = np.frombuffer(raw, np.float64, 4, off).copy()
+            off += 32
+            rec["fitgrad"] = np.frombuffer(raw, np.float64, 3 * nref, off).reshape(nref, 3).copy()
+            off += 24 * nref
+            rec["fitted1"] = np.frombuffer(raw, np.float64, 3 * n1, off).reshape(n1, 3).copy()
+            off += 24 * n1
+        out.append(rec)
     return out
 
 
@@ -78,6 +93,16 @@ def run_reference(c, frames, threads=1):
         if r.returncode != 0:
             raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
         return read_result(outp, c, len(frames))
+
+
+def rot(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    q0, q1, q2, q3 = q
+    return np.array([
+        [q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, 2 * (q1 * q2 - q0 * q3), 2 * (q0 * q2 + q1 * q3)],
+        [2 * (q0 * q3 + q1 * q2), q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, 2 * (q2 * q3 - q0 * q1)],
+        [2 * (q1 * q3 - q0 * q2), 2 * (q0 * q1 + q2 * q3), q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3]])
 
 
 def cases():
@@ -112,8 +137,19 @@ def cases():
                                                      nframes=4)
     out["groupcoord_masses_aniso"] = dict(base, kind="groupCoord", n1=33, n2=47, L=5.0,
                                           cutoff3=(3.0, 6.0, 4.0), masses=True)
+    # fitting (config 4): group1 centred / rotated onto reference positions
+    out["fit_self_center_rotate_aniso"] = dict(base, kind="coordNum", n1=60, n2=300, L=14.0,
+                                               cutoff3=(3.0, 6.0, 4.0), nframes=3,
+                                               fit=dict(center=True, rotate=True))
+    out["fit_group_center_rotate"] = dict(base, kind="coordNum", n1=50, n2=250, L=13.0, nfit=40,
+                                          nframes=3, fit=dict(center=True, rotate=True))
+    out["fit_group_center_only"] = dict(base, kind="coordNum", n1=45, n2=200, L=12.0, nfit=30,
+                                        fit=dict(center=True, rotate=False))
+    out["fit_self_rotate_only_selfcoordnum"] = dict(base, kind="selfCoordNum", n1=120, n2=0,
+                                                    L=11.0, cutoff3=(3.0, 5.0, 4.0),
+                                                    fit=dict(center=False, rotate=True))
     for name, c in out.items():
-        P = c["n1"] + c["n2"]
+        P = c["n1"] + c["n2"] + c.get("nfit", 0)
         L = c.pop("L")
         nf = c.pop("nframes", 1)
         f0 = pos(P, L)
@@ -122,6 +158,23 @@ def cases():
             frames.append(frames[-1] + rng.normal(0, 0.08, f0.shape))
         if c["masses"] is True:
             c["masses"] = rng.random(P) * 15.0 + 1.0
+        if c.get("fit"):
+            n1, n2, nfit = c["n1"], c["n2"], c.get("nfit", 0)
+            fitrows = slice(n1 + n2, P) if nfit else slice(0, n1)
+            # reference structure = frame 0 of the fitted atoms, moved and rotated elsewhere;
+            # later frames: rigid rotation + noise of those atoms (and of group1)
+            Rm = rot(rng)
+            c["fit"]["ref"] = (f0[fitrows] - f0[fitrows].mean(0)) @ Rm.T + np.array([3.0, -2.0, 5.0])
+            new = []
+            for fr in frames:
+                fr = fr.copy()
+                Rk = rot(rng)
+                ctr = fr[fitrows].mean(0)
+                for rows in ({(0, n1), (fitrows.start, fitrows.stop)}):
+                    a, b = rows
+                    fr[a:b] = (fr[a:b] - ctr) @ Rk.T + ctr + rng.normal(0, 0.05, (b - a, 3))
+                new.append(fr)
+            frames = new
         yield name, c, frames
 
 
@@ -139,6 +192,11 @@ def main():
             arrs["periodic"] = np.array(c["periodic"])
         if c["masses"] is not None:
             arrs["masses"] = np.array(c["masses"])
+        if c.get("fit"):
+            arrs["nfit"] = c.get("nfit", 0)
+            arrs["fit_center"] = c["fit"]["center"]
+            arrs["fit_rotate"] = c["fit"]["rotate"]
+            arrs["fit_ref"] = np.array(c["fit"]["ref"])
         for k, r in enumerate(res):
             arrs[f"value_{k}"] = r["value"]
             arrs[f"fa_{k}"] = r["fa"]
@@ -147,6 +205,10 @@ def main():
             arrs[f"forces_{k}"] = r["forces"]
             arrs[f"npl_{k}"] = r["npl"]
             arrs[f"pl_{k}"] = r["pl"]
+            if "q" in r:
+                arrs[f"q_{k}"] = r["q"]
+                arrs[f"fitgrad_{k}"] = r["fitgrad"]
+                arrs[f"fitted1_{k}"] = r["fitted1"]
         np.savez_compressed(OUT / f"{name}.npz", **arrs)
         print(f"{name}: {len(frames)} frame(s), value[0] = {res[0]['value']:.15g}, "
               f"npl[0] = {res[0]['npl']}")

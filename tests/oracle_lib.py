@@ -29,6 +29,18 @@ class Boundaries(C.Structure):
     ]
 
 
+class FitState(C.Structure):
+    _fields_ = [
+        ("center", C.c_int), ("rotate", C.c_int), ("center_origin", C.c_int),
+        ("q", C.c_double * 4),
+        ("R", (C.c_double * 3) * 3),
+        ("eigval", C.c_double * 4),
+        ("eigvec", (C.c_double * 4) * 4),
+        ("S", (C.c_double * 4) * 4),
+        ("ref_pos_cog", C.c_double * 3),
+    ]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("inv_r0", C.c_double * 3),
@@ -89,8 +101,63 @@ def lib():
     L.cvo_set_weighted_gradient.argtypes = [C.c_size_t, _dp, _dp, _dp]
     L.cvo_apply_colvar_force.argtypes = [C.c_size_t, C.POINTER(C.c_int), _dp, C.c_double, _dp,
                                          _dp]
+    L.cvo_apply_roto_translation.argtypes = [C.POINTER(FitState), C.c_size_t, _dp, _dp, C.c_size_t,
+                                             _dp, _dp]
+    L.cvo_calc_fit_gradients.argtypes = [C.POINTER(FitState), C.c_size_t, _dp, _dp, C.c_size_t,
+                                         _dp, _dp, _dp]
     _lib = L
     return L
+
+
+class Fit:
+    """centerToReference / rotateToReference of one group (atom_group::parse_fitting_options,
+    center_ref_pos: src/colvaratoms.cpp:815-934,1186-1211)."""
+
+    def __init__(self, ref_pos, center=True, rotate=True):
+        ref = np.asarray(ref_pos, dtype=np.float64)
+        self.nref = len(ref)
+        # center_ref_pos: sequential sum, divide, subtract
+        cog = np.zeros(3)
+        for r in ref:
+            cog += r
+        cog /= self.nref
+        self.ref_centered = soa(ref - cog)
+        self.fs = FitState()
+        self.fs.center, self.fs.rotate, self.fs.center_origin = int(center), int(rotate), 0
+        for d in range(3):
+            self.fs.ref_pos_cog[d] = cog[d]
+
+    def apply(self, pos_main, pos_fit=None):
+        """Returns (fitted main (n,3), main unrotated SoA, fitted fit-group positions or None)."""
+        L = lib()
+        n = len(pos_main)
+        pm = soa(pos_main)
+        un = np.zeros(3 * n)
+        if pos_fit is None:
+            L.cvo_apply_roto_translation(C.byref(self.fs), n, _ptr(pm), _ptr(un), 0, None,
+                                         _ptr(self.ref_centered))
+            return unsoa(pm, n), un, None
+        nf = len(pos_fit)
+        pf = soa(pos_fit)
+        L.cvo_apply_roto_translation(C.byref(self.fs), n, _ptr(pm), _ptr(un), nf, _ptr(pf),
+                                     _ptr(self.ref_centered))
+        return unsoa(pm, n), un, unsoa(pf, nf)
+
+    def fit_gradients(self, grad_main, main_unrot_soa, nfit):
+        L = lib()
+        n = len(grad_main)
+        out = np.zeros(3 * nfit)
+        L.cvo_calc_fit_gradients(C.byref(self.fs), n, _ptr(soa(grad_main)), _ptr(main_unrot_soa),
+                                 nfit, None, _ptr(self.ref_centered), _ptr(out))
+        return unsoa(out, nfit)
+
+    @property
+    def q(self):
+        return np.array(list(self.fs.q))
+
+    @property
+    def R(self):
+        return np.array([[self.fs.R[a][b] for b in range(3)] for a in range(3)])
 
 
 def make_params(r0=(4.0, 4.0, 4.0), en=6, ed=12, tolerance=0.0, boundaries=None):

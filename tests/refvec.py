@@ -19,6 +19,8 @@ def load(name):
     if c["kind"] == "groupCoord":  # hard-coded (src/colvarcomp_coordnums.cpp:78-82)
         c["g1c"] = c["g2c"] = True
     c["nframes"] = c["frames"].shape[0]
+    c["fitted"] = "fit_ref" in c
+    c["nfit"] = int(c["nfit"]) if c["fitted"] else 0
     return c
 
 
@@ -50,18 +52,40 @@ def run_oracle(c):
     use_pl = c["tol"] > 0 and c["kind"] != "groupCoord"
     pl = np.ones(npairs, dtype=np.uint8) if use_pl else None
     out = []
+    nfit = c["nfit"]
+    fit = None
+    if c["fitted"]:
+        fit = O.Fit(c["fit_ref"], bool(c["fit_center"]), bool(c["fit_rotate"]))
     for step in range(c["nframes"]):
         pos = c["frames"][step]
         rebuild = use_pl and step % c["freq"] == 0
+        p1 = pos[:n1]
+        extra = {}
+        if fit is not None:
+            # cvc::read_data -> calc_apply_roto_translation (src/colvaratoms.cpp:1127-1173)
+            p1, unrot, _ = fit.apply(pos[:n1], pos[n1 + n2:] if nfit else None)
         if self_:
-            v, g1 = O.selfcoordnum(p, pos[:n1], pairlist=pl, rebuild=rebuild)
+            v, g1 = O.selfcoordnum(p, p1, pairlist=pl, rebuild=rebuild)
             g2 = np.zeros((0, 3))
         else:
-            v, g1, g2 = O.coordnum(p, pos[:n1], pos[n1:], pairlist=pl, rebuild=rebuild,
+            v, g1, g2 = O.coordnum(p, p1, pos[n1:n1 + n2], pairlist=pl, rebuild=rebuild,
                                    g1_center_only=c["g1c"], g2_center_only=c["g2c"], mass1=m1,
                                    mass2=m2)
         fa = harmonic_fa(v)
-        forces = np.concatenate([fa * g1, fa * g2])
+        if fit is None:
+            forces = np.concatenate([fa * g1, fa * g2])
+        else:
+            # apply_colvar_force (src/colvaratoms.cpp:1665-1703): R^-1 grad on the main
+            # group, fit gradients on the group used for the fit
+            nf = nfit if nfit else n1
+            fg = fit.fit_gradients(g1, unrot, nf)
+            f1 = fa * (g1 @ fit.R if fit.fs.rotate else g1)   # rows: R^T g
+            forces = np.concatenate([f1, fa * g2, np.zeros((nfit, 3))])
+            if nfit:
+                forces[n1 + n2:] += fa * fg
+            else:
+                forces[:n1] += fa * fg
+            extra = dict(q=fit.q, fitgrad=fg, fitted1=p1)
         out.append(dict(value=v, fa=fa, grad1=g1, grad2=g2, forces=forces,
-                        pl=None if pl is None else np.flatnonzero(pl).astype(np.uint64)))
+                        pl=None if pl is None else np.flatnonzero(pl).astype(np.uint64), **extra))
     return out
