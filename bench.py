@@ -42,7 +42,9 @@ WORKLOADS = {
     "c3": dict(kind="selfCoordNum", n1=50000, n2=0, cutoff3=(4.0, 4.0, 4.0), tol=1e-3, freq=10,
                name="selfCoordNum 50k tolerance=1e-3 pairListFrequency=10"),
     "c4": dict(kind="coordNum", n1=10000, n2=500000, cutoff3=(3.0, 6.0, 4.0), tol=0.0, freq=100,
-               name="coordNum 10k x 500k aniso cutoff3=(3,6,4)"),
+               fit=True,
+               name="coordNum 10k x 500k aniso cutoff3=(3,6,4), group1 centerToReference + "
+                    "rotateToReference (fitted on itself, fit gradients on)"),
     "c5": dict(kind="coordNum", n1=100000, n2=1000000, cutoff3=(4.0, 4.0, 4.0), tol=0.0,
                freq=100, name="coordNum 100k x 1M iso r0=4 n=6 m=12"),
 }
@@ -112,10 +114,13 @@ def cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver):
     `smp cvcs` (the reference's documented way to use several cores)."""
     n1 = w["n1"]
     n2 = w["n2"] if w["kind"] != "selfCoordNum" else w["n1"]
-    rate_guess = 6.0e7 * threads
-    rows = int(max(min(n1, budget_s * rate_guess / n2), threads))
+    # the driver runs 1 warm-up + 2 timed calc() steps: size the slab so that the three of
+    # them take about budget_s at ~4.5e7 pair-evals/s per core
+    rate_guess = 4.5e7 * (threads if w["kind"] != "selfCoordNum" else 1)
+    per_step = budget_s / 3.0
+    rows = int(max(min(n1, per_step * rate_guess / n2), threads))
     if w["kind"] == "selfCoordNum":
-        rows = min(n1, int((2 * budget_s * rate_guess) ** 0.5))
+        rows = min(n1, int((2 * per_step * rate_guess) ** 0.5))
     with tempfile.TemporaryDirectory() as td:
         inp = Path(td) / "in.bin"
         if w["kind"] == "selfCoordNum":
@@ -124,18 +129,21 @@ def cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver):
             pos1, pos2 = proxy[i1][:rows], proxy[i2]
         write_driver_input(inp, w, pos1, pos2)
         out = subprocess.run([str(ref_driver), "--in", str(inp), "--threads", str(threads),
-                              "--steps", "3", "--time"], capture_output=True, text=True,
+                              "--steps", "2", "--time"], capture_output=True, text=True,
                              timeout=600, env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
         if out.returncode != 0:
             raise RuntimeError(out.stderr[-500:])
         res = json.loads(out.stdout.strip().splitlines()[-1])
     npairs = rows * (rows - 1) // 2 if w["kind"] == "selfCoordNum" else rows * n2
     sec = res["seconds_per_step"]
-    return dict(value=npairs / sec, unit=UNIT, cores=threads, kind="reference",
+    ncomp = int(res.get("components", 1))
+    how = (f"group1 split into {ncomp} components under smp cvcs" if ncomp > 1 else
+           "one component = one thread (the reference does not thread a single component)")
+    return dict(value=npairs / sec, unit=UNIT, cores=ncomp, kind="reference",
                 sample=f"unmodified Colvars library (oracle/_ref), colvarmodule::calc() on "
                        f"{rows} rows of group1 x {n2 if w['kind'] != 'selfCoordNum' else rows} "
-                       f"atoms ({npairs:.3g} pair-evals, {sec:.2f} s/step), group1 split into "
-                       f"{threads} components under smp cvcs, scaled linearly")
+                       f"atoms ({npairs:.3g} pair-evals, {sec:.2f} s/step), {how}, scaled "
+                       "linearly")
 
 
 def write_driver_input(path, w, pos1, pos2):
@@ -169,7 +177,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
+                 "-lms", "20", "-i", str(self.index)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -270,6 +278,16 @@ def main():
     npairs = pairs_of(w)
     cv = cb.CoordNum(w["kind"], i1, i2, cutoff3=w["cutoff3"], tolerance=w["tol"],
                      pairlist_freq=w["freq"], device=local_rank)
+    fitted = bool(w.get("fit"))
+    if fitted:
+        # refPositions = the solute as generated; the frame that is evaluated is that solute
+        # rigidly rotated about its centre plus 0.05 A noise, so the fit has real work to undo
+        ref = proxy[i1].copy()
+        cv.set_fitting(1, center=True, rotate=True, fitting_group=None, ref_pos=ref,
+                       enable_fit_gradients=True)
+        rng = np.random.default_rng(99)
+        ctr = ref.mean(0)
+        proxy[i1] = (ref - ctr) @ synth.random_rotation(7).T + ctr + rng.normal(0, 0.05, ref.shape)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -286,6 +304,8 @@ def main():
     def step(s):
         cv.read_data(d_pos, stream)
         cv.calc_value(step=s, gradients=True, stream=stream)
+        if fitted:
+            cv.calc_fit_gradients(stream)
         v = cv.value()
         cv.apply_force(k_force * (v - 0.1), d_force, stream)
         return v
@@ -298,12 +318,15 @@ def main():
     # FP64 roofline denominator, measured live (sustained, ~250 ms of pure DFMA)
     fp64_tflops, _ = cb.fp64_peak(local_rank, 250.0)
 
-    for s in range(args.warmup):
-        step(s)
-    barrier()
+    # clocks are sampled from before the warm-up (nvidia-smi needs ~0.1 s to deliver its first
+    # sample) through the end of the timed region; only samples under load are kept
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)
+    for s in range(args.warmup):
+        step(s)
+    barrier()
     ev = [(torch.cuda.Event(True), torch.cuda.Event(True), torch.cuda.Event(True),
            torch.cuda.Event(True)) for _ in range(args.steps)]
     launches = 0
@@ -317,11 +340,15 @@ def main():
         ek0.record(stream)
         cv.calc_value(step=args.warmup + s, gradients=True, stream=stream)
         ek1.record(stream)
+        if fitted:
+            cv.calc_fit_gradients(stream)
         value = cv.value()
         cv.apply_force(k_force * (value - 0.1), d_force, stream)
         e1.record(stream)
         ng = 1 if w["kind"] == "selfCoordNum" else 2
         launches += 2 * ng + cv.last_stats()[0] + ng  # gather+COM per group, calc, scatter
+        if fitted:
+            launches += 10  # cog, 2 translate, corr, eigen, rotate, fit-grad reduce/apply, scatter
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else {}

@@ -313,13 +313,24 @@ void plan_items(bool self, int n1, int n2_in, int rank, int world, std::vector<S
 {
   int const n2 = self ? n1 : n2_in;
   int const nb1 = (n1 + SWEEP_IB - 1) / SWEEP_IB;
-  // chunk length: as long as possible (fewer flushes) while leaving >= ~6 CTAs per SM
-  long long const target = 148LL * 6 * world;
+  // chunk length: the longest that still fills the machine.  CTAs run two per SM (register
+  // bound), i.e. in waves of 296 per GPU; a chunk costs (tiles + ~1.5 tiles of fixed
+  // work), the last wave is as long as a full one.  Pick the candidate with the least
+  // estimated time; big problems end up at JCMAX, a 1k x 100k problem at exactly one wave.
+  long long const slots = 148LL * 2;
   long long chunk = JCMAX;
-  if ((long long)nb1 * ((n2 + JCMAX - 1) / JCMAX) < target) {
-    long long const per_block = std::max(1LL, target / std::max(nb1, 1));
-    chunk = (long long)round_up((size_t)((n2 + per_block - 1) / per_block), 32);
-    chunk = std::min<long long>(std::max<long long>(chunk, 32LL * SWEEP_W), JCMAX);
+  double best = 1e300;
+  for (int cand = 32 * SWEEP_W; cand <= JCMAX; cand += 32) {
+    long long const nch = (n2 + cand - 1) / cand;
+    long long items = (long long)nb1 * nch;
+    if (self) items = items / 2 + nb1;  // upper triangle
+    long long const per_rank = (items + world - 1) / world;
+    long long const waves = (per_rank + slots - 1) / slots;
+    double const t = (double)waves * ((double)cand / 32.0 + 1.5);
+    if (t < best * (1.0 - 1e-9) || (t <= best * (1.0 + 1e-9) && cand > chunk)) {
+      best = t;
+      chunk = cand;
+    }
   }
   chunk_out = (int)chunk;
   int const nch = (n2 + (int)chunk - 1) / (int)chunk;

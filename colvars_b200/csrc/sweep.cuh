@@ -361,13 +361,21 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
   __syncthreads();  // accumulators zeroed
   mbar_wait(&mbar, 0);
 
-  bool const masked_item = item.diag || (item.i0 + W * 32 * R > A.i_end);
+  // rows of this warp: [iw0, iw1).  Masking (select path) is decided per warp and tile: rows
+  // beyond the group, a partial last tile, or -- selfCoordNum -- a tile that reaches into the
+  // warp's own rows (j > i has to be applied); tiles entirely at or below the rows are skipped.
+  int const iw0 = item.i0 + warp * (32 * R);
+  int const iw1 = iw0 + 32 * R;
+  bool const masked_rows = iw1 > A.i_end;
   int const tile0 = (warp * ntiles) / W;  // staggered start: warps touch different tiles
 #pragma unroll 1
   for (int tt = 0; tt < ntiles; tt++) {
     int tile = tile0 + tt;
     if (tile >= ntiles) tile -= ntiles;
-    bool const masked = masked_item || ((tile + 1) * 32 > item.jn);
+    int const jt0 = item.j0 + tile * 32;
+    if (item.diag && (jt0 + 32 <= iw0 + 1)) continue;  // no j > i in this tile for this warp
+    bool const masked =
+        masked_rows || ((tile + 1) * 32 > item.jn) || (item.diag && (jt0 < iw1));
     if (masked) {
       sweep_tile<EXP, ANISO, PBC, PL, R, true>(A, item, tile, lane, ibase, sx, sy, sz, ax, ay, az,
                                                 xi, yi, zi, a1x, a1y, a1z, fsum);
