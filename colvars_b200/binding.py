@@ -65,7 +65,7 @@ SYMBOLS = [
     "b200cv_config_defaults", "b200cv_create", "b200cv_destroy", "b200cv_last_error",
     "b200cv_set_group", "b200cv_set_fitting", "b200cv_set_boundaries", "b200cv_read_data",
     "b200cv_calc_value", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
-    "b200cv_eval", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
+    "b200cv_eval", "b200cv_eval_async", "b200cv_accumulate_gradients", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
     "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_comm_unique_id",
@@ -100,6 +100,8 @@ def load():
     L.b200cv_value.argtypes = [H, _dp]
     L.b200cv_apply_force.argtypes = [H, C.c_double, vp, sz, vp]
     L.b200cv_eval.argtypes = [H, vp, vp, C.c_int, vp, vp, vp]
+    L.b200cv_eval_async.argtypes = [H, vp, vp, C.c_int, vp, vp, vp]
+    L.b200cv_accumulate_gradients.argtypes = [H, vp, vp, vp]
     L.b200cv_eval_host.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
     L.b200cv_calc_host.argtypes = [H, vp, sz, ll, C.c_int, _dp]
     L.b200cv_apply_force_host.argtypes = [H, C.c_double, vp, sz]

@@ -136,6 +136,7 @@ struct b200cv_cvc {
   int last_flags = 0;
   bool have_calc = false;
   bool data_read = false;
+  bool async_eval = false;  // last evaluation cannot be re-run (graph capture)
   int launches = 0;
   size_t exact_pairs = 0;
 
@@ -635,6 +636,13 @@ int post_sync(b200cv_cvc *h, bool &redo)
   bool const rebuild = h->last_flags & B200CV_EF_REBUILD_PAIRLIST;
   h->exact_pairs = (size_t)rare_n;
   if (rare_n > h->rare_cap) {
+    if (h->async_eval) {
+      // a captured graph holds the queue's address: it cannot be re-allocated here
+      return fail(h, B200CV_MEMORY_ERROR,
+                  "exact-pair queue overflow in a captured evaluation (" +
+                      std::to_string(rare_n) + " pairs with |l2-1| < 1/16, capacity " +
+                      std::to_string(h->rare_cap) + "): this step's result is incomplete");
+    }
     int rc = ensure_rare_capacity(h, rare_n);
     if (rc) return rc;
     redo = true;
@@ -985,6 +993,7 @@ int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, voi
   if (!h->data_read) return fail(h, B200CV_BUG_ERROR, "calc_value before read_data");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   int const flags = calc_flags(h, step_relative, gradients);
+  h->async_eval = false;
   h->last_stream = (cudaStream_t)stream;
   h->last_step = step_relative;
   h->last_flags = flags;
@@ -1037,8 +1046,8 @@ int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_
   return B200CV_OK;
 }
 
-int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
-                double *d_grad1, double *d_grad2, void *stream)
+static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
+                       double *d_grad1, double *d_grad2, void *stream, bool sync)
 {
   if (!h) return B200CV_BUG_ERROR;
   if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
@@ -1064,17 +1073,63 @@ int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int f
   h->last_flags = flags;
   h->have_calc = true;
   h->data_read = true;
+  h->async_eval = !sync;
   rc = enqueue_calc(h, flags, s);
   if (rc) return rc;
-  // queue overflow has to be resolved before the gradients leave our buffers
-  rc = sync_and_check(h);
-  if (rc) return rc;
+  if (sync) {
+    // queue overflow has to be resolved before the gradients leave our buffers
+    rc = sync_and_check(h);
+    if (rc) return rc;
+  }
   if (flags & B200CV_EF_GRADIENTS) {
     if (d_grad1) CUDA_OK(h, launch_repack(G1.d_grad, G1.stride, d_grad1, (size_t)G1.n, G1.n, 1, s));
     if (!h->self() && d_grad2) {
       Group &G2 = h->g[1];
       CUDA_OK(h, launch_repack(G2.d_grad, G2.stride, d_grad2, (size_t)G2.n, G2.n, 1, s));
     }
+  }
+  return B200CV_OK;
+}
+
+int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
+                double *d_grad1, double *d_grad2, void *stream)
+{
+  return eval_device(h, d_pos1, d_pos2, flags, d_grad1, d_grad2, stream, true);
+}
+
+int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
+                      double *d_grad1, double *d_grad2, void *stream)
+{
+  if (h && (flags & B200CV_EF_USE_PAIRLIST) && h->cfg.tolerance > 0) {
+    return fail(h, B200CV_NOT_IMPLEMENTED,
+                "b200cv_eval_async cannot be used with a pair list (the rebuild needs a host "
+                "round trip); use b200cv_eval");
+  }
+  if (h && h->items_dirty) {
+    // allocations are not capturable: build the work-item table before any stream capture
+    CUDA_OK(h, cudaSetDevice(h->cfg.device));
+    if (!(h->center1() || h->center2())) {
+      int rc = build_items(h);
+      if (rc) return rc;
+    } else {
+      int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
+      if (rc) return rc;
+    }
+  }
+  return eval_device(h, d_pos1, d_pos2, flags, d_grad1, d_grad2, stream, false);
+}
+
+int b200cv_accumulate_gradients(b200cv_cvc *h, double *d_grad1, double *d_grad2, void *stream)
+{
+  if (!h) return B200CV_BUG_ERROR;
+  if (!h->have_calc) return fail(h, B200CV_BUG_ERROR, "accumulate_gradients before an evaluation");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Group &G1 = h->g[0];
+  if (d_grad1) CUDA_OK(h, launch_repack(G1.d_grad, G1.stride, d_grad1, (size_t)G1.n, G1.n, 1, s));
+  if (!h->self() && d_grad2) {
+    Group &G2 = h->g[1];
+    CUDA_OK(h, launch_repack(G2.d_grad, G2.stride, d_grad2, (size_t)G2.n, G2.n, 1, s));
   }
   return B200CV_OK;
 }
@@ -1104,6 +1159,7 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, 
   if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
     flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
   }
+  h->async_eval = false;
   h->last_stream = s;
   h->last_flags = flags;
   h->have_calc = true;

@@ -409,7 +409,9 @@ __global__ void repack_kernel(const double *__restrict__ src, size_t sstride, do
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     double const v = src[d * sstride + i];
-    if (accumulate) dst[d * dstride + i] += v;
+    // accumulate: the destination may be shared with other components running concurrently
+    // in the same graph (src/cuda/colvarcomp_distance_kernel.cu:137 does the same)
+    if (accumulate) atomicAdd(&dst[d * dstride + i], v);
     else dst[d * dstride + i] = v;
   }
 }

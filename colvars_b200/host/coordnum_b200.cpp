@@ -67,6 +67,9 @@ coordnum_b200::coordnum_b200(char const *function_type_in)
 coordnum_b200::~coordnum_b200()
 {
   if (engine) b200cv_destroy(engine);
+#if defined(COLVARS_CUDA)
+  if (capture_stream) cudaStreamDestroy(capture_stream);
+#endif
 }
 
 int coordnum_b200::b200_error(int code)
@@ -153,6 +156,13 @@ int coordnum_b200::init(std::string const &conf)
   rc = set_engine_group(engine, 1, group1);
   if (rc == B200CV_OK && !is_self) rc = set_engine_group(engine, 2, group2);
   if (rc != B200CV_OK) return error_code | b200_error(rc);
+#if defined(COLVARS_CUDA)
+  if (has_gpu_implementation()) {
+    // positions and gradients stay on the device (as colvar::rmsd does,
+    // src/colvarcomp_distances.cpp:930)
+    disable(f_cvc_require_cpu_buffers);
+  }
+#endif
   return error_code;
 }
 
@@ -179,3 +189,73 @@ void coordnum_b200::calc_gradients()
 {
   // produced by calc_value(), as in the reference (src/colvarcomp_coordnums.cpp:316-319)
 }
+
+
+#if defined(COLVARS_CUDA)
+
+bool coordnum_b200::has_gpu_implementation() const
+{
+  return cvmodule->proxy->get_smp_mode() == colvarproxy_smp::smp_mode_t::gpu && !(tolerance > 0);
+}
+
+namespace {
+
+// Record whatever `enqueue` puts on `stream` as nodes of `graph`
+template <typename F>
+int capture_into(cudaGraph_t &graph, cudaStream_t stream, F enqueue)
+{
+  if (cudaStreamBeginCaptureToGraph(stream, graph, nullptr, nullptr, 0,
+                                    cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    return COLVARS_ERROR;
+  }
+  int const rc = enqueue();
+  cudaGraph_t same = nullptr;
+  if (cudaStreamEndCapture(stream, &same) != cudaSuccess) return COLVARS_ERROR;
+  return rc == B200CV_OK ? COLVARS_OK : COLVARS_ERROR;
+}
+
+}  // namespace
+
+int coordnum_b200::add_calc_value_node(
+    cudaGraph_t &graph, std::unordered_map<std::string, cudaGraphNode_t> &nodes_map)
+{
+  (void)nodes_map;
+  if (!capture_stream &&
+      cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    return cvmodule->error("Error: cannot create a CUDA stream.\n", COLVARS_ERROR);
+  }
+  static_cast<boundaries_view const &>(boundary_conditions).push(engine);
+  auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
+  const double *p2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_pos : nullptr;
+  int const flags = is_enabled(f_cvc_gradient) ? B200CV_EF_GRADIENTS : B200CV_EF_NULL;
+  // gradients stay in the engine's buffers until add_calc_gradients_node hands them over:
+  // debug_gradients_gpu relaunches this graph many times (src/colvarcomp.cpp:986-996)
+  int const rc = capture_into(graph, capture_stream, [&]() {
+    return b200cv_eval_async(engine, b1.d_atoms_pos, p2, flags, nullptr, nullptr, capture_stream);
+  });
+  if (rc != COLVARS_OK) return b200_error(COLVARS_ERROR);
+  return COLVARS_OK;
+}
+
+int coordnum_b200::calc_value_after_gpu()
+{
+  // the scheduler has synchronised the stream; the scalar sits in mapped pinned memory
+  int const rc = b200cv_value(engine, &x.real_value);
+  if (rc != B200CV_OK) return b200_error(rc);
+  return COLVARS_OK;
+}
+
+int coordnum_b200::add_calc_gradients_node(
+    cudaGraph_t &graph, std::unordered_map<std::string, cudaGraphNode_t> &nodes_map)
+{
+  (void)nodes_map;
+  auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
+  double *g2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_grad : nullptr;
+  int const rc = capture_into(graph, capture_stream, [&]() {
+    return b200cv_accumulate_gradients(engine, b1.d_atoms_grad, g2, capture_stream);
+  });
+  if (rc != COLVARS_OK) return b200_error(COLVARS_ERROR);
+  return COLVARS_OK;
+}
+
+#endif  // COLVARS_CUDA

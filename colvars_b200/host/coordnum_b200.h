@@ -26,6 +26,18 @@ public:
   void calc_value() override;
   void calc_gradients() override;
 
+#if defined(COLVARS_CUDA)
+  // `smp gpu` (src/colvar_gpu_calc.cpp:268-437): this component contributes graph nodes
+  // that work on the atom groups' device buffers (colvaratoms_gpu_buffer_t).  Components
+  // with a pair list keep the CPU-buffer route (their rebuild needs a host round trip).
+  bool has_gpu_implementation() const override;
+  int add_calc_value_node(cudaGraph_t &graph,
+                          std::unordered_map<std::string, cudaGraphNode_t> &nodes_map) override;
+  int calc_value_after_gpu() override;
+  int add_calc_gradients_node(cudaGraph_t &graph,
+                              std::unordered_map<std::string, cudaGraphNode_t> &nodes_map) override;
+#endif
+
   /// Replace the factories of "coordNum", "selfCoordNum" and "groupCoord" in
   /// colvar::global_cvc_map (src/colvar.cpp:822-830, :908-910).  Call once after the
   /// colvarmodule exists and before the first configuration is parsed.
@@ -46,6 +58,9 @@ protected:
   int pairlist_freq = 100;
   size_t num_pairs = 0;
   b200cv_cvc *engine = nullptr;
+#if defined(COLVARS_CUDA)
+  cudaStream_t capture_stream = nullptr;
+#endif
 };
 
 class selfcoordnum_b200 : public coordnum_b200 {

@@ -141,6 +141,20 @@ int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_
 int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
                 double *d_grad1, double *d_grad2, void *stream);
 
+/* b200cv_eval without its internal synchronisation: only enqueues work on `stream`, so the
+ * call can sit inside a CUDA stream capture and become a child graph of the reference's
+ * calc_value graph (add_calc_value_node).  Not available with a pair list.  A queue
+ * overflow (more than 1 M pairs with |l2 - 1| < 1/16 in one evaluation) cannot be repaired
+ * in flight: b200cv_value() then returns B200CV_MEMORY_ERROR. */
+int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
+                      double *d_grad1, double *d_grad2, void *stream);
+
+/* d_grad1 / d_grad2 (d_atoms_grad layout) += the gradients of the last evaluation, with
+ * atomics (groups may be shared between components).  Only enqueues work: this is the node
+ * add_calc_gradients_node contributes when add_calc_value_node evaluated with
+ * d_grad1 = d_grad2 = NULL. */
+int b200cv_accumulate_gradients(b200cv_cvc *h, double *d_grad1, double *d_grad2, void *stream);
+
 /* Same evaluation for group arrays that live in HOST memory: atom_group::atoms_pos /
  * atoms_grad of a CPU-proxy run (SoA double[3*n], src/colvaratoms.h:770-815), i.e. after the
  * reference's own read_data() has gathered (and fitted) the groups.  Positions go up,

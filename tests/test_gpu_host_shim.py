@@ -21,17 +21,25 @@ from . import regression as R
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 RUNNER = ROOT / "colvars_b200" / "host" / "_build" / "run_colvars_b200"
+RUNNER_GPU = ROOT / "colvars_b200" / "host" / "_build" / "run_colvars_b200_gpu"
 
 
 def _close(a, b):
     return np.all(np.abs(a - b) <= np.maximum(1e-6 * np.abs(b), 1e-12))
 
 
+@pytest.mark.parametrize("route", ["cpu-proxy", "smp-gpu"])
 @pytest.mark.parametrize("case", R.CASES)
-def test_reference_host_with_b200_components(case, tmp_path):
+def test_reference_host_with_b200_components(case, route, tmp_path):
+    """route = cpu-proxy: CPU proxy arrays, components call b200cv_eval_host.
+    route = smp-gpu: the reference built with COLVARS_CUDA, device-resident proxy, the
+    reference's graph scheduler; components without a pair list contribute graph nodes
+    (b200cv_eval_async / b200cv_accumulate_gradients), those with one take the reference's
+    CPU-buffer route."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    RUNNER = RUNNER_GPU if route == "smp-gpu" else globals()["RUNNER"]
     if not RUNNER.exists():
         pytest.fail(f"{RUNNER} missing: build it with __graft_entry__.build() where "
                     "/root/reference exists")
@@ -59,3 +67,6 @@ def test_reference_host_with_b200_components(case, tmp_path):
     assert same >= total - 2, (same, total)
     if "debugGradients" in (d / "test.in").read_text():
         assert "Max gradient error" in r.stdout
+    if route == "smp-gpu":
+        on_graph = "graph route: yes" in r.stdout
+        assert on_graph == ("pairlist" not in case), r.stdout[-500:]
