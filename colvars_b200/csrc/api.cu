@@ -39,6 +39,8 @@ struct Group {
   double *d_pos = nullptr;
   double *d_grad = nullptr;     // points into the reduce buffer
   double *d_centers = nullptr;  // com[3] cog[3] com_grad[3] (+3 pad)
+  double *d_com_scratch = nullptr;       // per-CTA partials of com_cog_kernel
+  unsigned int *d_com_ticket = nullptr;  // its last-block-done counter
   std::vector<int> h_index;
   std::vector<double> h_mass;
   FitState fit;
@@ -294,6 +296,9 @@ int alloc_group(b200cv_cvc *h, Group &G, int n)
   CUDA_OK(h, cudaMemset(G.d_pos, 0, sizeof(double) * 3 * G.stride));
   CUDA_OK(h, cudaMalloc(&G.d_centers, sizeof(double) * 12));
   CUDA_OK(h, cudaMemset(G.d_centers, 0, sizeof(double) * 12));
+  CUDA_OK(h, cudaMalloc(&G.d_com_scratch, sizeof(double) * COM_SCRATCH_DOUBLES));
+  CUDA_OK(h, cudaMalloc(&G.d_com_ticket, sizeof(unsigned int)));
+  CUDA_OK(h, cudaMemset(G.d_com_ticket, 0, sizeof(unsigned int)));
   return B200CV_OK;
 }
 
@@ -797,6 +802,8 @@ int b200cv_destroy(b200cv_cvc *h)
     free_dev(G.d_weight);
     free_dev(G.d_pos);
     free_dev(G.d_centers);
+    free_dev(G.d_com_scratch);
+    free_dev(G.d_com_ticket);
     fit_free(G.fit);
   }
   free_dev(h->d_reduce);
@@ -980,8 +987,7 @@ int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stri
     rc = fit_read_and_apply(G.fit, d_proxy_pos, proxy_stride, 0, G.d_pos, G.stride, G.n, s, err);
     if (rc) return fail(h, rc, err);
     // calc_required_properties (src/colvaratoms.cpp:1325-1352)
-    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(),
-                              s));
+    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(), G.d_com_scratch, G.d_com_ticket, s));
   }
   h->data_read = true;
   return B200CV_OK;
@@ -1058,13 +1064,11 @@ static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2
   if (rc) return rc;
   Group &G1 = h->g[0];
   CUDA_OK(h, launch_repack(d_pos1, (size_t)G1.n, G1.d_pos, G1.stride, G1.n, 0, s));
-  CUDA_OK(h, launch_com_cog(G1.d_pos, G1.stride, G1.d_mass, G1.total_mass, G1.n, G1.com(),
-                            G1.cog(), s));
+  CUDA_OK(h, launch_com_cog(G1.d_pos, G1.stride, G1.d_mass, G1.total_mass, G1.n, G1.com(), G1.cog(), G1.d_com_scratch, G1.d_com_ticket, s));
   if (!h->self()) {
     Group &G2 = h->g[1];
     CUDA_OK(h, launch_repack(d_pos2, (size_t)G2.n, G2.d_pos, G2.stride, G2.n, 0, s));
-    CUDA_OK(h, launch_com_cog(G2.d_pos, G2.stride, G2.d_mass, G2.total_mass, G2.n, G2.com(),
-                              G2.cog(), s));
+    CUDA_OK(h, launch_com_cog(G2.d_pos, G2.stride, G2.d_mass, G2.total_mass, G2.n, G2.com(), G2.cog(), G2.d_com_scratch, G2.d_com_ticket, s));
   }
   if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
     flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
@@ -1153,8 +1157,7 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, 
     CUDA_OK(h, cudaMemcpy2DAsync(G.d_pos, sizeof(double) * G.stride, hp[k],
                                  sizeof(double) * G.n, sizeof(double) * G.n, 3,
                                  cudaMemcpyHostToDevice, s));
-    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(),
-                              s));
+    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(), G.d_com_scratch, G.d_com_ticket, s));
   }
   if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
     flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
@@ -1219,8 +1222,7 @@ int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
     std::string err;
     rc = fit_read_and_apply(G.fit, h->d_stage_pos, n_proxy, 1, G.d_pos, G.stride, G.n, s, err);
     if (rc) return fail(h, rc, err);
-    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(),
-                              s));
+    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(), G.d_com_scratch, G.d_com_ticket, s));
   }
   h->data_read = true;
   rc = b200cv_calc_value(h, step_relative, gradients, s);

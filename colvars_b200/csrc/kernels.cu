@@ -240,17 +240,48 @@ int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, 
   return (int)cudaGetLastError();
 }
 
-// calc_center_of_mass / calc_center_of_geometry (src/colvaratoms.cpp:1354-1395).  One CTA,
-// fixed order: thread t sums atoms t, t+1024, ...; binary tree across threads.
-__global__ void __launch_bounds__(1024) com_cog_kernel(const double *__restrict__ pos,
-                                                       size_t stride,
-                                                       const double *__restrict__ mass,
-                                                       double total_mass, int n, double *com,
-                                                       double *cog)
+// calc_center_of_mass / calc_center_of_geometry (src/colvaratoms.cpp:1354-1395; GPU twin
+// atoms_calc_cog_com_kernel, src/cuda/colvaratoms_kernel.cu:134-243).  Up to COM_BLOCKS CTAs
+// reduce a grid-strided share each into scratch[block][6]; the last CTA to finish (ticket
+// counter) sums the partials in block order, so the result does not depend on scheduling.
+constexpr int COM_BLOCKS = 296;
+constexpr int COM_THREADS = 256;
+
+__global__ void __launch_bounds__(COM_THREADS) com_cog_kernel(const double *__restrict__ pos,
+                                                              size_t stride,
+                                                              const double *__restrict__ mass,
+                                                              double total_mass, int n,
+                                                              double *com, double *cog,
+                                                              double *scratch,
+                                                              unsigned int *ticket)
 {
-  __shared__ double red[6][1024 / 32];
+  __shared__ double red[6][COM_THREADS / 32];
+  __shared__ bool last;
   double s[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < n; i += 1024) {
+  int const step = gridDim.x * COM_THREADS;
+  int i = blockIdx.x * COM_THREADS + threadIdx.x;
+  // four atoms per trip: 16 independent loads in flight per thread
+  for (; i + 3 * step < n; i += 4 * step) {
+    double m[4], x[4], y[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int const k = i + u * step;
+      m[u] = mass[k];
+      x[u] = pos[k];
+      y[u] = pos[stride + k];
+      z[u] = pos[2 * stride + k];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      s[0] = fma(m[u], x[u], s[0]);
+      s[1] = fma(m[u], y[u], s[1]);
+      s[2] = fma(m[u], z[u], s[2]);
+      s[3] += x[u];
+      s[4] += y[u];
+      s[5] += z[u];
+    }
+  }
+  for (; i < n; i += step) {
     double const m = mass[i];
     double const x = pos[i], y = pos[stride + i], z = pos[2 * stride + i];
     s[0] = fma(m, x, s[0]);
@@ -268,24 +299,53 @@ __global__ void __launch_bounds__(1024) com_cog_kernel(const double *__restrict_
     if (lane == 0) red[c][warp] = s[c];
   }
   __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      double v = red[c][lane];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      if (lane == 0) {
-        if (c < 3) com[c] = v / total_mass;
-        else cog[c - 3] = v / (double)n;
-      }
-    }
+  if (threadIdx.x < 6) {
+    double v = 0.0;
+    for (int w = 0; w < COM_THREADS / 32; w++) v += red[threadIdx.x][w];
+    scratch[blockIdx.x * 6 + threadIdx.x] = v;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // last CTA: partials of block b go to thread b % 256 (at most two per thread, loaded
+  // together), then the same fixed shuffle tree -- independent of which CTA came last
+  double t[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double v = 0.0;
+    for (unsigned bb = threadIdx.x; bb < gridDim.x; bb += COM_THREADS) {
+      v += __ldcg(&scratch[bb * 6 + c]);
+    }
+    t[c] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], d);
+    if (lane == 0) red[c][warp] = t[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = 0.0;
+    for (int w = 0; w < COM_THREADS / 32; w++) v += red[threadIdx.x][w];
+    if (threadIdx.x < 3) com[threadIdx.x] = v / total_mass;
+    else cog[threadIdx.x - 3] = v / (double)n;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch
 }
 
 int launch_com_cog(const double *pos, size_t stride, const double *mass, double total_mass,
-                   int n, double *com, double *cog, cudaStream_t stream)
+                   int n, double *com, double *cog, double *scratch, unsigned int *ticket,
+                   cudaStream_t stream)
 {
-  com_cog_kernel<<<1, 1024, 0, stream>>>(pos, stride, mass, total_mass, n, com, cog);
+  int blocks = (n + COM_THREADS * 8 - 1) / (COM_THREADS * 8);
+  blocks = blocks < 1 ? 1 : (blocks > COM_BLOCKS ? COM_BLOCKS : blocks);
+  com_cog_kernel<<<blocks, COM_THREADS, 0, stream>>>(pos, stride, mass, total_mass, n, com, cog,
+                                                     scratch, ticket);
   return (int)cudaGetLastError();
 }
 

@@ -101,9 +101,12 @@ int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
 // gather: pos[d*stride + i] = proxy[d*pstride + idx[i]]  (aos != 0: proxy[3*idx[i] + d])
 int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, int n,
                   double *pos, size_t stride, cudaStream_t stream);
-// COM = sum m x / M and COG = sum x / n in one pass (single CTA, fixed order)
+// COM = sum m x / M and COG = sum x / n in one pass (<= 296 CTAs, fixed summation order).
+// scratch: device double[296 * 6]; ticket: device counter, zero before the first launch.
+constexpr int COM_SCRATCH_DOUBLES = 296 * 6;
 int launch_com_cog(const double *pos, size_t stride, const double *mass, double total_mass,
-                   int n, double *com, double *cog, cudaStream_t stream);
+                   int n, double *com, double *cog, double *scratch, unsigned int *ticket,
+                   cudaStream_t stream);
 // pos += s * t (t in device memory, plus optional constant shift c)
 int launch_translate(double *pos, size_t stride, int n, const double *t_dev, double s,
                      cudaStream_t stream);
@@ -120,8 +123,7 @@ int launch_scatter_force(const double *grad, size_t stride, const int *idx, int 
 int launch_repack(const double *src, size_t sstride, double *dst, size_t dstride, int n,
                   int accumulate, cudaStream_t stream);
 
-// ---- fitting kernels (src/colvartypes.cpp:231-489, src/colvar_rotation_derivative.h) ----
-struct FitBuffers;  // defined in fit.cuh
+// ---- measurement helpers ------------------------------------------------------------------
 int launch_fp64_peak(double *d_out, int iters, int blocks, cudaStream_t stream);
 int launch_rcp_selftest(const double *d_x, int n, double *d_maxulp, cudaStream_t stream);
 
