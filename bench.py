@@ -244,6 +244,66 @@ def run_reference_arm(args, w):
     return 0
 
 
+def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
+    """Device-resident step of another BASELINE configuration: K timed steps, CUDA events, L2
+    flushed between steps.  Returns a small dict (pair-evals/s, ms/step, roofline fraction)."""
+    w = WORKLOADS[key]
+    proxy, i1, i2 = make_inputs(w)
+    dev = torch.device("cuda", device)
+    cv = cb.CoordNum(w["kind"], i1, i2, cutoff3=w["cutoff3"], tolerance=w["tol"],
+                     pairlist_freq=w["freq"], device=device)
+    fitted = bool(w.get("fit"))
+    if fitted:
+        ref = proxy[i1].copy()
+        cv.set_fitting(1, center=True, rotate=True, fitting_group=None, ref_pos=ref)
+        ctr = ref.mean(0)
+        proxy[i1] = (ref - ctr) @ synth.random_rotation(7).T + ctr + \
+            np.random.default_rng(99).normal(0, 0.05, ref.shape)
+    d_pos = torch.tensor(np.ascontiguousarray(proxy.T), device=dev)
+    d_force = torch.zeros_like(d_pos)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    if w["tol"] > 0:
+        steps = 2 * w["freq"]  # two full pair-list cycles
+    ev, kev = [], []
+    v = 0.0
+    for s in range(warmup + steps):
+        flush.fill_(s & 0xFF)
+        e0, k0, k1, e1 = (torch.cuda.Event(True) for _ in range(4))
+        e0.record(stream)
+        cv.read_data(d_pos, stream)
+        k0.record(stream)
+        cv.calc_value(step=s, gradients=True, stream=stream)
+        k1.record(stream)
+        if fitted:
+            cv.calc_fit_gradients(stream)
+        v = cv.value()
+        cv.apply_force(-0.004 * (v - 0.1), d_force, stream)
+        e1.record(stream)
+        if s >= warmup:
+            ev.append((e0, e1))
+            kev.append((s, k0, k1))
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    kms = [(s, a.elapsed_time(b)) for s, a, b in kev]
+    npairs = pairs_of(w)
+    out = {"workload": w["name"], "pairs_per_step": npairs, "steps": steps,
+           "value": npairs * len(ms) / (sum(ms) * 1e-3), "unit": UNIT,
+           "ms_per_step": float(np.mean(ms)), "last_value": v}
+    if w["tol"] > 0:
+        reb = [m for s, m in kms if s % w["freq"] == 0]
+        lst = [m for s, m in kms if s % w["freq"] != 0]
+        out["pairlist"] = {"rebuild_ms": float(np.mean(reb)), "list_ms": float(np.mean(lst)),
+                           "listed_pairs": int(len(cv.pairlist()))}
+        kern = float(np.mean(reb))
+    else:
+        kern = float(np.mean([m for _, m in kms]))
+    out["calc_value_ms"] = kern
+    out["roofline_frac"] = npairs / (kern * 1e-3) * synth.FLOP_PER_PAIR_VALUE_GRAD / 1e12 / fp64_tflops
+    cv.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,6 +313,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
 
@@ -447,6 +508,16 @@ def main():
             line["cpu_baseline"] = cpu_run(w, proxy, i1, i2, budget_s=12.0)
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)[:200]}
+    if world == 1 and args.workload == "c5" and not args.no_others:
+        # the other single-GPU configurations of BASELINE.json, device-resident step only
+        # (same timing rules; not the headline): BASELINE config 2 is the 1-GPU case
+        others = {}
+        for key in ("c2", "c4", "c3"):
+            try:
+                others[key] = quick_workload(cb, torch, key, local_rank, fp64_tflops)
+            except Exception as e:
+                others[key] = {"error": str(e)[:200]}
+        line["other_workloads"] = others
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
