@@ -293,7 +293,16 @@ int alloc_group(b200cv_cvc *h, Group &G, int n)
   CUDA_OK(h, cudaMalloc(&G.d_mass, sizeof(double) * std::max(n, 1)));
   CUDA_OK(h, cudaMalloc(&G.d_weight, sizeof(double) * std::max(n, 1)));
   CUDA_OK(h, cudaMalloc(&G.d_pos, sizeof(double) * 3 * G.stride));
-  CUDA_OK(h, cudaMemset(G.d_pos, 0, sizeof(double) * 3 * G.stride));
+  {
+    // padding atoms [n, stride) sit far away (-1e30; rows beyond a group use +1e30 in the
+    // sweep): finite everywhere, and invisible to the specialised path without masking
+    std::vector<double> init(3 * G.stride, 0.0);
+    for (int d = 0; d < 3; d++) {
+      for (size_t i = (size_t)n; i < G.stride; i++) init[d * G.stride + i] = -1.0e30;
+    }
+    CUDA_OK(h, cudaMemcpy(G.d_pos, init.data(), sizeof(double) * 3 * G.stride,
+                          cudaMemcpyHostToDevice));
+  }
   CUDA_OK(h, cudaMalloc(&G.d_centers, sizeof(double) * 12));
   CUDA_OK(h, cudaMemset(G.d_centers, 0, sizeof(double) * 12));
   CUDA_OK(h, cudaMalloc(&G.d_com_scratch, sizeof(double) * COM_SCRATCH_DOUBLES));

@@ -344,6 +344,11 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
     az[t] = 0.0;
   }
 
+  // On the specialised non-periodic path rows beyond the group and the padding of the last
+  // tile need no masking: they sit at +-1e30 (rows here, padding in the position buffers, see
+  // alloc_group), where 1/(1+l2^n') is ~1e-180 and the gradient factor underflows to exactly 0.
+  constexpr bool FAR_PADDING = (EXP > 0) && !PL && (PBC == BC_NONE);
+  double const row_pad = FAR_PADDING ? 1.0e30 : 0.0;
   // group1 atoms of this lane: i = ibase + 32 k
   int const ibase = item.i0 + warp * (32 * R) + lane;
   double xi[R], yi[R], zi[R], a1x[R], a1y[R], a1z[R];
@@ -351,9 +356,9 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
   for (int k = 0; k < R; k++) {
     int const i = ibase + k * 32;
     bool const ok = i < A.i_end;
-    xi[k] = ok ? A.x1[i] : 0.0;
-    yi[k] = ok ? A.y1[i] : 0.0;
-    zi[k] = ok ? A.z1[i] : 0.0;
+    xi[k] = ok ? A.x1[i] : row_pad;
+    yi[k] = ok ? A.y1[i] : row_pad;
+    zi[k] = ok ? A.z1[i] : row_pad;
     a1x[k] = a1y[k] = a1z[k] = 0.0;
   }
   double fsum = 0.0;
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
   // warp's own rows (j > i has to be applied); tiles entirely at or below the rows are skipped.
   int const iw0 = item.i0 + warp * (32 * R);
   int const iw1 = iw0 + 32 * R;
-  bool const masked_rows = iw1 > A.i_end;
+  bool const masked_rows = !FAR_PADDING && (iw1 > A.i_end);
   int const tile0 = (warp * ntiles) / W;  // staggered start: warps touch different tiles
 #pragma unroll 1
   for (int tt = 0; tt < ntiles; tt++) {
@@ -374,8 +379,8 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
     if (tile >= ntiles) tile -= ntiles;
     int const jt0 = item.j0 + tile * 32;
     if (item.diag && (jt0 + 32 <= iw0 + 1)) continue;  // no j > i in this tile for this warp
-    bool const masked =
-        masked_rows || ((tile + 1) * 32 > item.jn) || (item.diag && (jt0 < iw1));
+    bool const masked = masked_rows || (!FAR_PADDING && ((tile + 1) * 32 > item.jn)) ||
+                        (item.diag && (jt0 < iw1));
     if (masked) {
       sweep_tile<EXP, ANISO, PBC, PL, R, true>(A, item, tile, lane, ibase, sx, sy, sz, ax, ay, az,
                                                 xi, yi, zi, a1x, a1y, a1z, fsum);
