@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -26,6 +27,13 @@ using namespace b200cv;
 namespace {
 
 std::string g_create_error;
+
+// NVTX ranges around the phases of a step, named like the reference's GPU scheduler phases
+// (src/colvar_gpu_calc.cpp:711-722).  Header-only NVTX3: a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
@@ -537,6 +545,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.cap = h->pl_cap;
       E.partials = h->d_partials;
       E.flags = flags & ~B200CV_EF_REBUILD_PAIRLIST;
+      E.fast_exp = (h->exp_special == 3 && h->P.bc_type == 0) ? 3 : 0;
       E.P = h->P;
       CUDA_OK(h, launch_exact(E, stream));
       h->launches++;
@@ -981,6 +990,7 @@ int b200cv_set_fitting(b200cv_cvc *h, int which, int center, int rotate,
 
 int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride, void *stream)
 {
+  NvtxRange nvtx_range("b200cv::atom_group_read_data");
   if (!h) return B200CV_BUG_ERROR;
   if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1004,6 +1014,7 @@ int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stri
 
 int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, void *stream)
 {
+  NvtxRange nvtx_range("b200cv::cvc_calc_value");
   if (!h) return B200CV_BUG_ERROR;
   if (!h->data_read) return fail(h, B200CV_BUG_ERROR, "calc_value before read_data");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
@@ -1018,6 +1029,7 @@ int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, voi
 
 int b200cv_calc_fit_gradients(b200cv_cvc *h, void *stream)
 {
+  NvtxRange nvtx_range("b200cv::atom_group_calc_fit_gradients");
   if (!h) return B200CV_BUG_ERROR;
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   int const ng = h->self() ? 1 : 2;
@@ -1032,6 +1044,7 @@ int b200cv_calc_fit_gradients(b200cv_cvc *h, void *stream)
 
 int b200cv_value(b200cv_cvc *h, double *value)
 {
+  NvtxRange nvtx_range("b200cv::cvc_calc_value_after_gpu");
   if (!h || !value) return B200CV_BUG_ERROR;
   if (!h->have_calc) return fail(h, B200CV_BUG_ERROR, "value requested before calc_value");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
@@ -1044,6 +1057,7 @@ int b200cv_value(b200cv_cvc *h, double *value)
 int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_t proxy_stride,
                        void *stream)
 {
+  NvtxRange nvtx_range("b200cv::apply_forces");
   if (!h) return B200CV_BUG_ERROR;
   if (!h->have_calc) return fail(h, B200CV_BUG_ERROR, "apply_force before calc_value");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));

@@ -36,9 +36,26 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
        e += (unsigned long long)gridDim.x * EXACT_THREADS) {
     unsigned long long const ent = A.list[e];
     int const i = (int)(ent >> 32), j = (int)(ent & 0xffffffffu);
-    double Gx, Gy, Gz;
-    double const F = pair_exact(A.P, A.x1[i], A.y1[i], A.z1[i], A.x2[j], A.y2[j], A.z2[j],
-                                A.flags, Gx, Gy, Gz);
+    double const x1 = A.x1[i], y1 = A.y1[i], z1 = A.z1[i];
+    double const x2 = A.x2[j], y2 = A.y2[j], z2 = A.z2[j];
+    double Gx, Gy, Gz, F;
+    bool done = false;
+    if (A.fast_exp == 3) {
+      // pair-list walk, non-periodic, 6/12: the sweep's fast form for every pair that is not
+      // next to a decision threshold (same windows as the sweep), reference order otherwise
+      double const dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+      double const sx = dx * A.P.inv_r0[0], sy = dy * A.P.inv_r0[1], sz = dz * A.P.inv_r0[2];
+      double const u = fma(sz, sz, fma(sy, sy, sx * sx));
+      if (!pair_is_rare<true>(u, A.P)) {
+        double gq;
+        switching_fast<3, true>(u, false, A.P, F, gq);
+        Gx = A.P.c_grad[0] * gq * dx;
+        Gy = A.P.c_grad[1] * gq * dy;
+        Gz = A.P.c_grad[2] * gq * dz;
+        done = true;
+      }
+    }
+    if (!done) F = pair_exact(A.P, x1, y1, z1, x2, y2, z2, A.flags, Gx, Gy, Gz);
     fsum += F;
     if (grad && F > 0.0) {
       atomicAdd(&A.g1x[i], -Gx);

@@ -42,6 +42,7 @@ struct ExactArgs {
   unsigned long long pl_cap;
   unsigned long long *pl_count;
   int flags;                           // EF_*
+  int fast_exp;                        // 3: pair-list walk may use the sweep's fast 6/12 form
   PairParams P;
 };
 constexpr int EXACT_BLOCKS = 296;
