@@ -498,6 +498,16 @@ def main():
         "gpu_launches": int(launches),
         "wall_s": t_wall,
     }
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        hbm_peak, which = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+    if line["roofline"]["traffic"]:
+        gbs = line["roofline"]["traffic"] / (kern_ms_avg * 1e-3) / 1e9
+        # why the bound is not "hbm": DRAM traffic of the dominant kernel against the copy peak
+        line["roofline"]["hbm_check"] = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": gbs / hbm_peak, "peak_source": which}
     if split:
         line["pairlist"] = split
         line["roofline"]["note"] = roof_note
