@@ -298,6 +298,21 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
         kern = float(np.mean(reb))
     else:
         kern = float(np.mean([m for _, m in kms]))
+    # the same step as one CUDA-graph launch (b200cv_step)
+    if not (w["tol"] > 0):
+        gev = []
+        for s in range(warmup + steps):
+            flush.fill_(s & 0xFF)
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(stream)
+            cv.step(d_pos, step=s, gradients=True, stream=stream)
+            v = cv.value()
+            cv.apply_force(-0.004 * (v - 0.1), d_force, stream)
+            e1.record(stream)
+            if s >= warmup:
+                gev.append((e0, e1))
+        torch.cuda.synchronize()
+        out["graph_step_ms"] = float(np.mean([a.elapsed_time(b) for a, b in gev]))
     out["calc_value_ms"] = kern
     out["roofline_frac"] = npairs / (kern * 1e-3) * synth.FLOP_PER_PAIR_VALUE_GRAD / 1e12 / fp64_tflops
     cv.close()

@@ -64,7 +64,7 @@ _ip = C.POINTER(C.c_int)
 SYMBOLS = [
     "b200cv_config_defaults", "b200cv_create", "b200cv_destroy", "b200cv_last_error",
     "b200cv_set_group", "b200cv_set_fitting", "b200cv_set_boundaries", "b200cv_read_data",
-    "b200cv_calc_value", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
+    "b200cv_calc_value", "b200cv_step", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
     "b200cv_eval", "b200cv_eval_async", "b200cv_accumulate_gradients", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
@@ -96,6 +96,7 @@ def load():
     L.b200cv_set_boundaries.argtypes = [H, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     L.b200cv_read_data.argtypes = [H, vp, sz, vp]
     L.b200cv_calc_value.argtypes = [H, ll, C.c_int, vp]
+    L.b200cv_step.argtypes = [H, vp, sz, ll, C.c_int, vp]
     L.b200cv_calc_fit_gradients.argtypes = [H, vp]
     L.b200cv_value.argtypes = [H, _dp]
     L.b200cv_apply_force.argtypes = [H, C.c_double, vp, sz, vp]
@@ -245,6 +246,13 @@ class CoordNum:
     def calc_value(self, step=0, gradients=True, stream=None):
         self._check(self._L.b200cv_calc_value(self._h, int(step), int(gradients),
                                               _stream_ptr(stream)))
+
+    def step(self, proxy_pos, step=0, gradients=True, stream=None):
+        """read_data + calc_value (+ fit gradients) replayed from a CUDA graph."""
+        assert proxy_pos.is_cuda and proxy_pos.shape[0] == 3 and proxy_pos.is_contiguous()
+        self._check(self._L.b200cv_step(self._h, C.c_void_p(proxy_pos.data_ptr()),
+                                        proxy_pos.shape[1], int(step), int(gradients),
+                                        _stream_ptr(stream)))
 
     def calc_gradients(self):
         """Gradients are produced by calc_value (src/colvarcomp_coordnums.cpp:316-319)."""

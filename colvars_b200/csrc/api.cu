@@ -150,6 +150,18 @@ struct b200cv_cvc {
   int launches = 0;
   size_t exact_pairs = 0;
 
+  // CUDA graphs of the fused device-resident step (b200cv_step), keyed by what they froze
+  struct StepGraph {
+    int flags;
+    const double *pos;
+    size_t stride;
+    unsigned long long epoch;
+    int launches;
+    cudaGraphExec_t exec;
+  };
+  std::vector<StepGraph> step_graphs;
+  unsigned long long epoch = 0;  // bumped whenever a buffer, the cell or the work items change
+
   std::string err;
 
   unsigned int *rare_count() const { return reinterpret_cast<unsigned int *>(d_counters); }
@@ -392,6 +404,7 @@ void plan_items(bool self, int n1, int n2_in, int rank, int world, std::vector<S
 
 int build_items(b200cv_cvc *h)
 {
+  h->epoch++;
   std::vector<SweepItem> mine;
   plan_items(h->self(), h->g[0].n, h->g[1].n, h->rank, h->world, mine, h->chunk);
   free_dev(h->d_items);
@@ -429,6 +442,7 @@ int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->pl_cap && h->d_pl) return B200CV_OK;
   free_dev(h->d_pl);
+  h->epoch++;
   unsigned long long cap = std::max<unsigned long long>(need + need / 2, 1ull << 20);
   CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * cap));
   h->pl_cap = cap;
@@ -439,6 +453,7 @@ int ensure_rare_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->rare_cap && h->d_rare) return B200CV_OK;
   free_dev(h->d_rare);
+  h->epoch++;
   unsigned long long cap = std::max<unsigned long long>(need + need / 2, 1ull << 20);
   if (cap > 0xffffffffull) return fail(h, B200CV_MEMORY_ERROR, "exact-pair queue too large");
   CUDA_OK(h, cudaMalloc(&h->d_rare, sizeof(unsigned long long) * cap));
@@ -814,6 +829,7 @@ int b200cv_destroy(b200cv_cvc *h)
   if (!h) return B200CV_OK;
   cudaSetDevice(h->cfg.device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (auto &g : h->step_graphs) cudaGraphExecDestroy(g.exec);
   for (auto &G : h->g) {
     free_dev(G.d_index);
     free_dev(G.d_mass);
@@ -908,6 +924,12 @@ int b200cv_set_boundaries(b200cv_cvc *h, int px, int py, int pz, const double A[
   if (!h) return B200CV_BUG_ERROR;
   // system_boundary_conditions::set_boundaries (src/colvars_system.h:80-158)
   PairParams &P = h->P;
+  PairParams const before = P;
+  struct Bump {  // kernel parameters are frozen inside captured graphs
+    b200cv_cvc *h;
+    PairParams const &old;
+    ~Bump() { if (std::memcmp(&old, &h->P, sizeof(PairParams)) != 0) h->epoch++; }
+  } bump{h, before};
   reset_boundaries(P);
   P.periodic[0] = px ? 1 : 0;
   P.periodic[1] = py ? 1 : 0;
@@ -982,6 +1004,7 @@ int b200cv_set_fitting(b200cv_cvc *h, int which, int center, int rotate,
   if (!G.d_index) return fail(h, B200CV_INPUT_ERROR, "define the group before its fitting options");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   std::string err;
+  h->epoch++;
   int rc = fit_setup(G.fit, center, rotate, fit_proxy_index, nfit, G.n, G.stride, G.d_index,
                      G.h_index, ref_pos_soa, enable_fit_gradients, err);
   if (rc) return fail(h, rc, err);
@@ -1025,6 +1048,86 @@ int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, voi
   h->last_flags = flags;
   h->have_calc = true;
   return enqueue_calc(h, flags, h->last_stream);
+}
+
+int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
+                long long step_relative, int gradients, void *stream)
+{
+  if (!h) return B200CV_BUG_ERROR;
+  if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
+  NvtxRange nvtx_range("b200cv::step");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t user = (cudaStream_t)stream;
+  int const flags = calc_flags(h, step_relative, gradients);
+  bool const fitted = h->g[0].fit.active || h->g[1].fit.active;
+  auto plain = [&]() -> int {
+    int rc = b200cv_read_data(h, d_proxy_pos, proxy_stride, stream);
+    if (rc == B200CV_OK) rc = b200cv_calc_value(h, step_relative, gradients, stream);
+    if (rc == B200CV_OK && fitted && gradients) rc = b200cv_calc_fit_gradients(h, stream);
+    return rc;
+  };
+  // not captured: sharded runs (the collective), a pair list that has not been built yet
+  bool const use_pl = flags & B200CV_EF_USE_PAIRLIST;
+  bool const rebuild = flags & B200CV_EF_REBUILD_PAIRLIST;
+  if (h->world > 1 || (use_pl && !rebuild && !h->pl_valid)) return plain();
+
+  // everything that allocates or copies synchronously has to happen before the capture
+  if (!(h->center1() || h->center2())) {
+    if (h->items_dirty) {
+      int rc = build_items(h);
+      if (rc) return rc;
+    }
+  } else {
+    int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
+    if (rc) return rc;
+  }
+  b200cv_cvc::StepGraph *hit = nullptr;
+  for (auto &g : h->step_graphs) {
+    if (g.flags == flags && g.pos == d_proxy_pos && g.stride == proxy_stride &&
+        g.epoch == h->epoch) {
+      hit = &g;
+    }
+  }
+  if (!hit) {
+    // drop graphs that can never match again
+    for (size_t k = 0; k < h->step_graphs.size();) {
+      if (h->step_graphs[k].epoch != h->epoch) {
+        cudaGraphExecDestroy(h->step_graphs[k].exec);
+        h->step_graphs.erase(h->step_graphs.begin() + k);
+      } else {
+        k++;
+      }
+    }
+    cudaStream_t cap = h->own_stream;  // the caller's stream may be the legacy default stream
+    CUDA_OK(h, cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+    int rc = b200cv_read_data(h, d_proxy_pos, proxy_stride, cap);
+    if (rc == B200CV_OK) rc = enqueue_calc(h, flags, cap);
+    if (rc == B200CV_OK && fitted && gradients) rc = b200cv_calc_fit_gradients(h, cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    if (rc != B200CV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    CUDA_OK(h, e);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_OK(h, e);
+    size_t nodes = 0;
+    h->step_graphs.push_back({flags, d_proxy_pos, proxy_stride, h->epoch, h->launches, exec});
+    hit = &h->step_graphs.back();
+    (void)nodes;
+  }
+  CUDA_OK(h, cudaGraphLaunch(hit->exec, user));
+  h->launches = hit->launches;
+  h->async_eval = false;
+  h->last_stream = user;
+  h->last_step = step_relative;
+  h->last_flags = flags;
+  h->have_calc = true;
+  h->data_read = true;
+  return B200CV_OK;
 }
 
 int b200cv_calc_fit_gradients(b200cv_cvc *h, void *stream)

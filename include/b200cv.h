@@ -22,6 +22,7 @@
  *   b200cv_calc_value              coordnum/selfcoordnum/groupcoordnum::calc_value  src/colvarcomp_coordnums.cpp:274-313,547-555,567-577
  *                                  (= cvc::add_calc_value_node in smp gpu)   src/colvarcomp.h:170-173
  *   b200cv_value                   cvc::calc_value_after_gpu                 src/colvarcomp.h:176
+ *   b200cv_step                    the three calls above fused into one CUDA-graph launch
  *   b200cv_calc_fit_gradients      cvc::calc_fit_gradients                   src/colvarcomp.cpp:558-565, src/colvaratoms.cpp:1433-1527
  *   b200cv_apply_force             cvc::apply_force -> apply_colvar_force    src/colvarcomp.cpp:568-577, src/colvaratoms.cpp:1637-1704;
  *                                  apply_colvar_force_to_proxy_kernel        src/cuda/colvaratoms_kernel.cu:434-570
@@ -126,6 +127,13 @@ int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stri
                      void *stream);
 int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, void *stream);
 int b200cv_calc_fit_gradients(b200cv_cvc *h, void *stream);
+/* read_data + calc_value (+ calc_fit_gradients) as ONE CUDA-graph launch: the sequence is
+ * captured the first time it is seen for (proxy buffer, stride, step flags) and replayed
+ * afterwards; it is re-captured when anything it froze changes (cell, fitting options, queue
+ * capacities, work items).  For launch-bound small systems.  Falls back to the three plain
+ * calls in sharded runs and before the first pair-list rebuild. */
+int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
+                long long step_relative, int gradients, void *stream);
 /* Waits for the stream used by the last calc_value and returns x.real_value. */
 int b200cv_value(b200cv_cvc *h, double *value);
 /* F_proxy[idx_i] += force * (R^-1 grad_i) for both groups (+ fit gradients). */

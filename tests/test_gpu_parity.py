@@ -496,3 +496,53 @@ def test_fitted_group_device_resident_matches_host_path():
     torch.cuda.synchronize()
     close_val(v, float(c["value_0"]), 1e-9)
     close_arr(d_force.cpu().numpy().T, c["forces_0"], 1e-9)
+
+
+def test_fused_graph_step_equals_the_plain_calls():
+    """b200cv_step (one CUDA-graph launch) against read_data + calc_value on the same inputs:
+    pair-list cycle (rebuild / walk graphs), changing cell (re-capture), fitted group."""
+    import torch
+    from . import refvec
+    cb = _cb()
+    rng = np.random.default_rng(41)
+    pos = np.ascontiguousarray(rng.random((900 + 2100, 3)) * 21.0)
+    i1 = np.arange(900, dtype=np.int32)
+    i2 = np.arange(900, 3000, dtype=np.int32)
+    d_pos = torch.tensor(np.ascontiguousarray(pos.T), device="cuda")
+    for kw in (dict(), dict(tolerance=0.02, pairlist_freq=3), dict(cutoff3=(3.0, 5.0, 4.0))):
+        a = cb.CoordNum("coordNum", i1, i2, **kw)
+        b = cb.CoordNum("coordNum", i1, i2, **kw)
+        for step in range(7):
+            d_pos += 0.01
+            a.read_data(d_pos)
+            a.calc_value(step=step)
+            va = a.value()
+            b.step(d_pos, step=step)
+            vb = b.value()
+            close_val(vb, va, 1e-13)
+            close_arr(b.gradients(1), a.gradients(1), 1e-13)
+            close_arr(b.gradients(2), a.gradients(2), 1e-13)
+            if step == 3:  # cell change -> the graphs are re-captured
+                for cv in (a, b):
+                    cv.set_boundaries((1, 1, 1), (40.0, 0, 0), (0, 41.0, 0), (0, 0, 39.0))
+        if "tolerance" in kw:
+            assert np.array_equal(a.pairlist(), b.pairlist())
+        a.close()
+        b.close()
+    # fitted group through the graph
+    c = refvec.load("fit_group_center_rotate")
+    n1, n2, nfit = c["n1"], c["n2"], c["nfit"]
+    cv = cb.CoordNum("coordNum", np.arange(n1, dtype=np.int32),
+                     np.arange(n1, n1 + n2, dtype=np.int32), cutoff3=tuple(c["cutoff3"]))
+    cv.set_fitting(1, center=True, rotate=True,
+                   fitting_group=np.arange(n1 + n2, n1 + n2 + nfit, dtype=np.int32),
+                   ref_pos=c["fit_ref"])
+    d = torch.tensor(np.ascontiguousarray(c["frames"][0].T), device="cuda")
+    d_force = torch.zeros_like(d)
+    for _ in range(3):
+        cv.step(d, step=0)
+        v = cv.value()
+    cv.apply_force(refvec.harmonic_fa(v), d_force)
+    torch.cuda.synchronize()
+    close_val(v, float(c["value_0"]), 1e-9)
+    close_arr(d_force.cpu().numpy().T, c["forces_0"], 1e-9)
