@@ -478,6 +478,9 @@ def main():
 
     pairs_per_s = npairs * args.steps / (total_ms * 1e-3)
     roof_note = None
+    if split and not split["rebuild_ms"]:
+        roof_note = ("no pair-list rebuild fell inside the timed region: list-walk steps do not "
+                     "evaluate every pair, the FP64 roofline does not apply to them")
     if split and split["rebuild_ms"]:
         # pair-list workloads: only rebuild steps evaluate every pair; the roofline is quoted on
         # those, `value` stays the whole-job rate (list-walk steps count all pairs they stand for)
@@ -485,6 +488,8 @@ def main():
         roof_note = "roofline quoted on pair-list REBUILD steps only (full sweep)"
     kern_pairs_per_s = npairs / (kern_ms_avg * 1e-3)
     achieved_tflops = kern_pairs_per_s * synth.FLOP_PER_PAIR_VALUE_GRAD / 1e12
+    if split and not split["rebuild_ms"]:
+        achieved_tflops = float("nan")
     peak = fp64_tflops * world
     line = {
         "metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world,
@@ -543,6 +548,8 @@ def main():
             except Exception as e:
                 others[key] = {"error": str(e)[:200]}
         line["other_workloads"] = others
+    if line["roofline"]["achieved"] != line["roofline"]["achieved"]:  # NaN -> null
+        line["roofline"]["achieved"] = line["roofline"]["frac"] = None
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

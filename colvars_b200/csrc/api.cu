@@ -272,23 +272,28 @@ void fill_pair_params(b200cv_cvc *h)
   P.inv1mt = 1 / (1.0 - P.tol);
   P.ntol = -P.tol * P.inv1mt;
   P.l2_max = h->l2_max;
-  P.l2max_hi = hi_word(P.l2_max);
-  // l2 at which the unshifted switching function equals the tolerance (bisection; the
-  // function is monotonic on [1, 1e12] whenever such a root exists)
-  P.utol_hi = P.l2max_hi;
-  if (P.tol > 0) {
-    auto f0 = [&](double u) {
-      double d = 0.0;
-      return switching_host(u, d, c.exp_numer, c.exp_denom, 0.0) - P.tol;
-    };
-    double lo = 1.0 + 1e-6, hi = 1e12;
-    if (f0(lo) * f0(hi) < 0) {
-      for (int it = 0; it < 200; it++) {
-        double const mid = 0.5 * (lo + hi);
-        if (f0(lo) * f0(mid) <= 0) hi = mid; else lo = mid;
+  // decision window of the pair list: l2_max (Newton, reference order) and the exact root of
+  // f0(l2) = tol (bisection; the function is monotonic on [1, 1e12] whenever a root exists)
+  {
+    int lo = hi_word(P.l2_max), hi = lo;
+    if (P.tol > 0) {
+      auto f0 = [&](double u) {
+        double d = 0.0;
+        return switching_host(u, d, c.exp_numer, c.exp_denom, 0.0) - P.tol;
+      };
+      double a = 1.0 + 1e-6, bb = 1e12;
+      if (f0(a) * f0(bb) < 0) {
+        for (int it = 0; it < 200; it++) {
+          double const mid = 0.5 * (a + bb);
+          if (f0(a) * f0(mid) <= 0) bb = mid; else a = mid;
+        }
+        int const r = hi_word(0.5 * (a + bb));
+        lo = std::min(lo, r);
+        hi = std::max(hi, r);
       }
-      P.utol_hi = hi_word(0.5 * (lo + hi));
     }
+    P.thr_lo_hi = lo - 1;
+    P.thr_width = (unsigned)(hi - lo + 2);
   }
   h->exp_special = sweep_has_special(c.exp_numer, c.exp_denom) ? P.en2 : 0;
   for (int d = 0; d < 3; d++) {

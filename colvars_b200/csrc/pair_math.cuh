@@ -37,8 +37,11 @@ struct PairParams {
   double ntol;       // -tol * inv1mt
   double l2_max;     // tolerance_l2_max (1e20 without pair list)
   int en2, ed2;      // en/2, ed/2
-  int l2max_hi;      // high word of l2_max
-  int utol_hi;       // high word of the l2 at which f0(l2) = tol
+  // pair-list decision window on the high word of l2: [thr_lo_hi, thr_lo_hi + thr_width] covers
+  // l2_max (Newton's approximate root) and the exact root of f0(l2) = tol with one high-word
+  // step (2^-20 relative) of margin on both sides
+  int thr_lo_hi;
+  unsigned thr_width;
   // boundary conditions (src/colvars_system.h)
   int bc_type;       // reference enum: 0 non-periodic, 1 mixed, 2 orthogonal, 3 triclinic
   int periodic[3];
@@ -119,12 +122,14 @@ __device__ __forceinline__ bool hi_near(double a, int b_hi)
 
 // Is this pair one that only reference-order arithmetic reproduces?  A function of l2 alone,
 // evaluated on its high word (integer pipe): |l2 - 1| < 2^-4, or -- with a pair list -- l2
-// within ~2e-6 (relative) of l2_max or of the root of f0(l2) = tolerance, the two places
-// where the reference takes a yes/no decision (src/colvarcomp_coordnums.h:203-206,256-261).
+// inside the window that covers l2_max and the root of f0(l2) = tolerance (with ~1e-6
+// relative margin), the two places where the reference takes a yes/no decision
+// (src/colvarcomp_coordnums.h:203-206,256-261).  Outside that window "l2 > l2_max" and
+// "shifted F < 0" are the same statement, and both are far from flipping.
 template <bool PL> __device__ __forceinline__ bool pair_is_rare(double u, PairParams const &P)
 {
   bool rare = near_one(u);
-  if constexpr (PL) rare = rare || hi_near(u, P.l2max_hi) || hi_near(u, P.utol_hi);
+  if constexpr (PL) rare = rare || ((unsigned)(__double2hiint(u) - P.thr_lo_hi) <= P.thr_width);
   return rare;
 }
 
@@ -189,6 +194,21 @@ __device__ __forceinline__ void switching_fast(double u, bool off, PairParams co
       if (off) { F = 0.0; gq = 0.0; }
     }
   }
+}
+
+// Specialised form with the pair-list shift but WITHOUT the yes/no decision:
+// Fh = (f0 - tol)/(1 - tol) (may be negative), gqh = u^(n'-1) r^2.  The sweep applies the
+// decision (Fh > 0) itself and records it, so that a cold block can take a pair out again.
+template <int EXP>
+__device__ __forceinline__ void switching_shifted(double u, PairParams const &P, double &Fh,
+                                                  double &gqh)
+{
+  static_assert(EXP > 0, "specialised exponents only");
+  double const um1 = ipow<EXP - 1>(u);
+  double const q = fma(um1, u, 1.0);
+  double const r = fast_rcp(q);
+  Fh = fma(r, P.inv1mt, P.ntol);
+  gqh = um1 * (r * r);
 }
 
 // ---- exact (reference-order) path -------------------------------------------------------

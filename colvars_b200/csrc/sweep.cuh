@@ -137,6 +137,9 @@ __device__ __forceinline__ double pair_l2(PairParams const &P, double &dx, doubl
 // Two ways of keeping rare pairs out of the fast sums:
 //  * SELECT (masked tiles, pair-list sweeps, runtime exponents): per pair, test l2 and switch
 //    the pair off before it is evaluated;
+//  * UNDO_PL: the same idea for pair-list rebuild sweeps; the decision "listed or not" is the
+//    sign of the shifted function, recorded per pair in the tile's bit masks, and the cold
+//    block removes exactly the recorded contributions of pairs inside a decision window.
 //  * UNDO (specialised exponents, no pair list, interior tiles -- the benchmark path): per pair
 //    only fold the high word of l2 into a running minimum (2 integer instructions);
 //    evaluate and accumulate every pair; if the step saw a rare pair (about 1 step in 5000 at
@@ -155,6 +158,7 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
                                            double (&a1y)[R], double (&a1z)[R], double &fsum)
 {
   constexpr bool UNDO = (EXP > 0) && !PL && !MASKED;
+  constexpr bool UNDO_PL = (EXP > 0) && PL && !MASKED;
   PairParams const &P = A.P;
   double b2x = 0.0, b2y = 0.0, b2z = 0.0;
   unsigned plm[R];
@@ -211,6 +215,58 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
             b2y = fma(-gq, dy, b2y);
             a1z[k] = fma(-gq, dz, a1z[k]);
             b2z = fma(-gq, dz, b2z);
+            rmask |= 1u << k;
+          }
+        }
+      }
+    } else if constexpr (UNDO_PL) {
+      // pair-list sweep, interior tile: the yes/no decision is the sign of the shifted
+      // function (outside the decision window that is also "l2 <= l2_max"); it is recorded
+      // in plm, so the cold block knows exactly what to take out again.
+      unsigned near1 = 0xffffffffu, nearthr = 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        double dx = xj - xi[k];
+        double dy = yj - yi[k];
+        double dz = zj - zi[k];
+        double const u = pair_l2<ANISO, PBC>(P, dx, dy, dz);
+        int const uh = __double2hiint(u);
+        near1 = min(near1, (unsigned)(uh - 0x3FEE0000));
+        nearthr = min(nearthr, (unsigned)(uh - P.thr_lo_hi));
+        double Fh, gqh;
+        switching_shifted<EXP>(u, P, Fh, gqh);
+        bool const keep = __double_as_longlong(Fh) > 0ll;
+        double const F = keep ? Fh : 0.0;
+        double const gq = keep ? gqh : 0.0;
+        plm[k] |= (keep ? 1u : 0u) << t;
+        fsum += F;
+        a1x[k] = fma(gq, dx, a1x[k]);
+        b2x = fma(gq, dx, b2x);
+        a1y[k] = fma(gq, dy, a1y[k]);
+        b2y = fma(gq, dy, b2y);
+        a1z[k] = fma(gq, dz, a1z[k]);
+        b2z = fma(gq, dz, b2z);
+      }
+      if (__builtin_expect((near1 < 0x30000u) || (nearthr <= P.thr_width), 0)) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          double dx = xj - xi[k];
+          double dy = yj - yi[k];
+          double dz = zj - zi[k];
+          double const u = pair_l2<ANISO, PBC>(P, dx, dy, dz);
+          if (pair_is_rare<true>(u, P)) {
+            if ((plm[k] >> t) & 1u) {
+              double Fh, gqh;
+              switching_shifted<EXP>(u, P, Fh, gqh);
+              fsum -= Fh;
+              a1x[k] = fma(-gqh, dx, a1x[k]);
+              b2x = fma(-gqh, dx, b2x);
+              a1y[k] = fma(-gqh, dy, a1y[k]);
+              b2y = fma(-gqh, dy, b2y);
+              a1z[k] = fma(-gqh, dz, a1z[k]);
+              b2z = fma(-gqh, dz, b2z);
+              plm[k] &= ~(1u << t);
+            }
             rmask |= 1u << k;
           }
         }
