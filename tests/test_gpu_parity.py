@@ -546,3 +546,35 @@ def test_fused_graph_step_equals_the_plain_calls():
     torch.cuda.synchronize()
     close_val(v, float(c["value_0"]), 1e-9)
     close_arr(d_force.cpu().numpy().T, c["forces_0"], 1e-9)
+
+
+def test_config5_full_size_properties():
+    """BASELINE config 5 at full size (100 k x 1 M, 1e11 pairs): too big for the oracle as a
+    whole, so (a) 96 random group1 rows against the oracle (their gradients are sums over all
+    1 M group2 atoms), (b) additivity over a split of group1 (value and group2 gradients of the
+    halves add up to the whole), (c) Newton's third law, (d) translation invariance."""
+    cb = _cb()
+    from colvars_b200 import synth
+    n1, n2 = 100000, 1000000
+    proxy, i1, i2, L = synth.coordnum_case(n1, n2, seed=1234)
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
+    v = cv.calc_host(proxy)
+    g1, g2 = cv.gradients(1), cv.gradients(2)
+    # (a) random rows against the oracle
+    rows = np.sort(np.random.default_rng(8).choice(n1, 96, replace=False))
+    ov, og1, _ = O.coordnum(O.make_params(), proxy[i1][rows], proxy[i2], omp=8)
+    close_arr(g1[rows], og1)
+    # (c) third law; the sums run over 1e5 / 1e6 terms of size <= ~1
+    assert np.max(np.abs(g1.sum(0) + g2.sum(0))) <= 1e-7
+    # (b) additivity
+    half = n1 // 2 + 137
+    va = cb.CoordNum("coordNum", i1[:half], i2, cutoff=4.0)
+    vb = cb.CoordNum("coordNum", i1[half:], i2, cutoff=4.0)
+    xa = va.calc_host(proxy)
+    xb = vb.calc_host(proxy)
+    close_val(xa + xb, v, 1e-12)
+    close_arr(va.gradients(2) + vb.gradients(2), g2)
+    close_arr(np.concatenate([va.gradients(1), vb.gradients(1)]), g1)
+    # (d) translation
+    v2 = cv.calc_host(proxy + np.array([1.5, -2.5, 0.75]))
+    close_val(v2, v, 1e-11)
