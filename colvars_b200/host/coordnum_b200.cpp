@@ -2,6 +2,8 @@
 // the reference's own parser, then one C-ABI call per calc_value().
 #include "coordnum_b200.h"
 
+#include <cctype>
+#include <cstdio>
 #include <vector>
 
 #include "colvaratoms.h"
@@ -36,6 +38,12 @@ struct component_registry : public colvar {
 
 int set_engine_group(b200cv_cvc *h, int which, cvm::atom_group *g)
 {
+  if (g->b_dummy) {
+    // one pseudo-atom that is not part of the system: an id no real atom can have
+    int const id = 0x7ffffff0;
+    double const m = 1.0;
+    return b200cv_set_group(h, which, &id, &m, 1);
+  }
   size_t const n = g->size();
   std::vector<int> ids(n);
   std::vector<double> m(n);
@@ -134,7 +142,26 @@ int coordnum_b200::init(std::string const &conf)
   b200cv_config_defaults(&cfg);
   cfg.kind = is_self ? B200CV_SELFCOORDNUM : (is_group ? B200CV_GROUPCOORD : B200CV_COORDNUM);
   cfg.n1 = (int)group1->size();
-  cfg.n2 = is_self ? 0 : (int)group2->size();
+  dummy2 = !is_self && group2->b_dummy;
+  if (dummy2) {
+    // the position is private to the atom group; read the keyword once more -- by hand, so
+    // that this component's keyword registry (positions inside `conf`, used by
+    // check_keywords) is not disturbed
+    std::string low(conf);
+    for (char &ch : low) ch = (char)std::tolower((unsigned char)ch);
+    size_t const g2 = low.find("group2");
+    size_t const at = (g2 == std::string::npos) ? g2 : low.find("dummyatom", g2);
+    double v[3] = {0.0, 0.0, 0.0};
+    if (at != std::string::npos) {
+      std::string rest = conf.substr(at + 9);
+      for (char &ch : rest) {
+        if (ch == '(' || ch == ')' || ch == ',') ch = ' ';
+      }
+      std::sscanf(rest.c_str(), "%lf %lf %lf", &v[0], &v[1], &v[2]);
+    }
+    dummy2_pos = cvm::atom_pos(v[0], v[1], v[2]);
+  }
+  cfg.n2 = is_self ? 0 : (dummy2 ? 1 : (int)group2->size());
   cfg.cutoff3[0] = r0_vec.x;
   cfg.cutoff3[1] = r0_vec.y;
   cfg.cutoff3[2] = r0_vec.z;
@@ -148,10 +175,6 @@ int coordnum_b200::init(std::string const &conf)
   int rc = b200cv_create(&cfg, &engine);
   if (rc != B200CV_OK) {
     return error_code | cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
-  }
-  if (!is_self && group2->b_dummy) {
-    return error_code | cvmodule->error("Error: dummy atoms are not supported by the B200 "
-                                        "coordination-number engine.\n", COLVARS_NOT_IMPLEMENTED);
   }
   rc = set_engine_group(engine, 1, group1);
   if (rc == B200CV_OK && !is_self) rc = set_engine_group(engine, 2, group2);
@@ -180,6 +203,23 @@ void coordnum_b200::calc_value()
   const double *p2 = group2 ? &group2->pos_x(0) : nullptr;
   double *g2 = group2 ? &group2->grad_x(0) : nullptr;
   x.real_value = 0.0;
+  double dummy_pos[3], dummy_grad[3] = {0.0, 0.0, 0.0};
+  if (dummy2) {
+    // the reference loops over group2->size() == 0 atoms unless group2CenterOnly is on
+    // (its default for a dummy group2, src/colvarcomp_coordnums.cpp:74-75,190-194)
+    if (!b_group2_center_only) return;
+    // CPU proxy: the group's centre of mass is the dummy position (src/colvaratoms.cpp:1376)
+    // and follows set_dummy_pos(); under `smp gpu` the reference does not refresh it for
+    // components on the CPU-buffer route, so fall back to the parsed keyword there
+    bool const gpu_mode =
+        cvmodule->proxy->get_smp_mode() == colvarproxy_smp::smp_mode_t::gpu;
+    cvm::atom_pos const c = gpu_mode ? dummy2_pos : group2->center_of_mass();
+    dummy_pos[0] = c.x;
+    dummy_pos[1] = c.y;
+    dummy_pos[2] = c.z;
+    p2 = dummy_pos;
+    g2 = dummy_grad;  // a dummy atom takes no gradient
+  }
   int const rc = b200cv_eval_host(engine, &group1->pos_x(0), p2, flags, &group1->grad_x(0), g2,
                                   &x.real_value);
   if (rc != B200CV_OK) b200_error(rc);
@@ -195,7 +235,8 @@ void coordnum_b200::calc_gradients()
 
 bool coordnum_b200::has_gpu_implementation() const
 {
-  return cvmodule->proxy->get_smp_mode() == colvarproxy_smp::smp_mode_t::gpu && !(tolerance > 0);
+  return cvmodule->proxy->get_smp_mode() == colvarproxy_smp::smp_mode_t::gpu &&
+         !(tolerance > 0) && !dummy2;
 }
 
 namespace {

@@ -57,6 +57,9 @@ protected:
   cvm::real tolerance = 0.0;
   int pairlist_freq = 100;
   size_t num_pairs = 0;
+  /// group2 is a dummy atom (`dummyAtom (x, y, z)`): a fixed point that receives no force
+  bool dummy2 = false;
+  cvm::atom_pos dummy2_pos;  // as parsed from `dummyAtom`
   b200cv_cvc *engine = nullptr;
 #if defined(COLVARS_CUDA)
   cudaStream_t capture_stream = nullptr;
