@@ -40,7 +40,10 @@ namespace b200cv {
 #ifndef B200CV_JCMAX
 #define B200CV_JCMAX 1024
 #endif
-constexpr int JCMAX = B200CV_JCMAX;  // group2 atoms per chunk (24 B coordinates + 24 B accumulators each)
+constexpr int JCMAX = B200CV_JCMAX;
+#ifndef B200CV_TUNROLL
+#define B200CV_TUNROLL 1  // unroll factor of the 32-step rotation loop of a tile
+#endif  // group2 atoms per chunk (24 B coordinates + 24 B accumulators each)
 
 struct SweepItem {
   int i0;    // first group1 atom of the block
@@ -169,7 +172,8 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
   const double *__restrict__ py = sy + tbase;
   const double *__restrict__ pz = sz + tbase;
 
-#pragma unroll 1
+  constexpr int TUNROLL = B200CV_TUNROLL;
+#pragma unroll TUNROLL
   for (int t = 0; t < 32; t++) {
     int const jj = (lane + t) & 31;
     double const xj = px[jj];
