@@ -47,6 +47,10 @@ WORKLOADS = {
                     "rotateToReference (fitted on itself, fit gradients on)"),
     "c5": dict(kind="coordNum", n1=100000, n2=1000000, cutoff3=(4.0, 4.0, 4.0), tol=0.0,
                freq=100, name="coordNum 100k x 1M iso r0=4 n=6 m=12"),
+    # widening: distanceInv on the same tile sweep
+    "dinv": dict(kind="distanceInv", n1=10000, n2=500000, cutoff3=(4.0, 4.0, 4.0), tol=0.0,
+                 freq=100, exponent=6, flop_per_pair=synth.FLOP_PER_PAIR_DISTANCEINV,
+                 name="distanceInv 10k x 500k exponent=6"),
 }
 METRIC = "coordNum pair-evals/sec (value+grad)"
 UNIT = "pair-evals/s"
@@ -251,7 +255,7 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     proxy, i1, i2 = make_inputs(w)
     dev = torch.device("cuda", device)
     cv = cb.CoordNum(w["kind"], i1, i2, cutoff3=w["cutoff3"], tolerance=w["tol"],
-                     pairlist_freq=w["freq"], device=device)
+                     pairlist_freq=w["freq"], device=device, exponent=w.get("exponent"))
     fitted = bool(w.get("fit"))
     if fitted:
         ref = proxy[i1].copy()
@@ -314,7 +318,9 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
         torch.cuda.synchronize()
         out["graph_step_ms"] = float(np.mean([a.elapsed_time(b) for a, b in gev]))
     out["calc_value_ms"] = kern
-    out["roofline_frac"] = npairs / (kern * 1e-3) * synth.FLOP_PER_PAIR_VALUE_GRAD / 1e12 / fp64_tflops
+    flop = w.get("flop_per_pair", synth.FLOP_PER_PAIR_VALUE_GRAD)
+    out["flop_per_pair"] = flop
+    out["roofline_frac"] = npairs / (kern * 1e-3) * flop / 1e12 / fp64_tflops
     cv.close()
     return out
 
@@ -325,7 +331,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5",
+                    choices=sorted(k for k in WORKLOADS if k != "dinv"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
@@ -542,7 +549,7 @@ def main():
         # the other single-GPU configurations of BASELINE.json, device-resident step only
         # (same timing rules; not the headline): BASELINE config 2 is the 1-GPU case
         others = {}
-        for key in ("c2", "c4", "c3"):
+        for key in ("c2", "c4", "c3", "dinv"):
             try:
                 others[key] = quick_workload(cb, torch, key, local_rank, fp64_tflops)
             except Exception as e:

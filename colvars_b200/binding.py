@@ -25,8 +25,9 @@ BUG_ERROR = 1 << 3
 FILE_ERROR = 1 << 4
 MEMORY_ERROR = 1 << 5
 
-COORDNUM, SELFCOORDNUM, GROUPCOORD = 0, 1, 2
-KIND_BY_NAME = {"coordNum": COORDNUM, "selfCoordNum": SELFCOORDNUM, "groupCoord": GROUPCOORD}
+COORDNUM, SELFCOORDNUM, GROUPCOORD, DISTANCEINV = 0, 1, 2, 3
+KIND_BY_NAME = {"coordNum": COORDNUM, "selfCoordNum": SELFCOORDNUM, "groupCoord": GROUPCOORD,
+                "distanceInv": DISTANCEINV}
 
 EF_NULL = 0
 EF_GRADIENTS = 1
@@ -151,7 +152,7 @@ class CoordNum:
     def __init__(self, function_type="coordNum", group1=None, group2=None, *, cutoff=None,
                  cutoff3=None, exp_numer=6, exp_denom=12, group1_center_only=False,
                  group2_center_only=False, tolerance=0.0, pairlist_freq=100, mass1=None,
-                 mass2=None, device=0):
+                 mass2=None, device=0, exponent=None):
         L = load()
         self._L = L
         self._h = C.c_void_p()
@@ -177,6 +178,9 @@ class CoordNum:
             for d in range(3):
                 cfg.cutoff3[d] = float(cutoff3[d])
         cfg.exp_numer, cfg.exp_denom = int(exp_numer), int(exp_denom)
+        if function_type == "distanceInv":
+            # keyword "exponent" (src/colvarcomp_distances.cpp:383), default 6
+            cfg.exp_numer = 6 if exponent is None else int(exponent)
         cfg.group1_center_only = int(bool(group1_center_only))
         cfg.group2_center_only = int(bool(group2_center_only))
         cfg.tolerance = float(tolerance)

@@ -170,6 +170,7 @@ struct b200cv_cvc {
     return reinterpret_cast<unsigned long long *>(d_counters + 8);
   }
   bool self() const { return cfg.kind == B200CV_SELFCOORDNUM; }
+  bool dinv() const { return cfg.kind == B200CV_DISTANCEINV; }
   bool center1() const { return cfg.group1_center_only != 0; }
   bool center2() const { return cfg.group2_center_only != 0; }
   Group &grp2() { return self() ? g[0] : g[1]; }
@@ -299,6 +300,18 @@ void fill_pair_params(b200cv_cvc *h)
   for (int d = 0; d < 3; d++) {
     P.c_grad[d] = h->exp_special ? -2.0 * (double)P.en2 * P.inv1mt * P.inv_r0sq[d]
                                  : 2.0 * P.inv_r0sq[d];
+  }
+  P.func = 0;
+  if (h->dinv()) {
+    // pair term d^-n on the unscaled squared distance; G = -n F / d^2 * diff
+    // (src/colvarcomp_distances.cpp:415-427)
+    P.func = 1;
+    h->aniso = false;
+    h->exp_special = (P.en2 == 3) ? -3 : -1;
+    for (int d = 0; d < 3; d++) {
+      P.inv_r0[d] = P.inv_r0sq[d] = 1.0;
+      P.c_grad[d] = -(double)c.exp_numer;
+    }
   }
 }
 
@@ -606,7 +619,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       int const pbc = h->P.bc_type == 2 ? BC_ORTHO : BC_NONE;
       CUDA_OK(h, launch_sweep(S, h->nitems, h->exp_special, h->aniso, pbc, use_pl, stream));
       if (h->nitems > 0) h->launches++;
-      // pairs next to a decision threshold: reference-order arithmetic
+      // pairs next to a decision threshold: reference-order arithmetic (distanceInv has none:
+      // the launch then only zeroes its partial sums)
       ExactArgs E{};
       E.x1 = x1; E.y1 = y1; E.z1 = z1; E.x2 = x2; E.y2 = y2; E.z2 = z2;
       E.g1x = g1x; E.g1y = g1y; E.g1z = g1z; E.g2x = g2x; E.g2y = g2y; E.g2z = g2z;
@@ -646,6 +660,19 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
       }
     }
+  }
+  if (h->dinv()) {
+    DistInvPostArgs D{};
+    D.d_value = h->d_value;
+    D.h_value = h->world > 1 ? nullptr : h->h_value_dev;
+    D.grad = grad ? h->d_reduce + 32 : nullptr;
+    D.count = h->reduce_count - 32;
+    D.exponent = h->cfg.exp_numer;
+    D.npairs = (double)h->g[0].n * (double)h->g[1].n;
+    CUDA_OK(h, launch_distinv_post(D, stream));
+    h->launches += grad ? 2 : 1;
+  }
+  if (h->world > 1) {
     CUDA_OK(h, cudaMemcpyAsync(h->h_value, h->d_value, sizeof(double), cudaMemcpyDeviceToHost,
                                stream));
   }
@@ -757,7 +784,21 @@ int b200cv_create(const b200cv_config *cfg, b200cv_cvc **out)
   if (!cfg || !out) return fail(nullptr, B200CV_BUG_ERROR, "null argument");
   *out = nullptr;
   b200cv_config c = *cfg;
-  if (c.kind < 0 || c.kind > 2) return fail(nullptr, B200CV_INPUT_ERROR, "unknown component kind");
+  if (c.kind < 0 || c.kind > 3) return fail(nullptr, B200CV_INPUT_ERROR, "unknown component kind");
+  if (c.kind == B200CV_DISTANCEINV) {
+    // distance_inv::init (src/colvarcomp_distances.cpp:384-391)
+    if (c.exp_numer % 2) {
+      return fail(nullptr, B200CV_INPUT_ERROR,
+                  "Error: odd exponent provided, can only use even ones.");
+    }
+    if (c.exp_numer <= 0) {
+      return fail(nullptr, B200CV_INPUT_ERROR, "Error: negative or zero exponent provided.");
+    }
+    c.exp_denom = 2 * c.exp_numer;
+    c.cutoff3[0] = c.cutoff3[1] = c.cutoff3[2] = 1.0;
+    c.tolerance = 0.0;
+    c.group1_center_only = c.group2_center_only = 0;
+  }
   if (c.n1 < 1) return fail(nullptr, B200CV_INPUT_ERROR, "Error: group1 is empty");
   if (c.kind != B200CV_SELFCOORDNUM && c.n2 < 1) {
     return fail(nullptr, B200CV_INPUT_ERROR, "Error: group2 is empty");
@@ -889,6 +930,12 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
     for (int i = 0; i < n; i++) {
       if (seen.count(proxy_index[i])) {
         G.h_index.clear();
+        if (h->dinv()) {
+          // distance_inv::init (src/colvarcomp_distances.cpp:393-397)
+          return fail(h, B200CV_INPUT_ERROR,
+                      "Error: group1 and group2 have some atoms in common: this is not "
+                      "allowed for distanceInv.");
+        }
         return fail(h, B200CV_INPUT_ERROR,
                     "Error: group1 and group2 share a common atom (number: " +
                         std::to_string(proxy_index[i] + 1) + ")");

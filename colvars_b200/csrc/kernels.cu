@@ -3,6 +3,8 @@
 // gather / COM / rotate / scatter, and the measurement helpers.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace b200cv {
 
 // ============================ block reduction helper =======================================
@@ -226,6 +228,42 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream)
 {
   finalize_kernel<<<1, 256, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+// distanceInv epilogue: every thread recomputes the two scalars from the reduced sum (cheaper
+// than a second launch); a cooperative-groups-free two-phase scheme -- the raw sum is left
+// untouched until all blocks have read it: block 0 publishes x through a separate kernel.
+__global__ void __launch_bounds__(256) distinv_scale_kernel(const __grid_constant__ DistInvPostArgs A)
+{
+  double const sum = *A.d_value;
+  double const x = pow(sum * (1.0 / A.npairs), -1.0 / (double)A.exponent);
+  double const dxdsum = (-1.0 / (double)A.exponent) * ipow_rt(x, A.exponent + 1) / A.npairs;
+  for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < A.count; k += (size_t)gridDim.x * 256) {
+    A.grad[k] *= dxdsum;
+  }
+}
+
+__global__ void distinv_value_kernel(const __grid_constant__ DistInvPostArgs A)
+{
+  double const sum = *A.d_value;
+  double const x = pow(sum * (1.0 / A.npairs), -1.0 / (double)A.exponent);
+  *A.d_value = x;
+  if (A.h_value) {
+    __threadfence_system();
+    *A.h_value = x;
+  }
+}
+
+int launch_distinv_post(const DistInvPostArgs &args, cudaStream_t stream)
+{
+  if (args.grad && args.count > 0) {
+    int blocks = (int)std::min<size_t>((args.count + 255) / 256, 296 * 4);
+    distinv_scale_kernel<<<blocks, 256, 0, stream>>>(args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  distinv_value_kernel<<<1, 1, 0, stream>>>(args);
   return (int)cudaGetLastError();
 }
 

@@ -98,6 +98,19 @@ struct FinalizeArgs {
 };
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
 
+// distanceInv epilogue (src/colvarcomp_distances.cpp:442-455): *d_value holds sum_ij d^-n
+// (already reduced over ranks); x = (sum / npairs)^(-1/n) replaces it and every gradient entry
+// in grad[0..count) is scaled by dx/dsum = (-1/n) x^(n+1) / npairs.
+struct DistInvPostArgs {
+  double *d_value;
+  double *h_value;  // mapped pinned or null
+  double *grad;     // contiguous gradient block (group1 | group2), or null
+  size_t count;
+  int exponent;
+  double npairs;
+};
+int launch_distinv_post(const DistInvPostArgs &args, cudaStream_t stream);
+
 // ---- atom-group kernels (src/colvaratoms.cpp, src/cuda/colvaratoms_kernel.cu) -----------
 // gather: pos[d*stride + i] = proxy[d*pstride + idx[i]]  (aos != 0: proxy[3*idx[i] + d])
 int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, int n,

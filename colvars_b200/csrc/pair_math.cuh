@@ -36,7 +36,8 @@ struct PairParams {
   double inv1mt;     // 1 / (1 - tol)
   double ntol;       // -tol * inv1mt
   double l2_max;     // tolerance_l2_max (1e20 without pair list)
-  int en2, ed2;      // en/2, ed/2
+  int en2, ed2;      // en/2, ed/2 (distanceInv: en2 = exponent/2)
+  int func;          // 0: switching function (coordination numbers), 1: distanceInv pair term
   // pair-list decision window on the high word of l2: [thr_lo_hi, thr_lo_hi + thr_width] covers
   // l2_max (Newton's approximate root) and the exact root of f0(l2) = tol with one high-word
   // step (2^-20 relative) of margin on both sides
@@ -199,6 +200,26 @@ __device__ __forceinline__ void switching_fast(double u, bool off, PairParams co
 // Specialised form with the pair-list shift but WITHOUT the yes/no decision:
 // Fh = (f0 - tol)/(1 - tol) (may be negative), gqh = u^(n'-1) r^2.  The sweep applies the
 // decision (Fh > 0) itself and records it, so that a cold block can take a pair out again.
+// distanceInv pair term (src/colvarcomp_distances.cpp:415-427): with u = d^2 (inv_r0sq = 1 for
+// this function), F = u^(-n/2) and the gradient w.r.t. the second atom is -n F / u * diff, i.e.
+// gq = F / u with c_grad = -n.  Well conditioned everywhere: no exact-pair queue needed.
+// EXP = -1: runtime n/2 (P.en2);  EXP = -h, h >= 2: compile-time n/2 = h.
+template <int EXP>
+__device__ __forceinline__ void distinv_fast(double u, bool off, PairParams const &P, double &F,
+                                             double &gq)
+{
+  static_assert(EXP < 0, "distinv_fast is selected by negative EXP");
+  u = off ? 1.0 : u;
+  // any physical d^2 is far inside the seed's range; d = 0 gives NaN here and 0/0 in the
+  // reference's gradient (src/colvarcomp_distances.cpp:419)
+  double const r = fast_rcp(u);
+  double f;
+  if constexpr (EXP == -1) f = ipow_rt(r, P.en2);
+  else f = ipow<-EXP>(r);
+  F = off ? 0.0 : f;
+  gq = off ? 0.0 : f * r;
+}
+
 template <int EXP>
 __device__ __forceinline__ void switching_shifted(double u, PairParams const &P, double &Fh,
                                                   double &gqh)
@@ -333,6 +354,17 @@ __device__ inline double pair_exact(PairParams const &P, double x1, double y1, d
 {
   double dx, dy, dz;
   position_distance_exact(P, x1, y1, z1, x2, y2, z2, dx, dy, dz);
+  if (P.func == 1) {
+    // distance_inv::calc_value, reference operation order (src/colvarcomp_distances.cpp:415-427)
+    double const d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    double const pw = integer_power_exact(d2, P.en2);
+    double const dinv = (d2 == 0.0) ? 0.0 : __ddiv_rn(1.0, pw);
+    double const c = __dmul_rn(__ddiv_rn(__dmul_rn((double)(-P.en2), dinv), d2), 2.0);
+    Gx = __dmul_rn(c, dx);
+    Gy = __dmul_rn(c, dy);
+    Gz = __dmul_rn(c, dz);
+    return dinv;
+  }
   double const sx = __dmul_rn(dx, P.inv_r0[0]);
   double const sy = __dmul_rn(dy, P.inv_r0[1]);
   double const sz = __dmul_rn(dz, P.inv_r0[2]);

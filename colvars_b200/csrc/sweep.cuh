@@ -113,7 +113,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // ---- pair geometry -------------------------------------------------------------------------
-template <bool ANISO, int PBC>
+// UNIT: plain squared distance (distanceInv), no cutoff scaling
+template <bool ANISO, int PBC, bool UNIT = false>
 __device__ __forceinline__ double pair_l2(PairParams const &P, double &dx, double &dy, double &dz)
 {
   if constexpr (PBC == BC_ORTHO) {
@@ -126,7 +127,9 @@ __device__ __forceinline__ double pair_l2(PairParams const &P, double &dx, doubl
     dy = fma(-shy, P.cell[1][1], dy);
     dz = fma(-shz, P.cell[2][2], dz);
   }
-  if constexpr (ANISO) {
+  if constexpr (UNIT) {
+    return fma(dz, dz, fma(dy, dy, dx * dx));
+  } else if constexpr (ANISO) {
     double const sx_ = dx * P.inv_r0[0];
     double const sy_ = dy * P.inv_r0[1];
     double const sz_ = dz * P.inv_r0[2];
@@ -281,10 +284,10 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
         double dx = xj - xi[k];
         double dy = yj - yi[k];
         double dz = zj - zi[k];
-        double const u = pair_l2<ANISO, PBC>(P, dx, dy, dz);
+        double const u = pair_l2<ANISO, PBC, (EXP < 0)>(P, dx, dy, dz);
         // branch-free: a rare pair contributes nothing here and is remembered in a mask, so
         // that the R pairs of this step stay one basic block for the instruction scheduler
-        bool rare = pair_is_rare<PL>(u, P);
+        bool rare = (EXP < 0) ? false : pair_is_rare<PL>(u, P);
         bool off = rare;
         if constexpr (MASKED) {
           int const iglob = ibase + k * 32;
@@ -295,7 +298,8 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
         }
         rmask |= (rare ? 1u : 0u) << k;
         double F, gq;
-        switching_fast<EXP, PL>(u, off, P, F, gq);
+        if constexpr (EXP < 0) distinv_fast<EXP>(u, off, P, F, gq);
+        else switching_fast<EXP, PL>(u, off, P, F, gq);
         if constexpr (PL) {
           // F is +0 or positive: test the bit pattern on the integer pipe
           plm[k] |= (__double_as_longlong(F) != 0ll ? 1u : 0u) << t;

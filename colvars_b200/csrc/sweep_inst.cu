@@ -37,6 +37,15 @@ int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso,
                  bool pairlist, cudaStream_t stream)
 {
   if (nitems <= 0) return 0;
+  if (exp_special < 0) {
+    // distanceInv: exponent 6 (the default) compiled in, any other even exponent at run time
+    if (exp_special == -3) {
+      return pbc == BC_NONE ? launch_sweep_t<-3, false, BC_NONE, false>(args, nitems, stream)
+                            : launch_sweep_t<-3, false, BC_ORTHO, false>(args, nitems, stream);
+    }
+    return pbc == BC_NONE ? launch_sweep_t<-1, false, BC_NONE, false>(args, nitems, stream)
+                          : launch_sweep_t<-1, false, BC_ORTHO, false>(args, nitems, stream);
+  }
   if (exp_special == 3) {
     return aniso ? launch_sweep_ea<3, true>(args, nitems, pbc, pairlist, stream)
                  : launch_sweep_ea<3, false>(args, nitems, pbc, pairlist, stream);

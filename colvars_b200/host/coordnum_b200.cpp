@@ -33,6 +33,7 @@ struct component_registry : public colvar {
     global_cvc_map["coordNum"] = []() -> colvar::cvc * { return new coordnum_b200(); };
     global_cvc_map["selfCoordNum"] = []() -> colvar::cvc * { return new selfcoordnum_b200(); };
     global_cvc_map["groupCoord"] = []() -> colvar::cvc * { return new groupcoordnum_b200(); };
+    global_cvc_map["distanceInv"] = []() -> colvar::cvc * { return new distanceinv_b200(); };
   }
 };
 
@@ -172,13 +173,18 @@ int coordnum_b200::init(std::string const &conf)
   cfg.tolerance = tolerance;
   cfg.pairlist_freq = pairlist_freq;
   cfg.device = 0;
+  return error_code | create_engine(cfg);
+}
+
+int coordnum_b200::create_engine(b200cv_config const &cfg)
+{
   int rc = b200cv_create(&cfg, &engine);
   if (rc != B200CV_OK) {
-    return error_code | cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
+    return cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
   }
   rc = set_engine_group(engine, 1, group1);
-  if (rc == B200CV_OK && !is_self) rc = set_engine_group(engine, 2, group2);
-  if (rc != B200CV_OK) return error_code | b200_error(rc);
+  if (rc == B200CV_OK && group2) rc = set_engine_group(engine, 2, group2);
+  if (rc != B200CV_OK) return b200_error(rc);
 #if defined(COLVARS_CUDA)
   if (has_gpu_implementation()) {
     // positions and gradients stay on the device (as colvar::rmsd does,
@@ -186,7 +192,40 @@ int coordnum_b200::init(std::string const &conf)
     disable(f_cvc_require_cpu_buffers);
   }
 #endif
-  return error_code;
+  return COLVARS_OK;
+}
+
+// ---- distanceInv (src/colvarcomp_distances.cpp:365-470) ------------------------------------
+
+distanceinv_b200::distanceinv_b200() : coordnum_b200("distanceInv") { init_as_distance(); }
+
+int distanceinv_b200::init(std::string const &conf)
+{
+  int error_code = cvc::init(conf);
+  group1 = parse_group(conf, "group1");
+  group2 = parse_group(conf, "group2");
+  if (!group1 || !group2) return error_code | COLVARS_INPUT_ERROR;
+  get_keyval(conf, "exponent", exponent, exponent);
+  if (cvm::atom_group::overlap(*group1, *group2) != 0) {
+    error_code |= cvmodule->error("Error: group1 and group2 have some atoms in common: this is not "
+                                  "allowed for distanceInv.\n",
+                                  COLVARS_INPUT_ERROR);
+  }
+  if (is_enabled(f_cvc_debug_gradient)) {
+    cvmodule->log("Warning: debugGradients will not give correct results "
+                  "for distanceInv, because its value and gradients are computed "
+                  "simultaneously.\n");
+  }
+  if (error_code != COLVARS_OK) return error_code;
+  // parity of the exponent and its sign are checked behind the C ABI (reference messages)
+  b200cv_config cfg;
+  b200cv_config_defaults(&cfg);
+  cfg.kind = B200CV_DISTANCEINV;
+  cfg.n1 = (int)group1->size();
+  cfg.n2 = (int)group2->size();
+  cfg.exp_numer = exponent;
+  cfg.device = 0;
+  return error_code | create_engine(cfg);
 }
 
 void coordnum_b200::calc_value()

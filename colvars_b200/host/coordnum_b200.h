@@ -46,6 +46,8 @@ public:
 protected:
   explicit coordnum_b200(char const *function_type_in);
   int b200_error(int code);
+  /// b200cv_create + group upload (+ device-buffer route under `smp gpu`)
+  int create_engine(b200cv_config const &cfg);
 
   cvm::atom_group *group1 = nullptr;
   cvm::atom_group *group2 = nullptr;
@@ -74,6 +76,18 @@ public:
 class groupcoordnum_b200 : public coordnum_b200 {
 public:
   groupcoordnum_b200() : coordnum_b200("groupCoord") {}
+};
+
+/// Widening: colvar::distance_inv, "distanceInv"
+/// (src/colvarcomp_distances.cpp:365-470) on the same pair sweep; keywords group1, group2,
+/// exponent.
+class distanceinv_b200 : public coordnum_b200 {
+public:
+  distanceinv_b200();
+  int init(std::string const &conf) override;
+
+protected:
+  int exponent = 6;
 };
 
 #endif

@@ -67,6 +67,9 @@ def random_rotation(seed):
 # pair counts and the algorithmic flop figure of SURVEY.md section 8d / BASELINE.md section 3
 FLOP_PER_PAIR_VALUE_GRAD = 39
 FLOP_PER_PAIR_VALUE = 19
+# distanceInv, exponent 6, value + gradients: 3 differences, d^2 (1 mul + 2 fma), reciprocal
+# refinement (3 fma), r^3 (2 mul), F r (1 mul), sum (1 add), six gradient fma = 30 flop
+FLOP_PER_PAIR_DISTANCEINV = 30
 
 
 def num_pairs(kind, n1, n2=0):

@@ -64,6 +64,11 @@ extern "C" {
 #define B200CV_COORDNUM 0
 #define B200CV_SELFCOORDNUM 1
 #define B200CV_GROUPCOORD 2
+/* widening: colvar::distance_inv, "distanceInv" (src/colvarcomp_distances.cpp:365-470) -- the
+ * same group1 x group2 pair sweep with the pair term d^-n and the scalar epilogue
+ * (sum / (N1 N2))^(-1/n).  exp_numer carries the keyword "exponent" (even, > 0, default 6);
+ * cutoff3, exp_denom, tolerance and the *_center_only flags are ignored. */
+#define B200CV_DISTANCEINV 3
 
 /* evaluation flags, same values as colvar::coordnum::ef_* (src/colvarcomp_coordnums.h:32-37) */
 #define B200CV_EF_NULL 0
@@ -76,11 +81,11 @@ typedef struct b200cv_cvc b200cv_cvc;
 /* Keywords of a coordNum / selfCoordNum / groupCoord block
  * (src/colvarcomp_coordnums.cpp:73-153; doc/colvars-refman-main.tex:1913-2016). */
 typedef struct {
-  int kind;               /* B200CV_COORDNUM | _SELFCOORDNUM | _GROUPCOORD */
+  int kind;               /* B200CV_COORDNUM | _SELFCOORDNUM | _GROUPCOORD | _DISTANCEINV */
   int n1;                 /* atoms in group1 */
   int n2;                 /* atoms in group2 (ignored for selfCoordNum) */
   double cutoff3[3];      /* r0 per axis ("cutoff" = all three equal); default 4 A */
-  int exp_numer;          /* expNumer, even > 0; default 6 */
+  int exp_numer;          /* expNumer, even > 0; default 6 (distanceInv: "exponent") */
   int exp_denom;          /* expDenom, even > 0; default 12 */
   int group1_center_only; /* group1CenterOnly (forced on for groupCoord) */
   int group2_center_only; /* group2CenterOnly (forced on for groupCoord) */

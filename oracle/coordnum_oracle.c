@@ -574,3 +574,98 @@ void cvo_apply_colvar_force(size_t n, const int *atoms_index, const double *grad
     proxy_force_aos[3 * pi + 2] += fz;
   }
 }
+
+
+/* ---- distanceInv (widening) ------------------------------- */
+
+/* src/colvarcomp_distances.cpp:405-456 */
+double cvo_distance_inv(const cvo_boundaries *bc, int exponent, size_t n1, const double *pos1,
+                        size_t n2, const double *pos2, double *grad1, double *grad2,
+                        int nthreads)
+{
+  int const factor = -1 * (exponent / 2);
+  double sum = 0.0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  if (nthreads <= 1) {
+    for (size_t i = 0; i < n1; ++i) {
+      double const p1[3] = {pos1[i], pos1[n1 + i], pos1[2 * n1 + i]};
+      double g1[3] = {0, 0, 0};
+      for (size_t j = 0; j < n2; ++j) {
+        double const p2[3] = {pos2[j], pos2[n2 + j], pos2[2 * n2 + j]};
+        double dv[3];
+        cvo_position_distance(bc, p1, p2, dv);
+        double const d2 = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+        double const dinv = cvo_integer_power(d2, factor);
+        sum += dinv;
+        double const c = factor * dinv / d2 * 2.0;
+        double const gx = c * dv[0], gy = c * dv[1], gz = c * dv[2];
+        g1[0] += -1.0 * gx;
+        g1[1] += -1.0 * gy;
+        g1[2] += -1.0 * gz;
+        grad2[j] += gx;
+        grad2[n2 + j] += gy;
+        grad2[2 * n2 + j] += gz;
+      }
+      grad1[i] += g1[0];
+      grad1[n1 + i] += g1[1];
+      grad1[2 * n1 + i] += g1[2];
+    }
+  } else {
+    /* checker for large sizes, NOT the reference's summation order: rows in parallel and the
+     * scalar sum Kahan-compensated.  The reference adds ~N1*N2 positive terms of wildly
+     * different magnitude one after the other, which loses up to N1*N2*2^-53 relative (terms
+     * below half an ulp of the running sum vanish); this variant is what that loop would give
+     * in exact arithmetic, to ~1e-16. */
+    long double total = 0.0L;
+#pragma omp parallel
+    {
+      double *g2loc = (double *)calloc(3 * n2, sizeof(double));
+      long double tsum = 0.0L;
+#pragma omp for schedule(static)
+      for (long long ii = 0; ii < (long long)n1; ii++) {
+        size_t const i = (size_t)ii;
+        double const p1[3] = {pos1[i], pos1[n1 + i], pos1[2 * n1 + i]};
+        double g1[3] = {0, 0, 0};
+        double rs = 0.0, rc = 0.0; /* Kahan pair of this row */
+        for (size_t j = 0; j < n2; ++j) {
+          double const p2[3] = {pos2[j], pos2[n2 + j], pos2[2 * n2 + j]};
+          double dv[3];
+          cvo_position_distance(bc, p1, p2, dv);
+          double const d2 = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+          double const dinv = cvo_integer_power(d2, factor);
+          double const y = dinv - rc;
+          double const t = rs + y;
+          rc = (t - rs) - y;
+          rs = t;
+          double const c = factor * dinv / d2 * 2.0;
+          g1[0] += -1.0 * (c * dv[0]);
+          g1[1] += -1.0 * (c * dv[1]);
+          g1[2] += -1.0 * (c * dv[2]);
+          g2loc[j] += c * dv[0];
+          g2loc[n2 + j] += c * dv[1];
+          g2loc[2 * n2 + j] += c * dv[2];
+        }
+        tsum += (long double)rs - (long double)rc;
+        grad1[i] += g1[0];
+        grad1[n1 + i] += g1[1];
+        grad1[2 * n1 + i] += g1[2];
+      }
+#pragma omp critical
+      {
+        total += tsum;
+        for (size_t k = 0; k < 3 * n2; k++) grad2[k] += g2loc[k];
+      }
+      free(g2loc);
+    }
+    sum = (double)total;
+  }
+  double value = sum * (1.0 / (double)(n1 * n2));
+  value = pow(value, -1.0 / (double)exponent);
+  double const dxdsum =
+      (-1.0 / (double)exponent) * cvo_integer_power(value, exponent + 1) / (double)(n1 * n2);
+  for (size_t k = 0; k < 3 * n1; k++) grad1[k] = grad1[k] * dxdsum;
+  for (size_t k = 0; k < 3 * n2; k++) grad2[k] = grad2[k] * dxdsum;
+  return value;
+}

@@ -16,6 +16,8 @@ CASES = [
     "coordnum", "coordnum-pairlist", "coordnum-aniso", "coordnum-aniso-pairlist",
     "coordnum-group2centeronly", "selfcoordnum", "selfcoordnum-pairlist",
     "groupcoord", "groupcoord-aniso",
+    # widening: same pair-sweep skeleton, different pair function
+    "distanceinv",
 ]
 
 

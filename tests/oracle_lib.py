@@ -101,6 +101,9 @@ def lib():
     L.cvo_set_weighted_gradient.argtypes = [C.c_size_t, _dp, _dp, _dp]
     L.cvo_apply_colvar_force.argtypes = [C.c_size_t, C.POINTER(C.c_int), _dp, C.c_double, _dp,
                                          _dp]
+    L.cvo_distance_inv.restype = C.c_double
+    L.cvo_distance_inv.argtypes = [C.POINTER(Boundaries), C.c_int, C.c_size_t, _dp, C.c_size_t,
+                                   _dp, _dp, _dp, C.c_int]
     L.cvo_apply_roto_translation.argtypes = [C.POINTER(FitState), C.c_size_t, _dp, _dp, C.c_size_t,
                                              _dp, _dp]
     L.cvo_calc_fit_gradients.argtypes = [C.POINTER(FitState), C.c_size_t, _dp, _dp, C.c_size_t,
@@ -247,3 +250,15 @@ def switching_function(l2, en=6, ed=12, tol=0.0, flags=EF_GRADIENTS):
     d = C.c_double(0.0)
     f = L.cvo_switching_function(float(l2), C.byref(d), en, ed, float(tol), flags)
     return f, d.value
+
+
+def distance_inv(pos1, pos2, exponent=6, boundaries=None, omp=0):
+    """distance_inv::calc_value (src/colvarcomp_distances.cpp:405-456).  Returns
+    (value, grad1 (n1,3), grad2 (n2,3))."""
+    L = lib()
+    p = make_params(boundaries=boundaries)
+    n1, n2 = len(pos1), len(pos2)
+    g1, g2 = np.zeros(3 * n1), np.zeros(3 * n2)
+    v = L.cvo_distance_inv(C.byref(p.bc), int(exponent), n1, _ptr(soa(pos1)), n2,
+                           _ptr(soa(pos2)), _ptr(g1), _ptr(g2), int(omp))
+    return v, unsoa(g1, n1), unsoa(g2, n2)

@@ -25,9 +25,11 @@ CASES = [
     "coordnum", "coordnum-pairlist", "coordnum-aniso", "coordnum-aniso-pairlist",
     "coordnum-group2centeronly", "selfcoordnum", "selfcoordnum-pairlist",
     "groupcoord", "groupcoord-aniso",
+    # widening: distanceInv rides the same pair sweep
+    "distanceinv",
 ]
 
-KIND = {"coordNum": 0, "selfCoordNum": 1, "groupCoord": 2}
+KIND = {"coordNum": 0, "selfCoordNum": 1, "groupCoord": 2, "distanceInv": 3}
 
 
 @dataclass
@@ -44,6 +46,7 @@ class CvcConfig:
     group2_center_only: bool = False
     tolerance: float = 0.0
     pairlist_freq: int = 100
+    exponent: int = 6  # distanceInv (src/colvarcomp_distances.cpp:383)
     # harmonic bias
     centers: float = 0.0
     force_constant: float = 1.0
@@ -73,7 +76,7 @@ def _yes(v):
 def parse_test_in(path, index_groups):
     txt = Path(path).read_text()
     cfg = CvcConfig()
-    m = re.search(r"\b(coordNum|selfCoordNum|groupCoord)\s*\{", txt)
+    m = re.search(r"\b(coordNum|selfCoordNum|groupCoord|distanceInv)\s*\{", txt)
     cfg.function_type = m.group(1)
 
     def kv(key, default=None):
@@ -92,6 +95,7 @@ def parse_test_in(path, index_groups):
         cfg.cutoff3 = (float(c),) * 3
     cfg.exp_numer = int(kv("expNumer", 6))
     cfg.exp_denom = int(kv("expDenom", 12))
+    cfg.exponent = int(kv("exponent", 6))
     cfg.tolerance = float(kv("tolerance", 0.0))
     cfg.pairlist_freq = int(kv("pairListFrequency", 100))
     if cfg.function_type == "coordNum":
@@ -172,7 +176,12 @@ def run_oracle_case(cfg, frames):
         L.cvo_read_positions(n1, idx1.ctypes.data_as(C.POINTER(C.c_int)), O._ptr(proxy_pos),
                              O._ptr(pos1))
         rebuild = pl is not None and (step % cfg.pairlist_freq == 0)
-        if cfg.kind == 1:
+        if cfg.kind == 3:
+            pos2 = np.zeros(3 * n2)
+            L.cvo_read_positions(n2, idx2.ctypes.data_as(C.POINTER(C.c_int)), O._ptr(proxy_pos),
+                                 O._ptr(pos2))
+            v, g1, g2 = O.distance_inv(O.unsoa(pos1, n1), O.unsoa(pos2, n2), cfg.exponent)
+        elif cfg.kind == 1:
             v, g1 = O.selfcoordnum(p, O.unsoa(pos1, n1), pairlist=pl, rebuild=rebuild)
             g2 = np.zeros((0, 3))
         else:

@@ -66,7 +66,7 @@ def test_reference_regression_cases(case):
                      cutoff3=cfg.cutoff3, exp_numer=cfg.exp_numer, exp_denom=cfg.exp_denom,
                      group1_center_only=cfg.group1_center_only,
                      group2_center_only=cfg.group2_center_only, tolerance=cfg.tolerance,
-                     pairlist_freq=cfg.pairlist_freq)
+                     pairlist_freq=cfg.pairlist_freq, exponent=cfg.exponent)
     oracle = R.run_oracle_case(cfg, frames)
     results = []
     for step, xyz in enumerate(frames):
