@@ -47,7 +47,10 @@ for step in range(2):
 cv.apply_force(0.5, d_force)
 torch.cuda.synchronize()
 p = O.make_params()
-if self_:
+if kind == "distanceInv":
+    # the sum over ranks comes before the non-linear epilogue (DESIGN.md section 9)
+    ov, og1, og2 = O.distance_inv(pos[i1], pos[i2], 6, omp=4)
+elif self_:
     ov, og1 = O.selfcoordnum(p, pos, omp=4)
     og2 = None
 else:
@@ -78,7 +81,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("kind,n1,n2", [("coordNum", 5000, 20000), ("coordNum", 300, 30000),
-                                        ("selfCoordNum", 9000, 0)])
+                                        ("selfCoordNum", 9000, 0),
+                                        ("distanceInv", 3000, 40000)])
 def test_sharded_run_matches_oracle_on_every_rank(kind, n1, n2, tmp_path):
     import torch
     ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
