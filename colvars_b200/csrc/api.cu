@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -26,7 +27,8 @@ using namespace b200cv;
 
 namespace {
 
-std::string g_create_error;
+// message of the last failed b200cv_create on this thread (no handle exists to carry it)
+thread_local std::string g_create_error;
 
 // NVTX ranges around the phases of a step, named like the reference's GPU scheduler phases
 // (src/colvar_gpu_calc.cpp:711-722).  Header-only NVTX3: a no-op unless a profiler is attached.
@@ -65,9 +67,11 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::mutex mu;
   bool load(std::string &err)
   {
-    if (lib) return true;
+    std::lock_guard<std::mutex> lock(mu);
+    if (lib && AllReduce) return true;
     // picks up the copy already mapped into the process (e.g. torch's) or the system one
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {

@@ -1,6 +1,8 @@
 // sweep_inst.cu -- instantiations and dispatch of the tile sweep (sweep.cuh).
 #include "kernels.cuh"
 
+#include <atomic>
+
 namespace b200cv {
 
 // ============================ sweep dispatch =================================================
@@ -11,12 +13,17 @@ template <int EXP, bool ANISO, int PBC, bool PL>
 static int launch_sweep_t(const SweepArgs &args, int nitems, cudaStream_t stream)
 {
   auto kern = sweep_kernel<EXP, ANISO, PBC, PL, SWEEP_R, SWEEP_W, SWEEP_MINB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sweep_smem_bytes());
+  // the opt-in shared-memory size is a per-device function attribute
+  static std::atomic<unsigned long long> attr_done{0ull};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  unsigned long long const bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sweep_smem_bytes());
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   kern<<<nitems, SWEEP_W * 32, sweep_smem_bytes(), stream>>>(args);
   return (int)cudaGetLastError();

@@ -164,6 +164,9 @@ private:
 
 }  // namespace
 
+// defined by atomgroup_b200.cu when it is linked in front of the reference archive
+extern "C" int b200cv_atomgroup_kernels_linked(void) __attribute__((weak));
+
 int main(int argc, char **argv)
 {
   std::string config, traj, prefix;
@@ -200,6 +203,10 @@ int main(int argc, char **argv)
     for (auto &c : cv->get_cvcs()) gpu_route = gpu_route || c->has_gpu_implementation();
   }
   std::cout << "B200 components on the graph route: " << (gpu_route ? "yes" : "no") << "\n";
+  // which implementation of src/cuda/colvaratoms_kernel.h the atom groups' graphs were built on
+  std::cout << "atom-group kernels: "
+            << (b200cv_atomgroup_kernels_linked ? "b200 (atomgroup_b200.cu)" : "reference")
+            << "\n";
   double const max_gradient_error = cvmodule->get_max_gradient_error();
   if (max_gradient_error > 0.) {
     std::cout << "Max gradient error (debugGradients): " << max_gradient_error << "\n";

@@ -84,5 +84,8 @@ def test_reference_host_with_b200_components(case, route, tmp_path):
     if "debugGradients" in (d / "test.in").read_text():
         assert "Max gradient error" in r.stdout
     if route == "smp-gpu":
+        # gather / COM / fit / scatter graphs run on this repository's kernels, not on the
+        # archive member built from src/cuda/colvaratoms_kernel.cu
+        assert "atom-group kernels: b200" in r.stdout
         on_graph = "graph route: yes" in r.stdout
         assert on_graph == ("pairlist" not in case and "dummy" not in case), r.stdout[-500:]
