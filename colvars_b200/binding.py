@@ -66,7 +66,8 @@ SYMBOLS = [
     "b200cv_config_defaults", "b200cv_create", "b200cv_destroy", "b200cv_last_error",
     "b200cv_set_group", "b200cv_set_fitting", "b200cv_set_boundaries", "b200cv_read_data",
     "b200cv_calc_value", "b200cv_step", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
-    "b200cv_eval", "b200cv_eval_async", "b200cv_accumulate_gradients", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
+    "b200cv_eval", "b200cv_eval_async", "b200cv_accumulate_gradients",
+    "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
     "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_comm_unique_id",
@@ -104,6 +105,8 @@ def load():
     L.b200cv_eval.argtypes = [H, vp, vp, C.c_int, vp, vp, vp]
     L.b200cv_eval_async.argtypes = [H, vp, vp, C.c_int, vp, vp, vp]
     L.b200cv_accumulate_gradients.argtypes = [H, vp, vp, vp]
+    L.b200cv_pairlist_reserve.argtypes = [H, vp, vp, C.c_double, vp]
+    L.b200cv_pairlist_set_rebuild.argtypes = [H, C.c_int]
     L.b200cv_eval_host.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
     L.b200cv_calc_host.argtypes = [H, vp, sz, ll, C.c_int, _dp]
     L.b200cv_apply_force_host.argtypes = [H, C.c_double, vp, sz]
@@ -282,6 +285,26 @@ class CoordNum:
         g2 = C.c_void_p(grad2.data_ptr()) if grad2 is not None else None
         self._check(self._L.b200cv_eval(self._h, C.c_void_p(pos1.data_ptr()), p2, int(flags), g1,
                                         g2, _stream_ptr(stream)))
+
+    def eval_async(self, pos1, pos2=None, flags=EF_GRADIENTS, stream=None):
+        """Capturable evaluation (no synchronisation, no allocation): the scalar is fetched
+        with value() once the stream has drained, the gradients with accumulate_gradients()."""
+        p2 = C.c_void_p(pos2.data_ptr()) if pos2 is not None else None
+        self._check(self._L.b200cv_eval_async(self._h, C.c_void_p(pos1.data_ptr()), p2,
+                                              int(flags), None, None, _stream_ptr(stream)))
+
+    def accumulate_gradients(self, grad1, grad2=None, stream=None):
+        g2 = C.c_void_p(grad2.data_ptr()) if grad2 is not None else None
+        self._check(self._L.b200cv_accumulate_gradients(self._h, C.c_void_p(grad1.data_ptr()),
+                                                        g2, _stream_ptr(stream)))
+
+    def pairlist_reserve(self, pos1, pos2=None, headroom=2.0, stream=None):
+        p2 = C.c_void_p(pos2.data_ptr()) if pos2 is not None else None
+        self._check(self._L.b200cv_pairlist_reserve(self._h, C.c_void_p(pos1.data_ptr()), p2,
+                                                    float(headroom), _stream_ptr(stream)))
+
+    def pairlist_set_rebuild(self, rebuild):
+        self._check(self._L.b200cv_pairlist_set_rebuild(self._h, int(bool(rebuild))))
 
     def eval_host(self, pos1, pos2=None, flags=EF_GRADIENTS, grad1=None, grad2=None):
         """pos*/grad*: numpy SoA arrays (3, n) float64 in host memory; returns the value."""

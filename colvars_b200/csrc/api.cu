@@ -112,9 +112,14 @@ struct b200cv_cvc {
   double *d_value = nullptr;
   double *h_value = nullptr;                // mapped pinned
   double *h_value_dev = nullptr;            // device alias of h_value
-  unsigned long long *h_counters = nullptr; // mapped pinned [2]
+  unsigned long long *h_counters = nullptr; // mapped pinned [4]: rare, listed, gate mode, -
   unsigned long long *h_counters_dev = nullptr;
-  unsigned char *d_counters = nullptr;      // rare_count (u32 @0), pl_count (u64 @8)
+  unsigned char *d_counters = nullptr;      // rare_count (u32 @0), pl_count (u64 @8),
+                                            // persistent list length (u64 @16), gate (i32 @24)
+  // captured pair-list evaluations: 1 = the next launch rebuilds the list, 0 = it walks it
+  int *h_mode = nullptr;                    // mapped pinned, written by the host between launches
+  int *h_mode_dev = nullptr;
+  bool gated = false;                       // last evaluation was enqueued in gated form
   double *d_partials = nullptr;
   int partial_cap = 0;
 
@@ -173,6 +178,7 @@ struct b200cv_cvc {
   {
     return reinterpret_cast<unsigned long long *>(d_counters + 8);
   }
+  int *gate() const { return reinterpret_cast<int *>(d_counters + 24); }
   bool self() const { return cfg.kind == B200CV_SELFCOORDNUM; }
   bool dinv() const { return cfg.kind == B200CV_DISTANCEINV; }
   bool center1() const { return cfg.group1_center_only != 0; }
@@ -493,8 +499,13 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
   bool const rebuild = flags & B200CV_EF_REBUILD_PAIRLIST;
   h->launches = 0;
   int npart = 0;
+  bool const gated = h->gated && use_pl;
 
   CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, 16, stream));
+  if (gated) {
+    CUDA_OK(h, launch_fetch_gate(h->h_mode_dev, h->gate(), stream));
+    h->launches++;
+  }
 
   if (h->center1() || h->center2()) {
     // COM variants (src/colvarcomp_coordnums.cpp:190-247): O(N) work, reference-order pairs
@@ -505,6 +516,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     A.flags = flags;
     A.partials = h->d_partials;
     A.pairlist = use_pl ? h->d_pl_center : nullptr;
+    A.gate = gated ? h->gate() : nullptr;
     CUDA_OK(h, cudaMemsetAsync(G1.com_grad(), 0, 3 * sizeof(double), stream));
     CUDA_OK(h, cudaMemsetAsync(G2.com_grad(), 0, 3 * sizeof(double), stream));
     if (h->center1() && h->center2()) {
@@ -572,40 +584,50 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     bool const general_bc = (h->P.bc_type == 1 || h->P.bc_type == 3);
     bool const walk_list = use_pl && !rebuild && h->pl_valid;
 
-    if (walk_list) {
-      // non-rebuild step: only listed pairs (src/colvarcomp_coordnums.cpp:219-228)
+    // non-rebuild step: only listed pairs (src/colvarcomp_coordnums.cpp:219-228)
+    auto enqueue_walk = [&](double *partials, const int *gate) -> int {
       ExactArgs E{};
       E.x1 = x1; E.y1 = y1; E.z1 = z1; E.x2 = x2; E.y2 = y2; E.z2 = z2;
       E.g1x = g1x; E.g1y = g1y; E.g1z = g1z; E.g2x = g2x; E.g2y = g2y; E.g2z = g2z;
       E.list = h->d_pl;
-      E.count64 = h->pl_count() + 1;  // persistent copy of the list length (see below)
+      E.count64 = h->pl_count() + 1;  // persistent copy of the list length
       E.cap = h->pl_cap;
-      E.partials = h->d_partials;
+      E.partials = partials;
       E.flags = flags & ~B200CV_EF_REBUILD_PAIRLIST;
       E.fast_exp = (h->exp_special == 3 && h->P.bc_type == 0) ? 3 : 0;
+      E.gate = gate;
+      E.gate_on = 0;
       E.P = h->P;
       CUDA_OK(h, launch_exact(E, stream));
       h->launches++;
-      npart = EXACT_BLOCKS;
-    } else if (general_bc) {
-      DenseArgs D{};
-      D.x1 = x1; D.y1 = y1; D.z1 = z1; D.x2 = x2; D.y2 = y2; D.z2 = z2;
-      D.g1x = g1x; D.g1y = g1y; D.g1z = g1z; D.g2x = g2x; D.g2y = g2y; D.g2z = g2z;
-      D.n1 = G1.n;
-      D.n2 = G2.n;
-      D.self = h->self() ? 1 : 0;
-      D.i_begin = (int)((long long)G1.n * h->rank / h->world);
-      D.i_end = (int)((long long)G1.n * (h->rank + 1) / h->world);
-      D.partials = h->d_partials;
-      D.pl = rebuild ? h->d_pl : nullptr;
-      D.pl_cap = h->pl_cap;
-      D.pl_count = h->pl_count();
-      D.flags = flags;
-      D.P = h->P;
-      CUDA_OK(h, launch_dense(D, stream));
-      h->launches++;
-      npart = EXACT_BLOCKS;
-    } else {
+      return B200CV_OK;
+    };
+    // every pair: tile sweep (+ exact-pair queue) or, for mixed / triclinic cells, the dense
+    // kernel; records the pair list when `record`.  Returns the number of partial sums.
+    auto enqueue_all_pairs = [&](int sweep_flags, bool record, const int *gate,
+                                 int &nparts) -> int {
+      if (general_bc) {
+        DenseArgs D{};
+        D.x1 = x1; D.y1 = y1; D.z1 = z1; D.x2 = x2; D.y2 = y2; D.z2 = z2;
+        D.g1x = g1x; D.g1y = g1y; D.g1z = g1z; D.g2x = g2x; D.g2y = g2y; D.g2z = g2z;
+        D.n1 = G1.n;
+        D.n2 = G2.n;
+        D.self = h->self() ? 1 : 0;
+        D.i_begin = (int)((long long)G1.n * h->rank / h->world);
+        D.i_end = (int)((long long)G1.n * (h->rank + 1) / h->world);
+        D.partials = h->d_partials;
+        D.pl = record ? h->d_pl : nullptr;
+        D.pl_cap = h->pl_cap;
+        D.pl_count = h->pl_count();
+        D.flags = sweep_flags;
+        D.gate = gate;
+        D.gate_on = 1;
+        D.P = h->P;
+        CUDA_OK(h, launch_dense(D, stream));
+        h->launches++;
+        nparts = EXACT_BLOCKS;
+        return B200CV_OK;
+      }
       SweepArgs S{};
       S.x1 = x1; S.y1 = y1; S.z1 = z1; S.x2 = x2; S.y2 = y2; S.z2 = z2;
       S.g1x = g1x; S.g1y = g1y; S.g1z = g1z; S.g2x = g2x; S.g2y = g2y; S.g2z = g2z;
@@ -615,10 +637,12 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       S.rare_cap = h->rare_cap;
       S.rare_count = h->rare_count();
       S.pl = h->d_pl;
-      S.pl_cap = rebuild ? h->pl_cap : 0;  // all-true list before the first rebuild: no recording
+      S.pl_cap = record ? h->pl_cap : 0;  // all-true list before the first rebuild: no recording
       S.pl_count = h->pl_count();
       S.i_end = G1.n;
       S.want_grad = grad ? 1 : 0;
+      S.gate = gate;
+      S.gate_on = 1;
       S.P = h->P;
       int const pbc = h->P.bc_type == 2 ? BC_ORTHO : BC_NONE;
       CUDA_OK(h, launch_sweep(S, h->nitems, h->exp_special, h->aniso, pbc, use_pl, stream));
@@ -632,14 +656,35 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.count32 = h->rare_count();
       E.cap = h->rare_cap;
       E.partials = h->d_partials + std::max(h->nitems, 0);
-      E.pl = rebuild ? h->d_pl : nullptr;
+      E.pl = record ? h->d_pl : nullptr;
       E.pl_cap = h->pl_cap;
       E.pl_count = h->pl_count();
-      E.flags = flags;
+      E.flags = sweep_flags;
+      E.gate = gate;
+      E.gate_on = 1;
       E.P = h->P;
       CUDA_OK(h, launch_exact(E, stream));
       h->launches++;
-      npart = h->nitems + EXACT_BLOCKS;
+      nparts = h->nitems + EXACT_BLOCKS;
+      return B200CV_OK;
+    };
+
+    if (gated) {
+      // captured evaluation with a pair list: the graph holds the rebuild sweep AND the list
+      // walk; the mode word decides on the device which of the two does any work
+      int nparts = 0;
+      int rc = enqueue_all_pairs(flags | B200CV_EF_REBUILD_PAIRLIST, true, h->gate(), nparts);
+      if (rc) return rc;
+      rc = enqueue_walk(h->d_partials + nparts, h->gate());
+      if (rc) return rc;
+      npart = nparts + EXACT_BLOCKS;
+    } else if (walk_list) {
+      int rc = enqueue_walk(h->d_partials, nullptr);
+      if (rc) return rc;
+      npart = EXACT_BLOCKS;
+    } else {
+      int rc = enqueue_all_pairs(flags, rebuild, nullptr, npart);
+      if (rc) return rc;
     }
   }
 
@@ -651,6 +696,9 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
   F.rare_count = h->rare_count();
   F.pl_count = h->pl_count();
   F.h_counters = h->h_counters_dev;
+  F.gate = gated ? h->gate() : nullptr;
+  F.pl_persist = h->pl_count() + 1;
+  F.pl_cap = h->pl_cap;
   CUDA_OK(h, launch_finalize(F, stream));
   h->launches++;
 
@@ -707,7 +755,9 @@ int post_sync(b200cv_cvc *h, bool &redo)
 {
   redo = false;
   unsigned long long const rare_n = h->h_counters[0], pl_n = h->h_counters[1];
-  bool const rebuild = h->last_flags & B200CV_EF_REBUILD_PAIRLIST;
+  // gated (captured) evaluations: finalize_kernel reports the mode the finished launch ran in
+  bool const rebuild = h->gated ? (h->h_counters[2] == 1)
+                                : (bool)(h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
   h->exact_pairs = (size_t)rare_n;
   if (rare_n > h->rare_cap) {
     if (h->async_eval) {
@@ -722,6 +772,12 @@ int post_sync(b200cv_cvc *h, bool &redo)
     redo = true;
   }
   if (rebuild && !(h->center1() || h->center2())) {
+    if (pl_n > h->pl_cap && h->async_eval) {
+      return fail(h, B200CV_MEMORY_ERROR,
+                  "pair-list overflow in a captured evaluation (" + std::to_string(pl_n) +
+                      " listed pairs, capacity " + std::to_string(h->pl_cap) +
+                      "): reserve more with b200cv_pairlist_reserve before capturing");
+    }
     if (pl_n > h->pl_cap) {
       int rc = ensure_pairlist_capacity(h, pl_n);
       if (rc) return rc;
@@ -747,9 +803,10 @@ int sync_and_check(b200cv_cvc *h)
                   "pair queue overflow in a sharded run; raise the pair-list capacity");
     }
     if (!redo) {
-      bool const rebuild = h->last_flags & B200CV_EF_REBUILD_PAIRLIST;
+      bool const rebuild = !h->gated && (h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
       if (rebuild && !(h->center1() || h->center2())) {
-        // keep the list length on the device for the list-walk steps
+        // keep the list length on the device for the list-walk steps (gated evaluations
+        // do that in finalize_kernel)
         CUDA_OK(h, cudaMemcpyAsync(h->pl_count() + 1, &h->h_counters[1], 8,
                                    cudaMemcpyHostToDevice, h->last_stream));
         CUDA_OK(h, cudaStreamSynchronize(h->last_stream));
@@ -860,10 +917,13 @@ int b200cv_create(const b200cv_config *cfg, b200cv_cvc **out)
   CREATE_OK(cudaSetDevice(c.device));
   CREATE_OK(cudaHostAlloc(&h->h_value, sizeof(double), cudaHostAllocMapped));
   CREATE_OK(cudaHostGetDevicePointer(&h->h_value_dev, h->h_value, 0));
-  CREATE_OK(cudaHostAlloc(&h->h_counters, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+  CREATE_OK(cudaHostAlloc(&h->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
   CREATE_OK(cudaHostGetDevicePointer(&h->h_counters_dev, h->h_counters, 0));
-  h->h_counters[0] = h->h_counters[1] = 0;
+  h->h_counters[0] = h->h_counters[1] = h->h_counters[2] = h->h_counters[3] = 0;
   *h->h_value = 0.0;
+  CREATE_OK(cudaHostAlloc(&h->h_mode, sizeof(int), cudaHostAllocMapped));
+  CREATE_OK(cudaHostGetDevicePointer(&h->h_mode_dev, h->h_mode, 0));
+  *h->h_mode = 1;
   CREATE_OK(cudaMalloc(&h->d_counters, 32));
   CREATE_OK(cudaMemset(h->d_counters, 0, 32));
   CREATE_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -900,6 +960,7 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_stage_pos);
   if (h->h_value) cudaFreeHost(h->h_value);
   if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->h_mode) cudaFreeHost(h->h_mode);
   if (h->h_stage_grad) cudaFreeHost(h->h_stage_grad);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -1260,6 +1321,7 @@ static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2
   h->have_calc = true;
   h->data_read = true;
   h->async_eval = !sync;
+  h->gated = !sync && (flags & B200CV_EF_USE_PAIRLIST);
   rc = enqueue_calc(h, flags, s);
   if (rc) return rc;
   if (sync) {
@@ -1286,10 +1348,12 @@ int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int f
 int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
                       double *d_grad1, double *d_grad2, void *stream)
 {
-  if (h && (flags & B200CV_EF_USE_PAIRLIST) && h->cfg.tolerance > 0) {
-    return fail(h, B200CV_NOT_IMPLEMENTED,
-                "b200cv_eval_async cannot be used with a pair list (the rebuild needs a host "
-                "round trip); use b200cv_eval");
+  if (h && (flags & B200CV_EF_USE_PAIRLIST) && h->cfg.tolerance > 0 &&
+      h->cfg.kind != B200CV_GROUPCOORD) {
+    // gated form: rebuild sweep and list walk are both enqueued, b200cv_pairlist_set_rebuild
+    // picks one per launch.  The list (allocated by b200cv_set_group) cannot grow under a
+    // captured graph: size it with b200cv_pairlist_reserve first.
+    if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
   }
   if (h && h->items_dirty) {
     // allocations are not capturable: build the work-item table before any stream capture
@@ -1303,6 +1367,50 @@ int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
     }
   }
   return eval_device(h, d_pos1, d_pos2, flags, d_grad1, d_grad2, stream, false);
+}
+
+int b200cv_pairlist_set_rebuild(b200cv_cvc *h, int rebuild)
+{
+  if (!h) return B200CV_BUG_ERROR;
+  *h->h_mode = rebuild ? 1 : 0;  // mapped pinned: read by fetch_gate_kernel of the next launch
+  return B200CV_OK;
+}
+
+int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
+                            double headroom, void *stream)
+{
+  if (!h) return B200CV_BUG_ERROR;
+  if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD || h->center1() ||
+      h->center2()) {
+    // no compacted list to size (dense flags of fixed length, or none); still make sure
+    // nothing is left to allocate inside a capture
+    CUDA_OK(h, cudaSetDevice(h->cfg.device));
+    if (h->center1() || h->center2()) return ensure_partials(h, 2 * EXACT_BLOCKS);
+    if (h->items_dirty) return build_items(h);
+    return B200CV_OK;
+  }
+  // one synchronous rebuild sweep on the current positions (value only): grows the list until
+  // it fits, then adds the headroom
+  int rc = eval_device(h, d_pos1, d_pos2,
+                       B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST, nullptr, nullptr,
+                       stream, true);
+  if (rc) return rc;
+  if (!(headroom >= 1.0)) headroom = 1.0;
+  unsigned long long const n1 = h->g[0].n, n2 = h->self() ? n1 : h->g[1].n;
+  unsigned long long const pairs = h->self() ? n1 * (n1 - 1) / 2 : n1 * n2;
+  unsigned long long want = (unsigned long long)std::ceil(headroom * (double)h->pl_n) + 1024;
+  want = std::min(want, pairs);
+  if (want > h->pl_cap) {
+    // ensure_pairlist_capacity over-allocates by 1.5x: ask for exactly `want`
+    free_dev(h->d_pl);
+    h->epoch++;
+    CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * want));
+    h->pl_cap = want;
+  }
+  h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1)
+  h->pl_n = 0;
+  *h->h_mode = 1;
+  return B200CV_OK;
 }
 
 int b200cv_accumulate_gradients(b200cv_cvc *h, double *d_grad1, double *d_grad2, void *stream)

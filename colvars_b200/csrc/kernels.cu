@@ -29,6 +29,10 @@ template <int THREADS> __device__ __forceinline__ double block_sum(double v, dou
 __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_constant__ ExactArgs A)
 {
   __shared__ double red[EXACT_THREADS / 32];
+  if (A.gate != nullptr && *A.gate != A.gate_on) {
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
+    return;
+  }
   unsigned long long n = A.count32 ? (unsigned long long)*A.count32 : *A.count64;
   if (n > A.cap) n = A.cap;
   bool const grad = A.flags & EF_GRADIENTS;
@@ -87,6 +91,10 @@ int launch_exact(const ExactArgs &args, cudaStream_t stream)
 __global__ void __launch_bounds__(EXACT_THREADS) dense_kernel(const __grid_constant__ DenseArgs A)
 {
   __shared__ double red[EXACT_THREADS / 32];
+  if (A.gate != nullptr && *A.gate != A.gate_on) {
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
+    return;
+  }
   bool const grad = A.flags & EF_GRADIENTS;
   bool const rebuild = (A.flags & EF_REBUILD_PAIRLIST) && A.pl;
   double fsum = 0.0;
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) center_kernel(const __grid_cons
   __shared__ double red[EXACT_THREADS / 32];
   bool const grad = A.flags & EF_GRADIENTS;
   bool const use_pl = A.flags & EF_USE_PAIRLIST;
-  bool const rebuild = A.flags & EF_REBUILD_PAIRLIST;
+  bool const rebuild = A.gate ? (*A.gate == 1) : (bool)(A.flags & EF_REBUILD_PAIRLIST);
   double const cx = A.center[0], cy = A.center[1], cz = A.center[2];
   double fsum = 0.0, sgx = 0.0, sgy = 0.0, sgz = 0.0;
   if (A.n == 0) {
@@ -218,6 +226,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
       A.h_counters[0] = A.rare_count ? (unsigned long long)*A.rare_count : 0ull;
       A.h_counters[1] = A.pl_count ? *A.pl_count : 0ull;
     }
+    if (A.gate) {
+      int const mode = *A.gate;
+      if (A.h_counters) A.h_counters[2] = (unsigned long long)mode;
+      if (mode == 1 && A.pl_persist) {
+        unsigned long long const n = *A.pl_count;
+        *A.pl_persist = n < A.pl_cap ? n : A.pl_cap;
+      }
+    }
     if (A.h_value) {
       __threadfence_system();
       *A.h_value = red[0];
@@ -228,6 +244,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream)
 {
   finalize_kernel<<<1, 256, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+__global__ void fetch_gate_kernel(const int *h_mode_dev, int *d_gate) { *d_gate = *h_mode_dev; }
+
+int launch_fetch_gate(const int *h_mode_dev, int *d_gate, cudaStream_t stream)
+{
+  fetch_gate_kernel<<<1, 1, 0, stream>>>(h_mode_dev, d_gate);
   return (int)cudaGetLastError();
 }
 

@@ -43,6 +43,8 @@ struct ExactArgs {
   unsigned long long *pl_count;
   int flags;                           // EF_*
   int fast_exp;                        // 3: pair-list walk may use the sweep's fast 6/12 form
+  const int *gate;                     // see SweepArgs::gate
+  int gate_on;
   PairParams P;
 };
 constexpr int EXACT_BLOCKS = 296;
@@ -63,6 +65,8 @@ struct DenseArgs {
   unsigned long long pl_cap;
   unsigned long long *pl_count;
   int flags;
+  const int *gate;  // see SweepArgs::gate
+  int gate_on;
   PairParams P;
 };
 int launch_dense(const DenseArgs &args, cudaStream_t stream);
@@ -81,6 +85,7 @@ struct CenterArgs {
   unsigned char *pairlist;  // dense bool per pair (n entries) or NULL
   double *partials;         // [EXACT_BLOCKS]
   int flags;
+  const int *gate;          // non-null: *gate (1 rebuild / 0 walk) replaces EF_REBUILD_PAIRLIST
   PairParams P;
 };
 int launch_center(const CenterArgs &args, cudaStream_t stream);
@@ -94,9 +99,16 @@ struct FinalizeArgs {
   double *h_value;  // mapped pinned
   const unsigned int *rare_count;
   const unsigned long long *pl_count;
-  unsigned long long *h_counters;  // mapped pinned [2]: rare_count, pl_count
+  unsigned long long *h_counters;  // mapped pinned [4]: rare_count, pl_count, gate mode, unused
+  // gated evaluations: after a rebuild (*gate == 1) the list length is kept on the device
+  const int *gate;
+  unsigned long long *pl_persist;
+  unsigned long long pl_cap;
 };
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
+
+// copies the host-written mode word (mapped pinned) into device memory once per evaluation
+int launch_fetch_gate(const int *h_mode_dev, int *d_gate, cudaStream_t stream);
 
 // distanceInv epilogue (src/colvarcomp_distances.cpp:442-455): *d_value holds sum_ij d^-n
 // (already reduced over ranks); x = (sum / npairs)^(-1/n) replaces it and every gradient entry

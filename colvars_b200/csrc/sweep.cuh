@@ -67,6 +67,10 @@ struct SweepArgs {
   unsigned long long *pl_count;
   int i_end;      // group1 atoms with index >= i_end do not exist
   int want_grad;  // 0: value only (no gradient flush)
+  // captured (graph) pair-list evaluations enqueue the rebuild sweep AND the list walk; each
+  // kernel runs only when the device word *gate equals gate_on (null: always)
+  const int *gate;
+  int gate_on;
   PairParams P;
 };
 
@@ -384,6 +388,12 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
   __shared__ __align__(8) uint64_t mbar;
   __shared__ double red[W];
 
+  if constexpr (PL) {
+    if (A.gate != nullptr && *A.gate != A.gate_on) {
+      if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
+      return;
+    }
+  }
   SweepItem const item = A.items[blockIdx.x];
   int const lane = threadIdx.x & 31;
   int const warp = threadIdx.x >> 5;

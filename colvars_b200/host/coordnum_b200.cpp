@@ -274,8 +274,7 @@ void coordnum_b200::calc_gradients()
 
 bool coordnum_b200::has_gpu_implementation() const
 {
-  return cvmodule->proxy->get_smp_mode() == colvarproxy_smp::smp_mode_t::gpu &&
-         !(tolerance > 0) && !dummy2;
+  return cvmodule->proxy->get_smp_mode() == colvarproxy_smp::smp_mode_t::gpu && !dummy2;
 }
 
 namespace {
@@ -307,7 +306,17 @@ int coordnum_b200::add_calc_value_node(
   static_cast<boundaries_view const &>(boundary_conditions).push(engine);
   auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
   const double *p2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_pos : nullptr;
-  int const flags = is_enabled(f_cvc_gradient) ? B200CV_EF_GRADIENTS : B200CV_EF_NULL;
+  int flags = is_enabled(f_cvc_gradient) ? B200CV_EF_GRADIENTS : B200CV_EF_NULL;
+  if (tolerance > 0 && function_type() != "groupCoord") {
+    // pair list inside the graph: rebuild sweep and list walk are both captured, the engine's
+    // mode word (set in calc_value_after_gpu for the next step) picks one on the device.
+    // The list cannot grow under a graph, so size it now on the positions the read_data graph
+    // has just produced (src/colvar_gpu_calc.cpp:249-251 synchronises before this point).
+    flags |= B200CV_EF_USE_PAIRLIST;
+    if (b200cv_pairlist_reserve(engine, b1.d_atoms_pos, p2, 2.0, capture_stream) != B200CV_OK) {
+      return b200_error(COLVARS_ERROR);
+    }
+  }
   // gradients stay in the engine's buffers until add_calc_gradients_node hands them over:
   // debug_gradients_gpu relaunches this graph many times (src/colvarcomp.cpp:986-996)
   int const rc = capture_into(graph, capture_stream, [&]() {
@@ -322,6 +331,10 @@ int coordnum_b200::calc_value_after_gpu()
   // the scheduler has synchronised the stream; the scalar sits in mapped pinned memory
   int const rc = b200cv_value(engine, &x.real_value);
   if (rc != B200CV_OK) return b200_error(rc);
+  if (tolerance > 0) {
+    // compute_coordnum's rebuild test (src/colvarcomp_coordnums.cpp:255) for the NEXT launch
+    b200cv_pairlist_set_rebuild(engine, (cvmodule->step_relative() + 1) % pairlist_freq == 0);
+  }
   return COLVARS_OK;
 }
 

@@ -28,8 +28,8 @@ public:
 
 #if defined(COLVARS_CUDA)
   // `smp gpu` (src/colvar_gpu_calc.cpp:268-437): this component contributes graph nodes
-  // that work on the atom groups' device buffers (colvaratoms_gpu_buffer_t).  Components
-  // with a pair list keep the CPU-buffer route (their rebuild needs a host round trip).
+  // that work on the atom groups' device buffers (colvaratoms_gpu_buffer_t).  With a pair
+  // list the one captured graph holds the rebuild sweep and the list walk; a mode word picks.
   bool has_gpu_implementation() const override;
   int add_calc_value_node(cudaGraph_t &graph,
                           std::unordered_map<std::string, cudaGraphNode_t> &nodes_map) override;

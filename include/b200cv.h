@@ -162,6 +162,19 @@ int b200cv_eval(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int f
 int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2, int flags,
                       double *d_grad1, double *d_grad2, void *stream);
 
+/* Pair list under a captured graph (`smp gpu` route).  b200cv_eval_async with
+ * B200CV_EF_USE_PAIRLIST enqueues the rebuild sweep AND the list walk; a mode word written by
+ * the host between launches selects on the device which of the two does any work, so the same
+ * instantiated graph serves rebuild and list steps (compute_coordnum's
+ * `step_relative() % pairListFrequency == 0`, src/colvarcomp_coordnums.cpp:255, evaluated by the
+ * caller).  The mode starts at "rebuild".  Buffers cannot grow while a graph holds their
+ * addresses: b200cv_pairlist_reserve runs one synchronous rebuild on the current positions
+ * and sizes the list to headroom x the number of listed pairs (>= 1); a later overflow is
+ * reported by b200cv_value as B200CV_MEMORY_ERROR. */
+int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
+                            double headroom, void *stream);
+int b200cv_pairlist_set_rebuild(b200cv_cvc *h, int rebuild);
+
 /* d_grad1 / d_grad2 (d_atoms_grad layout) += the gradients of the last evaluation, with
  * atomics (groups may be shared between components).  Only enqueues work: this is the node
  * add_calc_gradients_node contributes when add_calc_value_node evaluated with

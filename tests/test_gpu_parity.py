@@ -578,3 +578,75 @@ def test_config5_full_size_properties():
     # (d) translation
     v2 = cv.calc_host(proxy + np.array([1.5, -2.5, 0.75]))
     close_val(v2, v, 1e-11)
+
+
+@pytest.mark.parametrize("kind,center", [("selfCoordNum", False), ("coordNum", False),
+                                         ("coordNum", True)])
+def test_pairlist_inside_one_captured_graph(kind, center):
+    """`smp gpu` route with a pair list: ONE captured graph (b200cv_eval_async +
+    b200cv_accumulate_gradients) is replayed for rebuild and list-walk steps alike; the mode
+    word set by the host between launches decides on the device which branch works.  Checked
+    per step against the synchronous path of a second handle and against the oracle."""
+    import torch
+    cb = _cb()
+    rng = np.random.default_rng(5)
+    n1, n2 = (1500, 0) if kind == "selfCoordNum" else (400, 3000)
+    L = 22.0
+    pos = rng.random((n1 + n2, 3)) * L
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32) if n2 else None
+    freq, tol, nsteps = 3, 0.01, 8
+    kw = dict(cutoff=4.0, tolerance=tol, pairlist_freq=freq)
+    if center:
+        kw["group2_center_only"] = True
+    cv = cb.CoordNum(kind, i1, i2, **kw)       # captured
+    ref = cb.CoordNum(kind, i1, i2, **kw)      # synchronous twin
+    p1 = torch.tensor(np.ascontiguousarray(pos[i1].T), device="cuda")
+    p2 = torch.tensor(np.ascontiguousarray(pos[i2].T), device="cuda") if n2 else None
+    g1 = torch.zeros_like(p1)
+    g2 = torch.zeros_like(p2) if n2 else None
+    flags = cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST
+    side = torch.cuda.Stream()
+    cv.pairlist_reserve(p1, p2, headroom=2.0, stream=side)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        cv.eval_async(p1, p2, flags, stream=side)
+        cv.accumulate_gradients(g1, g2, stream=side)
+    p = O.make_params((4.0,) * 3, tolerance=tol)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else (n1 if center else n1 * n2)
+    pl = np.ones(npairs, dtype=np.uint8)
+    for step in range(nsteps):
+        frame = pos + rng.normal(0, 0.03, pos.shape) * step
+        p1.copy_(torch.tensor(np.ascontiguousarray(frame[i1].T)))
+        if n2:
+            p2.copy_(torch.tensor(np.ascontiguousarray(frame[i2].T)))
+            g2.zero_()
+        g1.zero_()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()  # the reference's scheduler syncs before calc_value_after_gpu
+        v = cv.value()
+        # what the host shim does in calc_value_after_gpu: mode of the NEXT launch
+        cv.pairlist_set_rebuild((step + 1) % freq == 0)
+        rebuild = step % freq == 0
+        rf = flags | (cb.EF_REBUILD_PAIRLIST if rebuild else 0)
+        rg1 = torch.zeros_like(p1)
+        rg2 = torch.zeros_like(p2) if n2 else None
+        ref.eval(p1, p2, rf, rg1, rg2)
+        rv = ref.value()
+        torch.cuda.synchronize()
+        assert v == rv or abs(v - rv) <= 1e-13 * abs(rv)
+        close_arr(g1.cpu().numpy(), rg1.cpu().numpy(), 1e-13)
+        if n2:
+            close_arr(g2.cpu().numpy(), rg2.cpu().numpy(), 1e-13)
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild,
+                                      g2_center_only=center)
+            close_arr(g2.cpu().numpy().T, og2, 1e-11 if center else RTOL)
+        close_val(v, ov, 1e-11 if center else RTOL)
+        close_arr(g1.cpu().numpy().T, og1, 1e-11 if center else RTOL)
+        if not center:
+            assert np.array_equal(np.sort(cv.pairlist()), np.sort(ref.pairlist()))
