@@ -1160,6 +1160,7 @@ int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, voi
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   int const flags = calc_flags(h, step_relative, gradients);
   h->async_eval = false;
+  h->gated = false;
   h->last_stream = (cudaStream_t)stream;
   h->last_step = step_relative;
   h->last_flags = flags;
@@ -1176,6 +1177,7 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t user = (cudaStream_t)stream;
   int const flags = calc_flags(h, step_relative, gradients);
+  h->gated = false;  // this entry keeps one graph per flag set instead of gating
   bool const fitted = h->g[0].fit.active || h->g[1].fit.active;
   auto plain = [&]() -> int {
     int rc = b200cv_read_data(h, d_proxy_pos, proxy_stride, stream);
@@ -1239,6 +1241,7 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
   CUDA_OK(h, cudaGraphLaunch(hit->exec, user));
   h->launches = hit->launches;
   h->async_eval = false;
+  h->gated = false;
   h->last_stream = user;
   h->last_step = step_relative;
   h->last_flags = flags;
@@ -1453,6 +1456,7 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, 
     flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
   }
   h->async_eval = false;
+  h->gated = false;
   h->last_stream = s;
   h->last_flags = flags;
   h->have_calc = true;
