@@ -466,6 +466,34 @@ bool groups_ready(b200cv_cvc *h)
   return h->g[0].d_index && (h->self() || h->g[1].d_index);
 }
 
+// calc_required_properties (src/colvaratoms.cpp:1325-1352): COM and COG of a group as read
+// (and fitted).  The pair sweep never reads them, so they are computed with the step only
+// for a group that enters as its centre (group{1,2}CenterOnly, groupCoord) and otherwise on
+// demand (b200cv_get_centers): two launch-bound reductions less per step.
+bool centers_in_step(const b200cv_cvc *h, const Group &G)
+{
+  return (&G == &h->g[0]) ? h->center1() : h->center2();
+}
+
+int centers_now(b200cv_cvc *h, Group &G, cudaStream_t s)
+{
+  CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(),
+                            G.d_com_scratch, G.d_com_ticket, s));
+  return B200CV_OK;
+}
+
+int centers_after_read(b200cv_cvc *h, Group &G, cudaStream_t s)
+{
+  if (!centers_in_step(h, G)) return B200CV_OK;
+  return centers_now(h, G, s);
+}
+
+#define CUDA_OK_RC(expr)          \
+  do {                            \
+    int rc_ = (expr);             \
+    if (rc_ != B200CV_OK) return rc_; \
+  } while (0)
+
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->pl_cap && h->d_pl) return B200CV_OK;
@@ -1146,7 +1174,7 @@ int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stri
     rc = fit_read_and_apply(G.fit, d_proxy_pos, proxy_stride, 0, G.d_pos, G.stride, G.n, s, err);
     if (rc) return fail(h, rc, err);
     // calc_required_properties (src/colvaratoms.cpp:1325-1352)
-    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(), G.d_com_scratch, G.d_com_ticket, s));
+    CUDA_OK_RC(centers_after_read(h, G, s));
   }
   h->data_read = true;
   return B200CV_OK;
@@ -1310,11 +1338,11 @@ static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2
   if (rc) return rc;
   Group &G1 = h->g[0];
   CUDA_OK(h, launch_repack(d_pos1, (size_t)G1.n, G1.d_pos, G1.stride, G1.n, 0, s));
-  CUDA_OK(h, launch_com_cog(G1.d_pos, G1.stride, G1.d_mass, G1.total_mass, G1.n, G1.com(), G1.cog(), G1.d_com_scratch, G1.d_com_ticket, s));
+  CUDA_OK_RC(centers_after_read(h, G1, s));
   if (!h->self()) {
     Group &G2 = h->g[1];
     CUDA_OK(h, launch_repack(d_pos2, (size_t)G2.n, G2.d_pos, G2.stride, G2.n, 0, s));
-    CUDA_OK(h, launch_com_cog(G2.d_pos, G2.stride, G2.d_mass, G2.total_mass, G2.n, G2.com(), G2.cog(), G2.d_com_scratch, G2.d_com_ticket, s));
+    CUDA_OK_RC(centers_after_read(h, G2, s));
   }
   if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
     flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
@@ -1450,7 +1478,7 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, 
     CUDA_OK(h, cudaMemcpy2DAsync(G.d_pos, sizeof(double) * G.stride, hp[k],
                                  sizeof(double) * G.n, sizeof(double) * G.n, 3,
                                  cudaMemcpyHostToDevice, s));
-    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(), G.d_com_scratch, G.d_com_ticket, s));
+    CUDA_OK_RC(centers_after_read(h, G, s));
   }
   if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
     flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
@@ -1516,7 +1544,7 @@ int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
     std::string err;
     rc = fit_read_and_apply(G.fit, h->d_stage_pos, n_proxy, 1, G.d_pos, G.stride, G.n, s, err);
     if (rc) return fail(h, rc, err);
-    CUDA_OK(h, launch_com_cog(G.d_pos, G.stride, G.d_mass, G.total_mass, G.n, G.com(), G.cog(), G.d_com_scratch, G.d_com_ticket, s));
+    CUDA_OK_RC(centers_after_read(h, G, s));
   }
   h->data_read = true;
   rc = b200cv_calc_value(h, step_relative, gradients, s);
@@ -1629,6 +1657,13 @@ int b200cv_get_centers(b200cv_cvc *h, int which, double com[3], double cog[3])
   if (!G.d_centers) return fail(h, B200CV_INPUT_ERROR, "group not defined");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   CUDA_OK(h, cudaDeviceSynchronize());
+  if (!centers_in_step(h, G)) {
+    // not part of the step for this group: reduce the positions it currently holds
+    if (!h->data_read) return fail(h, B200CV_BUG_ERROR, "centers requested before read_data");
+    int rc = centers_now(h, G, h->own_stream);
+    if (rc) return rc;
+    CUDA_OK(h, cudaStreamSynchronize(h->own_stream));
+  }
   double c[6];
   CUDA_OK(h, cudaMemcpy(c, G.d_centers, sizeof(c), cudaMemcpyDeviceToHost));
   if (com) std::memcpy(com, c, 3 * sizeof(double));
