@@ -18,6 +18,8 @@ CASES = [
     "groupcoord", "groupcoord-aniso",
     # widening: same pair-sweep skeleton, different pair function
     "distanceinv",
+    # the single-pair user of the same pair function (colvar::h_bond)
+    "hbond",
 ]
 
 

@@ -29,6 +29,12 @@ CASES = [
     "distanceinv",
 ]
 
+# colvar::h_bond (src/colvarcomp_coordnums.cpp:323-469): ONE pair through compute_pair_coordnum
+# (acceptor = first atom, donor = second, r0 = 3.3, 6/8 by default).  Its golden pins the pair
+# function with general exponents; it is evaluated as a 1 x 1 coordNum here.  Not part of
+# CASES: the host shim leaves "hBond" to the reference (nothing to accelerate in one pair).
+PAIR_CASES = ["hbond"]
+
 KIND = {"coordNum": 0, "selfCoordNum": 1, "groupCoord": 2, "distanceInv": 3}
 
 
@@ -76,8 +82,9 @@ def _yes(v):
 def parse_test_in(path, index_groups):
     txt = Path(path).read_text()
     cfg = CvcConfig()
-    m = re.search(r"\b(coordNum|selfCoordNum|groupCoord|distanceInv)\s*\{", txt)
+    m = re.search(r"\b(coordNum|selfCoordNum|groupCoord|distanceInv|hBond)\s*\{", txt)
     cfg.function_type = m.group(1)
+    is_hbond = cfg.function_type == "hBond"
 
     def kv(key, default=None):
         mm = re.search(r"^\s*" + key + r"\s+(.+?)\s*$", txt, re.M | re.I)
@@ -94,7 +101,14 @@ def parse_test_in(path, index_groups):
     if c and not c3:
         cfg.cutoff3 = (float(c),) * 3
     cfg.exp_numer = int(kv("expNumer", 6))
-    cfg.exp_denom = int(kv("expDenom", 12))
+    cfg.exp_denom = int(kv("expDenom", 8 if is_hbond else 12))
+    if is_hbond:
+        # acceptor first, donor second (src/colvarcomp_coordnums.cpp:356-361)
+        cfg.function_type = "coordNum"
+        cfg.group1 = [int(kv("acceptor"))]
+        cfg.group2 = [int(kv("donor"))]
+        if not c:
+            cfg.cutoff3 = (3.3, 3.3, 3.3)
     cfg.exponent = int(kv("exponent", 6))
     cfg.tolerance = float(kv("tolerance", 0.0))
     cfg.pairlist_freq = int(kv("pairListFrequency", 100))

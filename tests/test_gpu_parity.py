@@ -53,7 +53,7 @@ def test_reciprocal_is_within_two_ulp():
         assert cb.selftest_rcp(0, 1 << 20, lo, hi) <= 2.0
 
 
-@pytest.mark.parametrize("case", R.CASES)
+@pytest.mark.parametrize("case", R.CASES + R.PAIR_CASES)
 def test_reference_regression_cases(case):
     """The reference's own coordnum regression inputs (5 frames of deca-alanine) through
     the host-buffer C-ABI step, against the golden traj/forces (the reference comparer's

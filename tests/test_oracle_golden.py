@@ -1,5 +1,6 @@
 """Pin the CPU oracle (oracle/coordnum_oracle.c) against the reference's own golden
-files for the coordination-number path: 9 regression cases x 5 frames,
+files for the coordination-number path: the 9 coordnum / groupcoord
+regression cases, hbond (the single-pair user of the same pair function) and distanceinv, 5 frames each:
 value + applied force (%.14e) and 104x3 per-atom forces (%.12e).
 
 The bar here is stricter than the reference's comparer (spiff, rel 1e-6): the oracle has
@@ -10,7 +11,7 @@ import pytest
 from . import regression as R
 
 
-@pytest.mark.parametrize("case", R.CASES)
+@pytest.mark.parametrize("case", R.CASES + R.PAIR_CASES)
 def test_oracle_reproduces_reference_golden_text(case):
     cfg, frames, traj, forces = R.load_case(case)
     assert len(frames) == 5 and frames[0].shape == (104, 3)
