@@ -412,7 +412,7 @@ def main():
     barrier()
     ev = [(torch.cuda.Event(True), torch.cuda.Event(True), torch.cuda.Event(True),
            torch.cuda.Event(True)) for _ in range(args.steps)]
-    launches = 0
+    launches0 = cb.kernel_launches()  # counted by the library itself, one per kernel launch
     value = 0.0
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
@@ -428,10 +428,7 @@ def main():
         value = cv.value()
         cv.apply_force(k_force * (value - 0.1), d_force, stream)
         e1.record(stream)
-        ng = 1 if w["kind"] == "selfCoordNum" else 2
-        launches += 2 * ng + cv.last_stats()[0] + ng  # gather+COM per group, calc, scatter
-        if fitted:
-            launches += 10  # cog, 2 translate, corr, eigen, rotate, fit-grad reduce/apply, scatter
+    launches = cb.kernel_launches() - launches0
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else {}

@@ -5,9 +5,11 @@ host/      C++ `colvar::cvc` shim for the unmodified Colvars host (see INTEGRATI
 binding.py ctypes plumbing used by tests/ and bench.py
 """
 from .binding import (CoordNum, B200cvError, load, comm_unique_id, plan_items, fp64_peak, selftest_rcp,
+                      kernel_launches,
                       EF_NULL, EF_GRADIENTS, EF_USE_PAIRLIST, EF_REBUILD_PAIRLIST, LIB_PATH,
                       SYMBOLS)
 
 __all__ = ["CoordNum", "B200cvError", "load", "comm_unique_id", "plan_items", "fp64_peak", "selftest_rcp",
+           "kernel_launches",
            "EF_NULL", "EF_GRADIENTS", "EF_USE_PAIRLIST", "EF_REBUILD_PAIRLIST", "LIB_PATH",
            "SYMBOLS"]

@@ -70,7 +70,7 @@ SYMBOLS = [
     "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
-    "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_comm_unique_id",
+    "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_kernel_launches", "b200cv_comm_unique_id",
     "b200cv_comm_init", "b200cv_set_shard", "b200cv_plan_items", "b200cv_fp64_peak", "b200cv_selftest_rcp",
 ]
 
@@ -119,6 +119,8 @@ def load():
     L.b200cv_pairlist_count.argtypes = [H, C.POINTER(sz)]
     L.b200cv_pairlist_export.argtypes = [H, C.POINTER(C.c_uint64), sz]
     L.b200cv_last_stats.argtypes = [H, _ip, C.POINTER(sz)]
+    L.b200cv_kernel_launches.argtypes = []
+    L.b200cv_kernel_launches.restype = C.c_ulonglong
     L.b200cv_comm_unique_id.argtypes = [C.c_char_p]
     L.b200cv_comm_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     L.b200cv_set_shard.argtypes = [H, C.c_int, C.c_int]
@@ -382,6 +384,11 @@ def _host_ptr(a):
     # torch CPU tensor (pinned or not)
     assert (not a.is_cuda) and a.is_contiguous() and a.dim() == 2 and a.shape[1] == 3
     return C.c_void_p(a.data_ptr()), a.shape[0]
+
+
+def kernel_launches():
+    """Kernels launched by libb200cv in this process so far."""
+    return int(load().b200cv_kernel_launches())
 
 
 def plan_items(function_type, n1, n2, rank=0, world=1):

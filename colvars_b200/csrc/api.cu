@@ -52,6 +52,7 @@ struct Group {
   double *d_com_scratch = nullptr;       // per-CTA partials of com_cog_kernel
   unsigned int *d_com_ticket = nullptr;  // its last-block-done counter
   std::vector<int> h_index;
+  int max_index = -1;
   std::vector<double> h_mass;
   FitState fit;
   double *com() const { return d_centers; }
@@ -115,7 +116,8 @@ struct b200cv_cvc {
   unsigned long long *h_counters = nullptr; // mapped pinned [4]: rare, listed, gate mode, -
   unsigned long long *h_counters_dev = nullptr;
   unsigned char *d_counters = nullptr;      // rare_count (u32 @0), pl_count (u64 @8),
-                                            // persistent list length (u64 @16), gate (i32 @24)
+                                            // persistent list length (u64 @16), gate (i32 @24),
+                                            // fused-finalize ticket (u32 @28)
   // captured pair-list evaluations: 1 = the next launch rebuilds the list, 0 = it walks it
   int *h_mode = nullptr;                    // mapped pinned, written by the host between launches
   int *h_mode_dev = nullptr;
@@ -179,6 +181,7 @@ struct b200cv_cvc {
     return reinterpret_cast<unsigned long long *>(d_counters + 8);
   }
   int *gate() const { return reinterpret_cast<int *>(d_counters + 24); }
+  unsigned int *fin_ticket() const { return reinterpret_cast<unsigned int *>(d_counters + 28); }
   bool self() const { return cfg.kind == B200CV_SELFCOORDNUM; }
   bool dinv() const { return cfg.kind == B200CV_DISTANCEINV; }
   bool center1() const { return cfg.group1_center_only != 0; }
@@ -534,6 +537,22 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     CUDA_OK(h, launch_fetch_gate(h->h_mode_dev, h->gate(), stream));
     h->launches++;
   }
+  // the final sum: a launch of its own, or the last CTA of the exact kernel (`finalized`)
+  bool finalized = false;
+  auto finalize_args = [&](int nparts) {
+    FinalizeArgs F{};
+    F.partials = h->d_partials;
+    F.n = nparts;
+    F.d_value = h->d_value;
+    F.h_value = (h->world > 1 || h->dinv()) ? nullptr : h->h_value_dev;
+    F.rare_count = h->rare_count();
+    F.pl_count = h->pl_count();
+    F.h_counters = h->h_counters_dev;
+    F.gate = gated ? h->gate() : nullptr;
+    F.pl_persist = h->pl_count() + 1;
+    F.pl_cap = h->pl_cap;
+    return F;
+  };
 
   if (h->center1() || h->center2()) {
     // COM variants (src/colvarcomp_coordnums.cpp:190-247): O(N) work, reference-order pairs
@@ -614,6 +633,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
 
     // non-rebuild step: only listed pairs (src/colvarcomp_coordnums.cpp:219-228)
     auto enqueue_walk = [&](double *partials, const int *gate) -> int {
+      bool const fuse = (gate == nullptr);
       ExactArgs E{};
       E.x1 = x1; E.y1 = y1; E.z1 = z1; E.x2 = x2; E.y2 = y2; E.z2 = z2;
       E.g1x = g1x; E.g1y = g1y; E.g1z = g1z; E.g2x = g2x; E.g2y = g2y; E.g2z = g2z;
@@ -625,6 +645,11 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.fast_exp = (h->exp_special == 3 && h->P.bc_type == 0) ? 3 : 0;
       E.gate = gate;
       E.gate_on = 0;
+      if (fuse) {
+        E.fin_ticket = h->fin_ticket();
+        E.fin = finalize_args(EXACT_BLOCKS);
+        finalized = true;
+      }
       E.P = h->P;
       CUDA_OK(h, launch_exact(E, stream));
       h->launches++;
@@ -690,10 +715,15 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.flags = sweep_flags;
       E.gate = gate;
       E.gate_on = 1;
+      nparts = h->nitems + EXACT_BLOCKS;
+      if (gate == nullptr) {
+        E.fin_ticket = h->fin_ticket();
+        E.fin = finalize_args(nparts);
+        finalized = true;
+      }
       E.P = h->P;
       CUDA_OK(h, launch_exact(E, stream));
       h->launches++;
-      nparts = h->nitems + EXACT_BLOCKS;
       return B200CV_OK;
     };
 
@@ -716,19 +746,11 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     }
   }
 
-  FinalizeArgs F{};
-  F.partials = h->d_partials;
-  F.n = npart;
-  F.d_value = h->d_value;
-  F.h_value = h->world > 1 ? nullptr : h->h_value_dev;
-  F.rare_count = h->rare_count();
-  F.pl_count = h->pl_count();
-  F.h_counters = h->h_counters_dev;
-  F.gate = gated ? h->gate() : nullptr;
-  F.pl_persist = h->pl_count() + 1;
-  F.pl_cap = h->pl_cap;
-  CUDA_OK(h, launch_finalize(F, stream));
-  h->launches++;
+  if (!finalized) {
+    FinalizeArgs const F = finalize_args(npart);
+    CUDA_OK(h, launch_finalize(F, stream));
+    h->launches++;
+  }
 
   if (h->world > 1) {
     if (h->comm) {
@@ -1015,6 +1037,21 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
     G.h_mass[i] = mass ? mass[i] : 1.0;
     total += G.h_mass[i];
     if (proxy_index[i] < 0) return fail(h, B200CV_INPUT_ERROR, "negative proxy index");
+    G.max_index = std::max(G.max_index, proxy_index[i]);
+  }
+  {
+    // an atom can be in a group only once (atom_group::add_atom_id; the host scatter and the
+    // device gather rely on it)
+    std::unordered_set<int> own;
+    own.reserve((size_t)n * 2);
+    for (int i = 0; i < n; i++) {
+      if (!own.insert(proxy_index[i]).second) {
+        G.h_index.clear();
+        return fail(h, B200CV_INPUT_ERROR,
+                    "Error: the same atom appears twice in a group (proxy index " +
+                        std::to_string(proxy_index[i]) + ")");
+      }
+    }
   }
   // atom_group::overlap (src/colvaratoms.cpp:1096-1105), O(N) here
   Group &O = h->g[2 - which];
@@ -1167,9 +1204,18 @@ int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stri
   int rc = reset_gradients(h, s);
   if (rc) return rc;
   int const ng = h->self() ? 1 : 2;
+  bool const one_launch = ng == 2 && !h->g[0].fit.active && !h->g[1].fit.active;
+  if (one_launch) {
+    GroupView const a{h->g[0].d_index, h->g[0].n, h->g[0].d_pos, h->g[0].stride, nullptr};
+    GroupView const b{h->g[1].d_index, h->g[1].n, h->g[1].d_pos, h->g[1].stride, nullptr};
+    CUDA_OK(h, launch_gather2(d_proxy_pos, proxy_stride, 0, a, b, s));
+  }
   for (int k = 0; k < ng; k++) {
     Group &G = h->g[k];
-    CUDA_OK(h, launch_gather(d_proxy_pos, proxy_stride, 0, G.d_index, G.n, G.d_pos, G.stride, s));
+    if (!one_launch) {
+      CUDA_OK(h, launch_gather(d_proxy_pos, proxy_stride, 0, G.d_index, G.n, G.d_pos, G.stride,
+                               s));
+    }
     std::string err;
     rc = fit_read_and_apply(G.fit, d_proxy_pos, proxy_stride, 0, G.d_pos, G.stride, G.n, s, err);
     if (rc) return fail(h, rc, err);
@@ -1314,11 +1360,20 @@ int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   int const ng = h->self() ? 1 : 2;
+  bool const one_launch = ng == 2;
+  if (one_launch) {
+    Group &A = h->g[0], &B = h->g[1];
+    GroupView const a{A.d_index, A.n, A.d_grad, A.stride, A.fit.rotate ? A.fit.d_q : nullptr};
+    GroupView const b{B.d_index, B.n, B.d_grad, B.stride, B.fit.rotate ? B.fit.d_q : nullptr};
+    CUDA_OK(h, launch_scatter_force2(a, b, force, d_proxy_force, proxy_stride, 0, s));
+  }
   for (int k = 0; k < ng; k++) {
     Group &G = h->g[k];
-    CUDA_OK(h, launch_scatter_force(G.d_grad, G.stride, G.d_index, G.n, force,
-                                    G.fit.rotate ? G.fit.d_q : nullptr, d_proxy_force,
-                                    proxy_stride, 0, s));
+    if (!one_launch) {
+      CUDA_OK(h, launch_scatter_force(G.d_grad, G.stride, G.d_index, G.n, force,
+                                      G.fit.rotate ? G.fit.d_q : nullptr, d_proxy_force,
+                                      proxy_stride, 0, s));
+    }
     std::string err;
     int rc = fit_scatter_force(G.fit, force, d_proxy_force, proxy_stride, 0, s, err);
     if (rc) return fail(h, rc, err);
@@ -1585,10 +1640,18 @@ int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, 
       int rc = fit_host_inverse_matrix(G.fit, Rinv, err);
       if (rc) return fail(h, rc, err);
     }
-    for (int i = 0; i < G.n; i++) {
-      size_t const p = (size_t)G.h_index[i];
-      if (p >= n_proxy) return fail(h, B200CV_BUG_ERROR, "proxy index out of range");
-      double gx = g[i], gy = g[G.stride + i], gz = g[2 * G.stride + i];
+    if (G.max_index >= 0 && (size_t)G.max_index >= n_proxy) {
+      return fail(h, B200CV_BUG_ERROR, "proxy index out of range");
+    }
+    const int *idx = G.h_index.data();
+    size_t const stride = G.stride;
+    int const n = G.n;
+    // distinct atoms of one group: the rows are independent, large groups are split over the
+    // host threads (the reference's loop is sequential, src/colvaratoms.cpp:1637-1704)
+#pragma omp parallel for schedule(static) if (n > 16384)
+    for (int i = 0; i < n; i++) {
+      size_t const p = (size_t)idx[i];
+      double gx = g[i], gy = g[stride + i], gz = g[2 * stride + i];
       if (rot) {
         double const tx = Rinv[0][0] * gx + Rinv[0][1] * gy + Rinv[0][2] * gz;
         double const ty = Rinv[1][0] * gx + Rinv[1][1] * gy + Rinv[1][2] * gz;
@@ -1759,6 +1822,8 @@ int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs)
   if (exact_pairs) *exact_pairs = h->exact_pairs;
   return B200CV_OK;
 }
+
+unsigned long long b200cv_kernel_launches(void) { return launches_so_far(); }
 
 // ---- multi-GPU -----------------------------------------------------------------------------------
 

@@ -372,6 +372,7 @@ int fit_read_and_apply(FitState &F, const double *proxy_pos, size_t pstride, int
   }
   if (F.center) {
     cog_kernel<<<1, 1024, 0, s>>>(fitp, fs, F.nfit, F.d_small + SM_COG);
+  note_launch();
     FIT_OK(cudaGetLastError());
     FIT_OK(launch_translate(d_pos, stride, n, F.d_small + SM_COG, -1.0, s));
     if (F.separate) FIT_OK(launch_translate(fitp, fs, F.nfit, F.d_small + SM_COG, -1.0, s));
@@ -382,8 +383,10 @@ int fit_read_and_apply(FitState &F, const double *proxy_pos, size_t pstride, int
   }
   if (F.rotate) {
     corr_kernel<<<1, 1024, 0, s>>>(fitp, fs, F.d_ref, F.fstride, F.nfit, F.d_small + SM_C);
+  note_launch();
     FIT_OK(cudaGetLastError());
     eigen_kernel<<<1, 32, 0, s>>>(F.d_small);
+  note_launch();
     FIT_OK(cudaGetLastError());
     FIT_OK(launch_rotate(d_pos, stride, n, F.d_q, s));
     if (F.separate) FIT_OK(launch_rotate(fitp, fs, F.nfit, F.d_q, s));
@@ -401,10 +404,12 @@ int fit_calc_gradients(FitState &F, const double *d_grad, size_t stride, int n, 
   if (!F.active || !F.fit_gradients) return B200CV_OK;
   fitgrad_reduce_kernel<<<1, 1024, 0, s>>>(d_grad, stride, F.d_main_unrot, F.mstride, n, F.d_small,
                                            F.center ? 1 : 0, F.rotate ? 1 : 0, F.nfit);
+  note_launch();
   FIT_OK(cudaGetLastError());
   fitgrad_apply_kernel<<<(F.nfit + 255) / 256, 256, 0, s>>>(F.d_ref, F.fstride, F.nfit, F.d_small,
                                                             F.center ? 1 : 0, F.rotate ? 1 : 0,
                                                             F.d_fit_grad, F.fstride);
+  note_launch();
   FIT_OK(cudaGetLastError());
   return B200CV_OK;
 }

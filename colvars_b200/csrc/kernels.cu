@@ -4,8 +4,13 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 
 namespace b200cv {
+
+static std::atomic<unsigned long long> g_launches{0ull};
+void note_launch() { g_launches.fetch_add(1ull, std::memory_order_relaxed); }
+unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 // ============================ block reduction helper =======================================
 
@@ -22,6 +27,42 @@ template <int THREADS> __device__ __forceinline__ double block_sum(double v, dou
   }
   __syncthreads();
   return s;  // valid on thread 0
+}
+
+// ---- the final sum (finalize_kernel, or the last CTA of exact_kernel) -------------------------
+// fixed summation order: thread t takes partials t, t+T, ...; then a binary tree.  volatile
+// loads: when the last CTA of a kernel runs this, the partials were written by other CTAs of
+// the same launch (made visible by their fence + ticket).
+template <int T>
+__device__ __forceinline__ void finalize_body(FinalizeArgs const &A, double *red)
+{
+  double s = 0.0;
+  for (int k = threadIdx.x; k < A.n; k += T) s += ((const volatile double *)A.partials)[k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = T / 2; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *A.d_value = red[0];
+    if (A.h_counters) {
+      A.h_counters[0] =
+          A.rare_count ? (unsigned long long)*(const volatile unsigned int *)A.rare_count : 0ull;
+      A.h_counters[1] = A.pl_count ? *(const volatile unsigned long long *)A.pl_count : 0ull;
+    }
+    if (A.gate) {
+      int const mode = *A.gate;
+      if (A.h_counters) A.h_counters[2] = (unsigned long long)mode;
+      if (mode == 1 && A.pl_persist) {
+        unsigned long long const n = *A.pl_count;
+        *A.pl_persist = n < A.pl_cap ? n : A.pl_cap;
+      }
+    }
+    // mapped pinned copies: the host reads them after synchronising with the stream, and
+    // kernel completion makes every write visible -- no fence needed
+    if (A.h_value) *A.h_value = red[0];
+  }
 }
 
 // ============================ exact pair queue / pair-list walk ================================
@@ -78,11 +119,27 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
   }
   double const s = block_sum<EXACT_THREADS>(fsum, red);
   if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+  if (A.fin_ticket != nullptr) {
+    // fused finalize: the CTA that arrives last adds up all partial sums (one launch less)
+    __shared__ bool last;
+    __shared__ double fin_red[EXACT_THREADS];
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last = (atomicAdd(A.fin_ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      finalize_body<EXACT_THREADS>(A.fin, fin_red);
+      if (threadIdx.x == 0) *A.fin_ticket = 0u;
+    }
+  }
 }
 
 int launch_exact(const ExactArgs &args, cudaStream_t stream)
 {
   exact_kernel<<<EXACT_BLOCKS, EXACT_THREADS, 0, stream>>>(args);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -129,6 +186,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) dense_kernel(const __grid_const
 int launch_dense(const DenseArgs &args, cudaStream_t stream)
 {
   dense_kernel<<<EXACT_BLOCKS, EXACT_THREADS, 0, stream>>>(args);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -203,6 +261,7 @@ int launch_center(const CenterArgs &args, cudaStream_t stream)
   int blocks = args.n == 0 ? 1 : (args.n + EXACT_THREADS - 1) / EXACT_THREADS;
   if (blocks > EXACT_BLOCKS) blocks = EXACT_BLOCKS;
   center_kernel<<<blocks, EXACT_THREADS, 0, stream>>>(args);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -211,38 +270,13 @@ int launch_center(const CenterArgs &args, cudaStream_t stream)
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs A)
 {
   __shared__ double red[256];
-  // fixed summation order: thread t takes partials t, t+256, ...; then a binary tree
-  double s = 0.0;
-  for (int k = threadIdx.x; k < A.n; k += 256) s += A.partials[k];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if (threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    *A.d_value = red[0];
-    if (A.h_counters) {
-      A.h_counters[0] = A.rare_count ? (unsigned long long)*A.rare_count : 0ull;
-      A.h_counters[1] = A.pl_count ? *A.pl_count : 0ull;
-    }
-    if (A.gate) {
-      int const mode = *A.gate;
-      if (A.h_counters) A.h_counters[2] = (unsigned long long)mode;
-      if (mode == 1 && A.pl_persist) {
-        unsigned long long const n = *A.pl_count;
-        *A.pl_persist = n < A.pl_cap ? n : A.pl_cap;
-      }
-    }
-    // mapped pinned copies: the host reads them after synchronising with the stream, and
-    // kernel completion makes every write visible -- no fence needed
-    if (A.h_value) *A.h_value = red[0];
-  }
+  finalize_body<256>(A, red);
 }
 
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream)
 {
   finalize_kernel<<<1, 256, 0, stream>>>(args);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -251,6 +285,7 @@ __global__ void fetch_gate_kernel(const int *h_mode_dev, int *d_gate) { *d_gate 
 int launch_fetch_gate(const int *h_mode_dev, int *d_gate, cudaStream_t stream)
 {
   fetch_gate_kernel<<<1, 1, 0, stream>>>(h_mode_dev, d_gate);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -280,10 +315,12 @@ int launch_distinv_post(const DistInvPostArgs &args, cudaStream_t stream)
   if (args.grad && args.count > 0) {
     int blocks = (int)std::min<size_t>((args.count + 255) / 256, 296 * 4);
     distinv_scale_kernel<<<blocks, 256, 0, stream>>>(args);
+  note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   distinv_value_kernel<<<1, 1, 0, stream>>>(args);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -312,6 +349,36 @@ int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, 
 {
   if (n <= 0) return 0;
   gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(proxy, pstride, aos, idx, n, pos, stride);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
+__global__ void gather2_kernel(const double *__restrict__ proxy, size_t pstride, int aos,
+                               GroupView a, GroupView b, int blocks_a)
+{
+  bool const first = (int)blockIdx.x < blocks_a;
+  GroupView const &g = first ? a : b;
+  int const i = ((int)blockIdx.x - (first ? 0 : blocks_a)) * (int)blockDim.x + (int)threadIdx.x;
+  if (i >= g.n) return;
+  size_t const p = (size_t)g.idx[i];
+  if (aos) {
+    g.data[i] = proxy[3 * p];
+    g.data[g.stride + i] = proxy[3 * p + 1];
+    g.data[2 * g.stride + i] = proxy[3 * p + 2];
+  } else {
+    g.data[i] = proxy[p];
+    g.data[g.stride + i] = proxy[pstride + p];
+    g.data[2 * g.stride + i] = proxy[2 * pstride + p];
+  }
+}
+
+int launch_gather2(const double *proxy, size_t pstride, int aos, const GroupView &a,
+                   const GroupView &b, cudaStream_t stream)
+{
+  int const ba = (a.n + 255) / 256, bb = (b.n + 255) / 256;
+  if (ba + bb <= 0) return 0;
+  gather2_kernel<<<ba + bb, 256, 0, stream>>>(proxy, pstride, aos, a, b, ba);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -421,6 +488,7 @@ int launch_com_cog(const double *pos, size_t stride, const double *mass, double 
   blocks = blocks < 1 ? 1 : (blocks > COM_BLOCKS ? COM_BLOCKS : blocks);
   com_cog_kernel<<<blocks, COM_THREADS, 0, stream>>>(pos, stride, mass, total_mass, n, com, cog,
                                                      scratch, ticket);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -438,6 +506,7 @@ int launch_translate(double *pos, size_t stride, int n, const double *t_dev, dou
 {
   if (n <= 0) return 0;
   translate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pos, stride, n, t_dev, s);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -472,6 +541,7 @@ int launch_rotate(double *pos, size_t stride, int n, const double *q_dev, cudaSt
 {
   if (n <= 0) return 0;
   rotate_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pos, stride, n, q_dev);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -490,6 +560,7 @@ int launch_weighted_gradient(const double *w, const double *g_dev, int n, double
 {
   if (n <= 0) return 0;
   weighted_gradient_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, g_dev, n, grad, stride);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -533,6 +604,47 @@ int launch_scatter_force(const double *grad, size_t stride, const int *idx, int 
   if (n <= 0) return 0;
   scatter_force_kernel<<<(n + 255) / 256, 256, 0, stream>>>(grad, stride, idx, n, f, q_dev,
                                                             proxy_force, pstride, aos);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
+__global__ void scatter_force2_kernel(GroupView a, GroupView b, int blocks_a, double f,
+                                      double *proxy_force, size_t pstride, int aos)
+{
+  bool const first = (int)blockIdx.x < blocks_a;
+  GroupView const &g = first ? a : b;
+  int const i = ((int)blockIdx.x - (first ? 0 : blocks_a)) * (int)blockDim.x + (int)threadIdx.x;
+  if (i >= g.n) return;
+  double gx = g.data[i], gy = g.data[g.stride + i], gz = g.data[2 * g.stride + i];
+  if (g.q) {
+    double R[3][3];
+    quat_to_matrix(g.q, R);
+    double const tx = R[0][0] * gx + R[1][0] * gy + R[2][0] * gz;
+    double const ty = R[0][1] * gx + R[1][1] * gy + R[2][1] * gz;
+    double const tz = R[0][2] * gx + R[1][2] * gy + R[2][2] * gz;
+    gx = tx;
+    gy = ty;
+    gz = tz;
+  }
+  size_t const p = (size_t)g.idx[i];
+  if (aos) {
+    atomicAdd(&proxy_force[3 * p], f * gx);
+    atomicAdd(&proxy_force[3 * p + 1], f * gy);
+    atomicAdd(&proxy_force[3 * p + 2], f * gz);
+  } else {
+    atomicAdd(&proxy_force[p], f * gx);
+    atomicAdd(&proxy_force[pstride + p], f * gy);
+    atomicAdd(&proxy_force[2 * pstride + p], f * gz);
+  }
+}
+
+int launch_scatter_force2(const GroupView &a, const GroupView &b, double f, double *proxy_force,
+                          size_t pstride, int aos, cudaStream_t stream)
+{
+  int const ba = (a.n + 255) / 256, bb = (b.n + 255) / 256;
+  if (ba + bb <= 0) return 0;
+  scatter_force2_kernel<<<ba + bb, 256, 0, stream>>>(a, b, ba, f, proxy_force, pstride, aos);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -556,6 +668,7 @@ int launch_repack(const double *src, size_t sstride, double *dst, size_t dstride
 {
   if (n <= 0) return 0;
   repack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, sstride, dst, dstride, n, accumulate);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -584,6 +697,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
 int launch_fp64_peak(double *d_out, int iters, int blocks, cudaStream_t stream)
 {
   fp64_peak_kernel<<<blocks, 256, 0, stream>>>(d_out, iters);
+  note_launch();
   return (int)cudaGetLastError();
 }
 
@@ -610,6 +724,7 @@ __global__ void rcp_selftest_kernel(const double *x, int n, double *maxulp)
 int launch_rcp_selftest(const double *d_x, int n, double *d_maxulp, cudaStream_t stream)
 {
   rcp_selftest_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_x, n, d_maxulp);
+  note_launch();
   return (int)cudaGetLastError();
 }
 

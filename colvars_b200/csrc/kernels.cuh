@@ -4,6 +4,11 @@
 
 namespace b200cv {
 
+// every kernel this library launches is counted (bench.py reports the number it launched
+// inside its timed region): one relaxed atomic increment on the host per launch
+void note_launch();
+unsigned long long launches_so_far();
+
 // sweep geometry (compile-time): R register atoms per lane, W warps per CTA
 #ifndef B200CV_SWEEP_R
 #define B200CV_SWEEP_R 8
@@ -26,6 +31,21 @@ int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso,
                  bool pairlist, cudaStream_t stream);
 bool sweep_has_special(int en, int ed);
 
+// value = sum(partials[0..n)) in a fixed order -> device scalar + mapped pinned host copy;
+// also publishes the queue counters to the host.
+struct FinalizeArgs {
+  const double *partials;
+  int n;
+  double *d_value;
+  double *h_value;  // mapped pinned
+  const unsigned int *rare_count;
+  const unsigned long long *pl_count;
+  unsigned long long *h_counters;  // mapped pinned [4]: rare_count, pl_count, gate mode, unused
+  // gated evaluations: after a rebuild (*gate == 1) the list length is kept on the device
+  const int *gate;
+  unsigned long long *pl_persist;
+  unsigned long long pl_cap;
+};
 // Pairs queued by the sweep (or every listed pair on non-rebuild steps, or every pair for
 // the general-PBC fallback) evaluated in the reference's operation order.
 struct ExactArgs {
@@ -45,6 +65,10 @@ struct ExactArgs {
   int fast_exp;                        // 3: pair-list walk may use the sweep's fast 6/12 form
   const int *gate;                     // see SweepArgs::gate
   int gate_on;
+  // fused finalize (fin_ticket != NULL, never together with a gate): the last CTA to finish
+  // sums fin.partials and publishes the value; the ticket re-arms itself
+  unsigned int *fin_ticket;
+  FinalizeArgs fin;
   PairParams P;
 };
 constexpr int EXACT_BLOCKS = 296;
@@ -90,21 +114,6 @@ struct CenterArgs {
 };
 int launch_center(const CenterArgs &args, cudaStream_t stream);
 
-// value = sum(partials[0..n)) in a fixed order -> device scalar + mapped pinned host copy;
-// also publishes the queue counters to the host.
-struct FinalizeArgs {
-  const double *partials;
-  int n;
-  double *d_value;
-  double *h_value;  // mapped pinned
-  const unsigned int *rare_count;
-  const unsigned long long *pl_count;
-  unsigned long long *h_counters;  // mapped pinned [4]: rare_count, pl_count, gate mode, unused
-  // gated evaluations: after a rebuild (*gate == 1) the list length is kept on the device
-  const int *gate;
-  unsigned long long *pl_persist;
-  unsigned long long pl_cap;
-};
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
 
 // copies the host-written mode word (mapped pinned) into device memory once per evaluation
@@ -127,6 +136,19 @@ int launch_distinv_post(const DistInvPostArgs &args, cudaStream_t stream);
 // gather: pos[d*stride + i] = proxy[d*pstride + idx[i]]  (aos != 0: proxy[3*idx[i] + d])
 int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, int n,
                   double *pos, size_t stride, cudaStream_t stream);
+// both groups of a component in one launch (steps of a few hundred microseconds are bound by
+// the number of launches, not by these kernels' work)
+struct GroupView {
+  const int *idx;
+  int n;
+  double *data;     // positions (gather) or gradients (scatter), SoA planes
+  size_t stride;
+  const double *q;  // scatter: device quaternion of a rotated group, or NULL
+};
+int launch_gather2(const double *proxy, size_t pstride, int aos, const GroupView &a,
+                   const GroupView &b, cudaStream_t stream);
+int launch_scatter_force2(const GroupView &a, const GroupView &b, double f, double *proxy_force,
+                          size_t pstride, int aos, cudaStream_t stream);
 // COM = sum m x / M and COG = sum x / n in one pass (<= 296 CTAs, fixed summation order).
 // scratch: device double[296 * 6]; ticket: device counter, zero before the first launch.
 constexpr int COM_SCRATCH_DOUBLES = 296 * 6;

@@ -26,6 +26,7 @@ static int launch_sweep_t(const SweepArgs &args, int nitems, cudaStream_t stream
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   kern<<<nitems, SWEEP_W * 32, sweep_smem_bytes(), stream>>>(args);
+  note_launch();
   return (int)cudaGetLastError();
 }
 

@@ -214,6 +214,9 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *h_indices, size_t capacity);
 /* Counters of the last calc_value: kernels launched, pairs sent to the exact
  * (reference-order) path. */
 int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs);
+/* Kernels this library has launched in this process so far (all handles, every stream).
+ * bench.py reports the difference over its timed region as "gpu_launches". */
+unsigned long long b200cv_kernel_launches(void);
 
 /* ---- multi-GPU (one process per GPU; group1 rows sharded, group2 replicated) ---------- */
 /* NCCL unique id (128 bytes) created on rank 0 and handed to every rank by the caller. */

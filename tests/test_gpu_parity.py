@@ -650,3 +650,10 @@ def test_pairlist_inside_one_captured_graph(kind, center):
         close_arr(g1.cpu().numpy().T, og1, 1e-11 if center else RTOL)
         if not center:
             assert np.array_equal(np.sort(cv.pairlist()), np.sort(ref.pairlist()))
+
+
+def test_duplicate_atoms_in_a_group_are_rejected():
+    cb = _cb()
+    with pytest.raises(cb.B200cvError, match="twice in a group"):
+        cb.CoordNum("coordNum", np.array([0, 1, 1], dtype=np.int32),
+                    np.array([5, 6], dtype=np.int32))

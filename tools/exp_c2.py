@@ -37,3 +37,22 @@ for n1, n2 in ((1000, 100000), (1024, 100000), (1000, 94720), (2000, 100000), (4
     print(f"{n1:6d} x {n2:7d}: items {len(items):5d} chunk {chunk:5d}  value+grad {tg:8.1f} us "
           f"({pairs / tg / 1e6:7.1f} Gpair/s)   value only {tv:8.1f} us", flush=True)
     cv.close()
+
+# host-buffer (e2e) path of the 1k x 100k case: where the wall time goes
+import time
+proxy, i1, i2, L = synth.coordnum_case(1000, 100000, seed=1234)
+cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
+h_pos = torch.tensor(proxy).pin_memory()
+h_force = torch.zeros_like(h_pos).pin_memory()
+tc, ta = [], []
+for r in range(30):
+    t0 = time.perf_counter()
+    v = cv.calc_host(h_pos, step=r)
+    t1 = time.perf_counter()
+    cv.apply_force_host(-0.004 * (v - 0.1), h_force)
+    t2 = time.perf_counter()
+    if r >= 5:
+        tc.append(t1 - t0)
+        ta.append(t2 - t1)
+print(f"e2e 1k x 100k: calc_host {np.median(tc) * 1e6:.1f} us, apply_force_host "
+      f"{np.median(ta) * 1e6:.1f} us", flush=True)
