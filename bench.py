@@ -509,10 +509,10 @@ def main():
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved_tflops / peak,
                      # DRAM bytes per sweep launch from the committed ncu capture
-                     # (profiles/r01_c5_sweep_v2_ncu_raw.csv: 54.46 MB read + 0.78 MB written;
+                     # (profiles/r01_c5_sweep_v3_ncu_raw.csv: 54.44 MB read + 0.51 MB written;
                      # algorithmic input 26.4 MB -- the kernel is FP64-bound, not HBM-bound)
-                     "traffic": 55246080 if (args.workload == "c5" and world == 1) else None,
-                     "kernel": "sweep_kernel (+ exact/finalize) = calc_value",
+                     "traffic": 54941952 if (args.workload == "c5" and world == 1) else None,
+                     "kernel": "sweep_kernel (+ exact queue with the final sum) = calc_value",
                      "kernel_ms": kern_ms_avg,
                      "flop_per_pair": synth.FLOP_PER_PAIR_VALUE_GRAD,
                      "peak_source": "DFMA microbenchmark run live in this process "
