@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -397,6 +398,11 @@ void plan_items(bool self, int n1, int n2_in, int rank, int world, std::vector<S
       best = t;
       chunk = cand;
     }
+  }
+  if (const char *forced = std::getenv("B200CV_CHUNK")) {
+    // tuning experiments only: group2 atoms per work item (multiple of 32, <= JCMAX)
+    long long const c = std::atoll(forced);
+    if (c >= 32 && c <= JCMAX && c % 32 == 0) chunk = c;
   }
   chunk_out = (int)chunk;
   int const nch = (n2 + (int)chunk - 1) / (int)chunk;
@@ -1824,6 +1830,11 @@ int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs)
 }
 
 unsigned long long b200cv_kernel_launches(void) { return launches_so_far(); }
+
+#if defined(B200CV_TRACE)
+// debug builds only: {start, tiles begin, tiles end, end (ns), smid} per CTA of the last sweep
+int b200cv_trace_dump(unsigned long long *out, int n) { return b200cv::trace_dump(out, n); }
+#endif
 
 // ---- multi-GPU -----------------------------------------------------------------------------------
 

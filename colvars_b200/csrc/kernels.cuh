@@ -8,6 +8,9 @@ namespace b200cv {
 // inside its timed region): one relaxed atomic increment on the host per launch
 void note_launch();
 unsigned long long launches_so_far();
+#if defined(B200CV_TRACE)
+int trace_dump(unsigned long long *out, int n);  // sweep_inst.cu, debug builds only
+#endif
 
 // sweep geometry (compile-time): R register atoms per lane, W warps per CTA
 #ifndef B200CV_SWEEP_R

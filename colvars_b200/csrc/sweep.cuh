@@ -374,6 +374,17 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
   }
 }
 
+#if defined(B200CV_TRACE)
+// debug builds only (make EXTRA=-DB200CV_TRACE): per-CTA timeline, read back by b200cv_trace_dump
+__device__ unsigned long long g_trace[6 * 65536];
+__device__ __forceinline__ unsigned long long trace_now()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 // ---- the kernel -----------------------------------------------------------------------------
 template <int EXP, bool ANISO, int PBC, bool PL, int R, int W, int MINB>
 __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_constant__ SweepArgs A)
@@ -394,7 +405,11 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
       return;
     }
   }
-  SweepItem const item = A.items[blockIdx.x];
+#if defined(B200CV_TRACE)
+  unsigned long long const trace_t0 = trace_now();
+#endif
+  int const item_index = blockIdx.x;
+  SweepItem const item = A.items[item_index];
   int const lane = threadIdx.x & 31;
   int const warp = threadIdx.x >> 5;
   int const jn_pad = (item.jn + 31) & ~31;
@@ -439,6 +454,9 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
 
   __syncthreads();  // accumulators zeroed
   mbar_wait(&mbar, 0);
+#if defined(B200CV_TRACE)
+  unsigned long long const trace_t1 = trace_now();
+#endif
 
   // rows of this warp: [iw0, iw1).  Masking (select path) is decided per warp and tile: rows
   // beyond the group, a partial last tile, or -- selfCoordNum -- a tile that reaches into the
@@ -464,6 +482,9 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
     }
   }
 
+#if defined(B200CV_TRACE)
+  unsigned long long const trace_t2 = trace_now();
+#endif
   // value: warp tree, then one partial per CTA in a fixed order
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
@@ -473,7 +494,7 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < W; w++) s += red[w];
-    A.partials[blockIdx.x] = s;
+    A.partials[item_index] = s;
   }
 
   if (A.want_grad) {
@@ -494,6 +515,18 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
       atomicAdd(&A.g2z[item.j0 + t], cz * az[t]);
     }
   }
+#if defined(B200CV_TRACE)
+  if (threadIdx.x == 0 && blockIdx.x < 65536) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_trace[6 * blockIdx.x + 0] = trace_t0;
+    g_trace[6 * blockIdx.x + 1] = trace_t1;
+    g_trace[6 * blockIdx.x + 2] = trace_t2;
+    g_trace[6 * blockIdx.x + 3] = trace_now();
+    g_trace[6 * blockIdx.x + 4] = smid;
+    g_trace[6 * blockIdx.x + 5] = (unsigned long long)item_index;
+  }
+#endif
 }
 
 constexpr size_t sweep_smem_bytes() { return 6 * JCMAX * sizeof(double); }

@@ -62,4 +62,11 @@ int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso,
                : launch_sweep_ea<0, false>(args, nitems, pbc, pairlist, stream);
 }
 
+#if defined(B200CV_TRACE)
+int trace_dump(unsigned long long *out, int n)
+{
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 6 * (size_t)n);
+}
+#endif
+
 }  // namespace b200cv

@@ -56,3 +56,20 @@ for r in range(30):
         ta.append(t2 - t1)
 print(f"e2e 1k x 100k: calc_host {np.median(tc) * 1e6:.1f} us, apply_force_host "
       f"{np.median(ta) * 1e6:.1f} us", flush=True)
+
+# is the first wave slower because of a cold start?  five evaluations back to back (no L2
+# flush, no gap), an event between each
+proxy, i1, i2, L = synth.coordnum_case(1000, 100000, seed=1234)
+cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
+d_pos = torch.tensor(np.ascontiguousarray(proxy.T), device="cuda")
+s = torch.cuda.current_stream()
+cv.read_data(d_pos, s)
+for rep in range(3):
+    evs = [torch.cuda.Event(True) for _ in range(7)]
+    evs[0].record(s)
+    for k in range(6):
+        cv.calc_value(step=k, gradients=True, stream=s)
+        evs[k + 1].record(s)
+    torch.cuda.synchronize()
+    print("back-to-back calc_value us:", " ".join(f"{evs[k].elapsed_time(evs[k + 1]) * 1e3:.1f}"
+                                                    for k in range(6)), flush=True)
