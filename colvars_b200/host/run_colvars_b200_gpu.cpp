@@ -166,6 +166,7 @@ private:
 
 // defined by atomgroup_b200.cu when it is linked in front of the reference archive
 extern "C" int b200cv_atomgroup_kernels_linked(void) __attribute__((weak));
+extern "C" int b200cv_rotation_kernels_linked(void) __attribute__((weak));
 
 int main(int argc, char **argv)
 {
@@ -207,6 +208,8 @@ int main(int argc, char **argv)
   std::cout << "atom-group kernels: "
             << (b200cv_atomgroup_kernels_linked ? "b200 (atomgroup_b200.cu)" : "reference")
             << "\n";
+  std::cout << "optimal-rotation kernels: "
+            << (b200cv_rotation_kernels_linked ? "b200 (rotation_b200.cu)" : "reference") << "\n";
   double const max_gradient_error = cvmodule->get_max_gradient_error();
   if (max_gradient_error > 0.) {
     std::cout << "Max gradient error (debugGradients): " << max_gradient_error << "\n";

@@ -88,5 +88,6 @@ def test_reference_host_with_b200_components(case, route, tmp_path):
         # gather / COM / fit / scatter graphs run on this repository's kernels, not on the
         # archive member built from src/cuda/colvaratoms_kernel.cu
         assert "atom-group kernels: b200" in r.stdout
+        assert "optimal-rotation kernels: b200" in r.stdout
         on_graph = "graph route: yes" in r.stdout
         assert on_graph == ("dummy" not in case), r.stdout[-500:]

@@ -17,6 +17,7 @@
 #include "colvarmodule.h"
 #include "colvartypes.h"
 #include "cuda/colvaratoms_kernel.h"
+#include "cuda/colvartypes_kernel.h"
 
 extern "C" int b200cv_atomgroup_kernels_linked(void) __attribute__((weak));
 
@@ -160,6 +161,50 @@ int main(int argc, char **argv)
         return colvars_gpu::apply_force(d_grad, d_idx, d_force, n, P, nd, g, {});
       },
       [&]() { return checksum(d_force, 3 * (size_t)P) / (reps + 3); });
+  // optimal rotation: correlation matrix of (positions, gradients-as-reference) + 4x4 eigenproblem
+  {
+    double *d_S, *d_Sv, *d_L;
+    cvm::rmatrix *h_C;
+    cvm::quaternion *d_qq, *d_qold;
+    int *h_flags;
+    CK(cudaMalloc(&d_S, 16 * sizeof(double)));
+    CK(cudaMalloc(&d_Sv, 16 * sizeof(double)));
+    CK(cudaMalloc(&d_L, 4 * sizeof(double)));
+    CK(cudaMalloc(&d_qq, sizeof(cvm::quaternion)));
+    CK(cudaMalloc(&d_qold, sizeof(cvm::quaternion)));
+    CK(cudaMemset(d_qold, 0, sizeof(cvm::quaternion)));
+    CK(cudaHostAlloc(&h_C, sizeof(cvm::rmatrix), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&h_flags, 2 * sizeof(int), cudaHostAllocMapped));
+    h_flags[0] = h_flags[1] = 0;
+    auto lead = [&]() {
+      double v[4], l[4];
+      cudaMemcpy(v, d_Sv, sizeof(v), cudaMemcpyDeviceToHost);
+      cudaMemcpy(l, d_L, sizeof(l), cudaMemcpyDeviceToHost);
+      double const sg = v[0] < 0 ? -1.0 : 1.0;  // the sign of an eigenvector is arbitrary
+      return l[0] + sg * (v[0] + 2 * v[1] + 3 * v[2] + 5 * v[3]);
+    };
+    one("memset S + build_overlapping_matrix",
+        [&](cudaGraphNode_t &nd, cudaGraph_t &g) {
+          cudaGraphNode_t ms;
+          cudaMemsetParams mp = {0};
+          mp.dst = d_S; mp.value = 0; mp.elementSize = 4; mp.width = 32; mp.height = 1; mp.pitch = 128;
+          if (cudaGraphAddMemsetNode(&ms, g, nullptr, 0, &mp) != cudaSuccess) return 1;
+          return colvars_gpu::build_overlapping_matrix(d_pos, d_pos + n, d_pos + 2 * n, d_grad,
+                                                       d_grad + n, d_grad + 2 * n, d_S, d_Sv, h_C,
+                                                       d_tb, n, nd, g, {ms});
+        },
+        [&]() { return checksum(d_S, 16); });
+    one("jacobi_4x4",
+        [&](cudaGraphNode_t &nd, cudaGraph_t &g) {
+          // the eigen-solver overwrites its input: restore it from S first
+          cudaGraphNode_t cp;
+          if (cudaGraphAddMemcpyNode1D(&cp, g, nullptr, 0, d_Sv, d_S, 16 * sizeof(double),
+                                       cudaMemcpyDeviceToDevice) != cudaSuccess) return 1;
+          return colvars_gpu::jacobi_4x4(d_Sv, d_L, h_flags, d_qq, false, 1e-2, d_qold,
+                                         h_flags + 1, nd, g, {cp});
+        },
+        lead);
+  }
   // in-place transforms last: they change d_pos on every launch
   one("apply_translation",
       [&](cudaGraphNode_t &nd, cudaGraph_t &g) {
