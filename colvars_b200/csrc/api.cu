@@ -437,6 +437,31 @@ void plan_items(bool self, int n1, int n2_in, int rank, int world, std::vector<S
       if ((int)(k % (size_t)world) == rank) mine.push_back(all[k]);
     }
   }
+  // The kernel ends when its last CTA does: with several waves of equal items the SMs drain
+  // one by one over the duration of a whole item (0.4 ms for 32 tiles -- 2 % of a step at 8
+  // GPUs).  Cut the items of the last two waves into quarters so the drain is a quarter as long.
+  if ((long long)mine.size() > 2 * slots && !std::getenv("B200CV_CHUNK")) {
+    size_t const first_small = mine.size() - (size_t)(2 * slots);
+    std::vector<SweepItem> tail;
+    tail.reserve((size_t)(8 * slots));
+    for (size_t k = first_small; k < mine.size(); k++) {
+      SweepItem const it = mine[k];
+      int const tiles = (it.jn + 31) / 32;
+      int const per = std::max(4, (tiles + 3) / 4);  // tiles per piece
+      for (int t0 = 0; t0 < tiles; t0 += per) {
+        int const j0 = it.j0 + t0 * 32;
+        int const jn = std::min(per * 32, it.j0 + it.jn - j0);
+        int diag = 0;
+        if (self) {
+          if (j0 + jn <= it.i0 + 1) continue;     // no j > i in this piece
+          diag = (j0 < it.i0 + SWEEP_IB) ? 1 : 0;
+        }
+        tail.push_back(SweepItem{it.i0, j0, jn, diag});
+      }
+    }
+    mine.resize(first_small);
+    mine.insert(mine.end(), tail.begin(), tail.end());
+  }
 }
 
 int build_items(b200cv_cvc *h)
