@@ -29,6 +29,13 @@ import tempfile
 import time
 from pathlib import Path
 
+if os.environ.get("LOCAL_RANK") is not None and os.environ.get("OMP_NUM_THREADS") == "1":
+    # torchrun pins every rank to ONE OpenMP thread by default.  The host-buffer path (`e2e`)
+    # scatters forces with OpenMP: give each rank its share of the host cores instead.  Has to
+    # happen before any OpenMP runtime is loaded.
+    _world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or _world) // _world))
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
