@@ -657,3 +657,40 @@ def test_duplicate_atoms_in_a_group_are_rejected():
     with pytest.raises(cb.B200cvError, match="twice in a group"):
         cb.CoordNum("coordNum", np.array([0, 1, 1], dtype=np.int32),
                     np.array([5, 6], dtype=np.int32))
+
+
+def test_captured_pairlist_overflow_is_an_error_not_a_truncation():
+    """A captured graph holds the list's address, so the list cannot grow: when a rebuild finds
+    more pairs than were reserved, the step's value must come back as an error."""
+    import torch
+    cb = _cb()
+    rng = np.random.default_rng(9)
+    n = 6000
+    pos = rng.random((n, 3)) * 60.0
+    i1 = np.arange(n, dtype=np.int32)
+    cv = cb.CoordNum("selfCoordNum", i1, cutoff=4.0, tolerance=0.01, pairlist_freq=2)
+    p1 = torch.tensor(np.ascontiguousarray(pos.T), device="cuda")
+    g1 = torch.zeros_like(p1)
+    side = torch.cuda.Stream()
+    cv.pairlist_reserve(p1, None, headroom=1.0, stream=side)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        cv.eval_async(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST, stream=side)
+        cv.accumulate_gradients(g1, None, stream=side)
+    graph.replay()
+    torch.cuda.synchronize()
+    v0 = cv.value()  # fits: same positions as the reservation
+    assert v0 > 0
+    # the same atoms at a third of the box size: ~27x as many pairs within range.  The list was
+    # allocated with at least 2^20 entries, so check that the new count really exceeds it
+    p1.mul_(1.0 / 3.0)
+    cv.pairlist_set_rebuild(True)
+    graph.replay()
+    torch.cuda.synchronize()
+    dense = cb.CoordNum("selfCoordNum", i1, cutoff=4.0, tolerance=0.01, pairlist_freq=2)
+    dense.eval(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST | cb.EF_REBUILD_PAIRLIST,
+               torch.zeros_like(p1), None)
+    assert len(dense.pairlist()) > (1 << 20)
+    with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
+        cv.value()
