@@ -303,6 +303,13 @@ int coordnum_b200::add_calc_value_node(
       cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
     return cvmodule->error("Error: cannot create a CUDA stream.\n", COLVARS_ERROR);
   }
+  // the scheduler never calls cvc::read_data() on this route, so copy the cell the way it does
+  // (src/colvarcomp.cpp:457-465); it is frozen into the graph
+  if (is_enabled(f_cvc_pbc_minimum_image)) {
+    boundary_conditions = cvmodule->proxy->get_system_boundaries();
+  } else {
+    boundary_conditions.reset();
+  }
   static_cast<boundaries_view const &>(boundary_conditions).push(engine);
   auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
   const double *p2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_pos : nullptr;
