@@ -54,6 +54,11 @@ public:
     }
     return COLVARS_OK;
   }
+  void set_cell(double ax, double by, double cz)
+  {
+    boundaries_.set_boundaries(true, true, true, cvm::rvector(ax, 0, 0), cvm::rvector(0, by, 0),
+                               cvm::rvector(0, 0, cz));
+  }
   void request_total_force(bool yesno) override { total_force_requested = yesno; }
   bool total_forces_enabled() const override { return total_force_requested; }
   bool total_forces_same_step() const override { return total_force_requested; }
@@ -172,12 +177,16 @@ int main(int argc, char **argv)
 {
   std::string config, traj, prefix;
   bool forces = false;
+  double cell[3] = {0, 0, 0};
   for (int a = 1; a < argc; a++) {
     std::string const s = argv[a];
     if ((s == "-c" || s == "--configuration_file") && a + 1 < argc) config = argv[++a];
     else if ((s == "-t" || s == "--trajectory_file") && a + 1 < argc) traj = argv[++a];
     else if ((s == "-o" || s == "--output_prefix") && a + 1 < argc) prefix = argv[++a];
     else if (s == "--force") forces = true;
+    else if (s == "--cell" && a + 3 < argc) {
+      for (int d = 0; d < 3; d++) cell[d] = std::stod(argv[++a]);
+    }
   }
   if (config.empty() || traj.empty()) {
     std::cerr << "usage: run_colvars_b200_gpu -c test.in -t trajectory.xyz [-o prefix [--force]]\n";
@@ -191,6 +200,7 @@ int main(int argc, char **argv)
   err |= cvmodule->setup_output();
   coordnum_b200::install(cvmodule);
   err |= cvmodule->read_config_file(config.c_str());
+  if (cell[0] > 0) proxy->set_cell(cell[0], cell[1], cell[2]);
   std::ifstream ifs(traj);
   int natoms = 0;
   ifs >> natoms;

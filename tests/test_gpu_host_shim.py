@@ -91,3 +91,38 @@ def test_reference_host_with_b200_components(case, route, tmp_path):
         assert "optimal-rotation kernels: b200" in r.stdout
         on_graph = "graph route: yes" in r.stdout
         assert on_graph == ("dummy" not in case), r.stdout[-500:]
+
+
+@pytest.mark.parametrize("case", ["coordnum", "selfcoordnum-pairlist", "coordnum-aniso"])
+def test_periodic_cell_through_the_reference_host(case, tmp_path):
+    """The reference's functional tests are non-periodic.  Here the same inputs run in a small
+    orthorhombic cell (minimum images matter for most pairs) three times: the reference's own
+    components, the B200 components on CPU-proxy buffers, and on the `smp gpu` graph route
+    (cell taken from the proxy at capture time) -- all through the unmodified host."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    for f in ("trajectory.xyz", "index.ndx"):
+        shutil.copy(R.GOLDEN / f, tmp_path / f)
+    d = tmp_path / "case"
+    d.mkdir()
+    shutil.copy(R.GOLDEN / f"{case}_harmonic-fixed" / "test.in", d / "test.in")
+    cell = ["--cell", "3.1", "2.7", "2.9"]
+    runs = {"ref": [str(RUNNER), "--reference-components"], "cpu": [str(RUNNER)],
+            "gpu": [str(RUNNER_GPU)]}
+    out = {}
+    for tag, cmd in runs.items():
+        r = subprocess.run(cmd + cell + ["-c", "case/test.in", "-t", "trajectory.xyz", "-o",
+                                         f"case/{tag}", "--force"], cwd=tmp_path,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, tag + r.stdout[-2000:] + r.stderr[-2000:]
+        out[tag] = (np.loadtxt(d / f"{tag}.colvars.traj", comments="#"),
+                    [np.loadtxt(d / f"{tag}_forces_{k}.dat") for k in range(5)])
+    # the cell matters: not the non-periodic golden
+    gold = np.loadtxt(R.GOLDEN / f"{case}_harmonic-fixed" / "AutoDiff" / "test_out.colvars.traj",
+                      comments="#")
+    assert np.max(np.abs(out["ref"][0][:, 1] - gold[:, 1])) > 1e-3
+    for tag in ("cpu", "gpu"):
+        assert np.allclose(out[tag][0], out["ref"][0], rtol=1e-11, atol=1e-13), tag
+        for k in range(5):
+            assert np.allclose(out[tag][1][k], out["ref"][1][k], rtol=1e-9, atol=1e-13), (tag, k)
