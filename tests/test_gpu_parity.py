@@ -694,3 +694,46 @@ def test_captured_pairlist_overflow_is_an_error_not_a_truncation():
     assert len(dense.pairlist()) > (1 << 20)
     with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
         cv.value()
+
+
+def test_handles_are_independent_across_host_threads():
+    """`smp cvcs` runs calc_value() of different components on different OpenMP threads
+    (src/colvarproxy.cpp:299-315): the C ABI has to be re-entrant per handle.  Four threads,
+    each with its own handle (ctypes drops the GIL during the calls), against serial results."""
+    import threading
+    cb = _cb()
+    cases = []
+    for k, kind in enumerate(["coordNum", "selfCoordNum", "coordNum", "distanceInv"]):
+        n1, n2 = (300 + 50 * k, 0 if kind == "selfCoordNum" else 900 + 100 * k)
+        proxy, i1, i2 = rand_case(n1, n2, seed=70 + k, L=14.0)
+        kw = dict(tolerance=0.01, pairlist_freq=2) if k == 2 else {}
+        cv = cb.CoordNum(kind, i1, i2 if n2 else None, **kw)
+        serial = []
+        for step in range(6):
+            serial.append((cv.calc_host(proxy + 0.01 * step, step=step), cv.gradients(1).copy()))
+        cv.close()
+        cases.append((kind, i1, i2 if n2 else None, kw, proxy, serial))
+    errors = []
+
+    def work(case):
+        kind, i1, i2, kw, proxy, serial = case
+        try:
+            cv = cb.CoordNum(kind, i1, i2, **kw)
+            for rep in range(3):
+                for step in range(6):
+                    v = cv.calc_host(proxy + 0.01 * step, step=step)
+                    g = cv.gradients(1)
+                    sv, sg = serial[step]
+                    # atomics reorder the gradient sums between runs: 1e-13, not bitwise
+                    assert abs(v - sv) <= 1e-13 * abs(sv), (kind, step, v, sv)
+                    assert np.max(np.abs(g - sg)) <= 1e-13 * np.max(np.abs(sg)), (kind, step)
+            cv.close()
+        except Exception as e:  # noqa: BLE001 - reported in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(c,)) for c in cases]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
