@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/b200cv.h"
+#include "cells.cuh"
 #include "fit.cuh"
 #include "kernels.cuh"
 
@@ -134,6 +135,11 @@ struct b200cv_cvc {
   unsigned long long pl_n = 0;  // entries of the current list
   bool pl_valid = false;        // a rebuild has happened
   unsigned char *d_pl_center = nullptr;  // dense flags for the centre-only variants
+
+  // cell-list rebuild of the pair list (cells.cuh); used once a rebuild has shown the list to
+  // be sparse
+  CellBuffers cells;
+  bool cells_ready = false;
 
   // sweep work items
   SweepItem *d_items = nullptr;
@@ -528,6 +534,22 @@ int centers_after_read(b200cv_cvc *h, Group &G, cudaStream_t s)
     if (rc_ != B200CV_OK) return rc_; \
   } while (0)
 
+// the last rebuild listed fewer than 2 % of this rank's pairs
+bool sparse_list(const b200cv_cvc *h)
+{
+  unsigned long long const n1 = h->g[0].n, n2 = h->self() ? n1 : h->g[1].n;
+  unsigned long long const pairs = (h->self() ? n1 * (n1 - 1) / 2 : n1 * n2) / (unsigned)h->world;
+  return h->pl_n * 50ull < pairs;
+}
+
+// rebuild through the cell list (cells.cuh) instead of the all-pairs sweep?
+bool rebuild_with_cells(const b200cv_cvc *h, int flags)
+{
+  return (flags & B200CV_EF_REBUILD_PAIRLIST) && (flags & B200CV_EF_USE_PAIRLIST) &&
+         h->cells_ready && h->P.bc_type == 0 && h->pl_valid && !(h->gated) && sparse_list(h) &&
+         std::getenv("B200CV_CELLS") != nullptr;  // opt-in until validated on the GPU
+}
+
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->pl_cap && h->d_pl) return B200CV_OK;
@@ -771,6 +793,33 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       int rc = enqueue_walk(h->d_partials, nullptr);
       if (rc) return rc;
       npart = EXACT_BLOCKS;
+    } else if (rebuild_with_cells(h, flags)) {
+      // rebuild of a list that the previous rebuild showed to be sparse: only pairs in
+      // neighbouring cells can be within tolerance_l2_max, everything else is exactly zero
+      static_assert(CELL_BLOCKS <= 2 * EXACT_BLOCKS, "partials are sized for 2 * EXACT_BLOCKS");
+      double cut[3];
+      for (int d = 0; d < 3; d++) cut[d] = std::sqrt(h->P.l2_max) / h->P.inv_r0[d];
+      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut, stream));
+      h->launches += 4;
+      CellPairArgs C{};
+      C.x1 = x1; C.y1 = y1; C.z1 = z1; C.x2 = x2; C.y2 = y2; C.z2 = z2;
+      C.g1x = g1x; C.g1y = g1y; C.g1z = g1z; C.g2x = g2x; C.g2y = g2y; C.g2z = g2z;
+      C.n2 = G2.n;
+      C.self = h->self() ? 1 : 0;
+      C.i_begin = (int)((long long)G1.n * h->rank / h->world);
+      C.i_end = (int)((long long)G1.n * (h->rank + 1) / h->world);
+      C.sorted2 = h->cells.d_sorted;
+      C.cell_start = h->cells.d_cell_start;
+      C.grid = h->cells.d_grid;
+      C.pl = h->d_pl;
+      C.pl_cap = h->pl_cap;
+      C.pl_count = h->pl_count();
+      C.partials = h->d_partials;
+      C.flags = flags;
+      C.P = h->P;
+      CUDA_OK(h, launch_cell_pairs(C, stream));
+      h->launches++;
+      npart = CELL_BLOCKS;
     } else {
       int rc = enqueue_all_pairs(flags, rebuild, nullptr, npart);
       if (rc) return rc;
@@ -1038,6 +1087,7 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_pl);
   free_dev(h->d_pl_center);
   free_dev(h->d_items);
+  cells_free(h->cells);
   free_dev(h->d_stage_pos);
   if (h->h_value) cudaFreeHost(h->h_value);
   if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -1125,6 +1175,8 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
         unsigned long long const pairs = h->self() ? n1 * (n1 - 1) / 2 : n1 * n2;
         rc = ensure_pairlist_capacity(h, std::min<unsigned long long>(pairs, 64ull * (n1 + n2)));
         if (rc) return rc;
+        CUDA_OK(h, cells_setup(h->cells, (int)n2));
+        h->cells_ready = true;
       }
     }
   }
@@ -1305,9 +1357,11 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
     int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
     if (rc) return rc;
   }
+  // a rebuild is captured in two forms: all-pairs sweep (first rebuild) and cell list
+  int const graph_key = flags | (rebuild_with_cells(h, flags) ? (1 << 30) : 0);
   b200cv_cvc::StepGraph *hit = nullptr;
   for (auto &g : h->step_graphs) {
-    if (g.flags == flags && g.pos == d_proxy_pos && g.stride == proxy_stride &&
+    if (g.flags == graph_key && g.pos == d_proxy_pos && g.stride == proxy_stride &&
         g.epoch == h->epoch) {
       hit = &g;
     }
@@ -1339,7 +1393,7 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
     cudaGraphDestroy(graph);
     CUDA_OK(h, e);
     size_t nodes = 0;
-    h->step_graphs.push_back({flags, d_proxy_pos, proxy_stride, h->epoch, h->launches, exec});
+    h->step_graphs.push_back({graph_key, d_proxy_pos, proxy_stride, h->epoch, h->launches, exec});
     hit = &h->step_graphs.back();
     (void)nodes;
   }

@@ -1,0 +1,253 @@
+// cells.cu -- see cells.cuh.  Grid construction (bounding box, cell ids, radix sort, cell
+// offsets) and the neighbour-cell pair kernel of the pair-list rebuild.
+#include "cells.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+namespace b200cv {
+
+namespace {
+
+constexpr int GRID_THREADS = 1024;
+
+// ---- bounding box of group2 -> grid parameters (one CTA; a rebuild happens every
+// pairListFrequency steps, this is not on the per-step path) -------------------------------
+__global__ void __launch_bounds__(GRID_THREADS)
+grid_kernel(const double *__restrict__ x, const double *__restrict__ y,
+            const double *__restrict__ z, int n, double cutx, double cuty, double cutz,
+            CellGrid *grid)
+{
+  __shared__ double red[6][GRID_THREADS / 32];
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = threadIdx.x; i < n; i += GRID_THREADS) {
+    double const p[3] = {x[i], y[i], z[i]};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      lo[d] = fmin(lo[d], p[d]);
+      hi[d] = fmax(hi[d], p[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[d][threadIdx.x >> 5] = lo[d];
+      red[3 + d][threadIdx.x >> 5] = hi[d];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double const cut[3] = {cutx, cuty, cutz};
+    int ncells = 1;
+    for (int d = 0; d < 3; d++) {
+      double a = red[d][0], b = red[3 + d][0];
+      for (int w = 1; w < GRID_THREADS / 32; w++) {
+        a = fmin(a, red[d][w]);
+        b = fmax(b, red[3 + d][w]);
+      }
+      double const ext = fmax(b - a, 0.0);
+      // at least one cut-off radius wide (with a margin far above the rounding of the cell
+      // index), and at most CELL_MAX_DIM cells per axis
+      double cell = fmax(cut[d] * (1.0 + 1.0e-9), ext / (double)CELL_MAX_DIM * (1.0 + 1.0e-9));
+      if (!(cell > 0.0)) cell = 1.0;
+      int dim = (int)floor(ext / cell) + 1;
+      dim = max(1, min(dim, CELL_MAX_DIM));
+      grid->origin[d] = a;
+      grid->inv_cell[d] = 1.0 / cell;
+      grid->dim[d] = dim;
+      ncells *= dim;
+    }
+    grid->ncells = ncells;
+  }
+}
+
+__device__ __forceinline__ int cell_coord(double p, double origin, double inv_cell, int dim)
+{
+  // clamped in floating point first: a query atom may be arbitrarily far outside the grid
+  double const c = floor((p - origin) * inv_cell);
+  return (int)fmin(fmax(c, -2.0), (double)dim + 1.0);
+}
+
+__global__ void cell_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                const double *__restrict__ z, int n,
+                                const CellGrid *__restrict__ grid, int *key, int *val)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CellGrid const g = *grid;
+  int const cx = min(max(cell_coord(x[i], g.origin[0], g.inv_cell[0], g.dim[0]), 0), g.dim[0] - 1);
+  int const cy = min(max(cell_coord(y[i], g.origin[1], g.inv_cell[1], g.dim[1]), 0), g.dim[1] - 1);
+  int const cz = min(max(cell_coord(z[i], g.origin[2], g.inv_cell[2], g.dim[2]), 0), g.dim[2] - 1);
+  key[i] = (cz * g.dim[1] + cy) * g.dim[0] + cx;
+  val[i] = i;
+}
+
+// cell_start[c] = first position of the sorted keys with key >= c, for c in [0, ncells]
+__global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
+                                  const CellGrid *__restrict__ grid, int *cell_start)
+{
+  int const c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > grid->ncells) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int const mid = (lo + hi) >> 1;
+    if (key_sorted[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  cell_start[c] = lo;
+}
+
+// ---- candidate pairs: one warp per group1 row, lanes over the atoms of the 3 x 3 x-spans of
+// neighbouring cells (cells adjacent in x are contiguous in key order) -------------------------
+__global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
+{
+  __shared__ double red[CELL_THREADS / 32];
+  CellGrid const g = *A.grid;
+  int const lane = threadIdx.x & 31;
+  int const warps_per_block = CELL_THREADS / 32;
+  int const gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  int const nwarps = gridDim.x * warps_per_block;
+  bool const grad = A.flags & EF_GRADIENTS;
+  double fsum = 0.0;
+  for (int i = A.i_begin + gwarp; i < A.i_end; i += nwarps) {
+    double const xi = A.x1[i], yi = A.y1[i], zi = A.z1[i];
+    int const cx = cell_coord(xi, g.origin[0], g.inv_cell[0], g.dim[0]);
+    int const cy = cell_coord(yi, g.origin[1], g.inv_cell[1], g.dim[1]);
+    int const cz = cell_coord(zi, g.origin[2], g.inv_cell[2], g.dim[2]);
+    int const x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    if (x0 <= x1) {
+      for (int nz = max(cz - 1, 0); nz <= min(cz + 1, g.dim[2] - 1); nz++) {
+        for (int ny = max(cy - 1, 0); ny <= min(cy + 1, g.dim[1] - 1); ny++) {
+          int const row = (nz * g.dim[1] + ny) * g.dim[0];
+          int const begin = A.cell_start[row + x0], end = A.cell_start[row + x1 + 1];
+          for (int p0 = begin; p0 < end; p0 += 32) {
+            int const p = p0 + lane;
+            double F = 0.0, Gx = 0.0, Gy = 0.0, Gz = 0.0;
+            int j = -1;
+            if (p < end) {
+              j = A.sorted2[p];
+              if (!A.self || j > i) {
+                F = pair_exact(A.P, xi, yi, zi, A.x2[j], A.y2[j], A.z2[j], A.flags, Gx, Gy, Gz);
+              }
+            }
+            bool const listed = F > 0.0;
+            fsum += F;
+            if (grad && listed) {
+              gx += Gx;
+              gy += Gy;
+              gz += Gz;
+              atomicAdd(&A.g2x[j], Gx);
+              atomicAdd(&A.g2y[j], Gy);
+              atomicAdd(&A.g2z[j], Gz);
+            }
+            unsigned const m = __ballot_sync(0xffffffffu, listed);
+            if (m != 0u && A.pl != nullptr) {
+              unsigned long long base = 0ull;
+              if (lane == 0) base = atomicAdd(A.pl_count, (unsigned long long)__popc(m));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (listed) {
+                unsigned long long const slot = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+                if (slot < A.pl_cap) {
+                  A.pl[slot] = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (grad) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        gx += __shfl_xor_sync(0xffffffffu, gx, s);
+        gy += __shfl_xor_sync(0xffffffffu, gy, s);
+        gz += __shfl_xor_sync(0xffffffffu, gz, s);
+      }
+      if (lane == 0 && (gx != 0.0 || gy != 0.0 || gz != 0.0)) {
+        atomicAdd(&A.g1x[i], -gx);
+        atomicAdd(&A.g1y[i], -gy);
+        atomicAdd(&A.g1z[i], -gz);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, s);
+  if (lane == 0) red[threadIdx.x >> 5] = fsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < warps_per_block; w++) s += red[w];
+    A.partials[blockIdx.x] = s;
+  }
+}
+
+}  // namespace
+
+int cells_setup(CellBuffers &B, int n2)
+{
+  if (B.d_grid && B.n2 == n2) return 0;
+  cells_free(B);
+  B.n2 = n2;
+  cudaError_t e;
+  if ((e = cudaMalloc(&B.d_grid, sizeof(CellGrid))) != cudaSuccess) return (int)e;
+  size_t const nb = sizeof(int) * (size_t)std::max(n2, 1);
+  if ((e = cudaMalloc(&B.d_key, nb)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_key_sorted, nb)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_val, nb)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_sorted, nb)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_cell_start, sizeof(int) * ((size_t)CELL_MAX + 2))) != cudaSuccess) {
+    return (int)e;
+  }
+  B.temp_bytes = 0;
+  e = cub::DeviceRadixSort::SortPairs(nullptr, B.temp_bytes, B.d_key, B.d_key_sorted, B.d_val,
+                                      B.d_sorted, n2, 0, 22);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_temp, std::max<size_t>(B.temp_bytes, 16))) != cudaSuccess) return (int)e;
+  return 0;
+}
+
+void cells_free(CellBuffers &B)
+{
+  cudaFree(B.d_grid);
+  cudaFree(B.d_key);
+  cudaFree(B.d_key_sorted);
+  cudaFree(B.d_val);
+  cudaFree(B.d_sorted);
+  cudaFree(B.d_cell_start);
+  cudaFree(B.d_temp);
+  B = CellBuffers();
+}
+
+int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
+                const double cut[3], cudaStream_t stream)
+{
+  grid_kernel<<<1, GRID_THREADS, 0, stream>>>(x2, y2, z2, n2, cut[0], cut[1], cut[2], B.d_grid);
+  note_launch();
+  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, B.d_val);
+  note_launch();
+  size_t bytes = B.temp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(B.d_temp, bytes, B.d_key, B.d_key_sorted,
+                                                  B.d_val, B.d_sorted, n2, 0, 22, stream);
+  if (e != cudaSuccess) return (int)e;
+  note_launch();
+  cell_start_kernel<<<(CELL_MAX + 1 + 255) / 256, 256, 0, stream>>>(B.d_key_sorted, n2, B.d_grid,
+                                                                   B.d_cell_start);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream)
+{
+  cell_pairs_kernel<<<CELL_BLOCKS, CELL_THREADS, 0, stream>>>(args);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b200cv

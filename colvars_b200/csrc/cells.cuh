@@ -1,0 +1,67 @@
+// cells.cuh -- cell-list rebuild of the pair list (non-periodic).
+//
+// On a rebuild step the reference visits every pair (src/colvarcomp_coordnums.cpp:219-232), but a
+// pair with l2 > tolerance_l2_max returns 0 before anything is evaluated and is not listed
+// (src/colvarcomp_coordnums.h:256-261).  With cells at least one cut-off radius wide per axis
+// (|d_axis| > cell_axis  =>  (d_axis / r0_axis)^2 > l2_max  =>  l2 > l2_max) every pair outside
+// the 27 neighbouring cells is such a pair, so it can be skipped without changing any number:
+// value, gradients and list are those of the full sweep.  Candidates are evaluated in the
+// reference's operation order (pair_exact), so every listed / not-listed decision is the
+// reference's own.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pair_math.cuh"
+
+namespace b200cv {
+
+constexpr int CELL_MAX_DIM = 128;  // cells per axis at most (2^21 cells)
+constexpr int CELL_MAX = CELL_MAX_DIM * CELL_MAX_DIM * CELL_MAX_DIM;
+constexpr int CELL_BLOCKS = 592;
+constexpr int CELL_THREADS = 256;
+
+// grid of the group2 atoms, computed on the device (no host round trip)
+struct CellGrid {
+  double origin[3];
+  double inv_cell[3];
+  int dim[3];
+  int ncells;
+};
+
+struct CellBuffers {
+  CellGrid *d_grid = nullptr;
+  int *d_key = nullptr, *d_key_sorted = nullptr;  // cell id per group2 atom
+  int *d_val = nullptr, *d_sorted = nullptr;      // atom index, sorted by cell
+  int *d_cell_start = nullptr;                    // [CELL_MAX + 1]
+  void *d_temp = nullptr;                         // radix-sort scratch
+  size_t temp_bytes = 0;
+  int n2 = 0;
+};
+
+struct CellPairArgs {
+  const double *x1, *y1, *z1;
+  const double *x2, *y2, *z2;
+  double *g1x, *g1y, *g1z;
+  double *g2x, *g2y, *g2z;
+  int n2, self;
+  int i_begin, i_end;  // group1 rows of this rank
+  const int *sorted2;
+  const int *cell_start;
+  const CellGrid *grid;
+  unsigned long long *pl;
+  unsigned long long pl_cap;
+  unsigned long long *pl_count;
+  double *partials;  // [CELL_BLOCKS]
+  int flags;
+  PairParams P;
+};
+
+// allocate for n2 group2 atoms (not capturable: call before any stream capture)
+int cells_setup(CellBuffers &B, int n2);
+void cells_free(CellBuffers &B);
+// grid + sort of the group2 atoms; cut[d] = cut-off radius along axis d
+int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
+                const double cut[3], cudaStream_t stream);
+int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream);
+
+}  // namespace b200cv
