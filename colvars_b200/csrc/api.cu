@@ -131,6 +131,7 @@ struct b200cv_cvc {
   unsigned long long *d_rare = nullptr;
   unsigned int rare_cap = 0;
   unsigned long long *d_pl = nullptr;
+  unsigned long long *d_pl_scratch = nullptr;  // cell-list rebuild writes here, then shuffles
   unsigned long long pl_cap = 0;
   unsigned long long pl_n = 0;  // entries of the current list
   bool pl_valid = false;        // a rebuild has happened
@@ -546,17 +547,21 @@ bool sparse_list(const b200cv_cvc *h)
 bool rebuild_with_cells(const b200cv_cvc *h, int flags)
 {
   return (flags & B200CV_EF_REBUILD_PAIRLIST) && (flags & B200CV_EF_USE_PAIRLIST) &&
-         h->cells_ready && h->P.bc_type == 0 && h->pl_valid && !(h->gated) && sparse_list(h) &&
-         std::getenv("B200CV_CELLS") != nullptr;  // opt-in until validated on the GPU
+         h->cells_ready && h->d_pl_scratch && h->P.bc_type == 0 && h->pl_valid && !(h->gated) &&
+         sparse_list(h) && !std::getenv("B200CV_NO_CELLS");
 }
 
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->pl_cap && h->d_pl) return B200CV_OK;
   free_dev(h->d_pl);
+  free_dev(h->d_pl_scratch);
   h->epoch++;
   unsigned long long cap = std::max<unsigned long long>(need + need / 2, 1ull << 20);
   CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * cap));
+  if (h->cells_ready) {
+    CUDA_OK(h, cudaMalloc(&h->d_pl_scratch, sizeof(unsigned long long) * cap));
+  }
   h->pl_cap = cap;
   return B200CV_OK;
 }
@@ -811,14 +816,16 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.sorted2 = h->cells.d_sorted;
       C.cell_start = h->cells.d_cell_start;
       C.grid = h->cells.d_grid;
-      C.pl = h->d_pl;
+      C.pl = h->d_pl_scratch;
       C.pl_cap = h->pl_cap;
       C.pl_count = h->pl_count();
       C.partials = h->d_partials;
       C.flags = flags;
+      C.fast_exp = (h->exp_special == 3) ? 3 : 0;
       C.P = h->P;
       CUDA_OK(h, launch_cell_pairs(C, stream));
-      h->launches++;
+      CUDA_OK(h, launch_list_shuffle(h->d_pl_scratch, h->d_pl, h->pl_count(), h->pl_cap, stream));
+      h->launches += 2;
       npart = CELL_BLOCKS;
     } else {
       int rc = enqueue_all_pairs(flags, rebuild, nullptr, npart);
@@ -1085,6 +1092,7 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_partials);
   free_dev(h->d_rare);
   free_dev(h->d_pl);
+  free_dev(h->d_pl_scratch);
   free_dev(h->d_pl_center);
   free_dev(h->d_items);
   cells_free(h->cells);
@@ -1173,10 +1181,10 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
       } else {
         unsigned long long const n1 = h->g[0].n, n2 = h->self() ? n1 : h->g[1].n;
         unsigned long long const pairs = h->self() ? n1 * (n1 - 1) / 2 : n1 * n2;
-        rc = ensure_pairlist_capacity(h, std::min<unsigned long long>(pairs, 64ull * (n1 + n2)));
-        if (rc) return rc;
         CUDA_OK(h, cells_setup(h->cells, (int)n2));
         h->cells_ready = true;
+        rc = ensure_pairlist_capacity(h, std::min<unsigned long long>(pairs, 64ull * (n1 + n2)));
+        if (rc) return rc;
       }
     }
   }
@@ -1574,8 +1582,12 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
   if (want > h->pl_cap) {
     // ensure_pairlist_capacity over-allocates by 1.5x: ask for exactly `want`
     free_dev(h->d_pl);
+    free_dev(h->d_pl_scratch);
     h->epoch++;
     CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * want));
+    if (h->cells_ready) {
+      CUDA_OK(h, cudaMalloc(&h->d_pl_scratch, sizeof(unsigned long long) * want));
+    }
     h->pl_cap = want;
   }
   h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1)

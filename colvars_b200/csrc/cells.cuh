@@ -53,6 +53,7 @@ struct CellPairArgs {
   unsigned long long *pl_count;
   double *partials;  // [CELL_BLOCKS]
   int flags;
+  int fast_exp;  // 3: candidates may use the sweep's fast 6/12 form (see ExactArgs::fast_exp)
   PairParams P;
 };
 
@@ -63,5 +64,11 @@ void cells_free(CellBuffers &B);
 int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
                 const double cut[3], cudaStream_t stream);
 int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream);
+// dst[(k * PRIME) mod n] = src[k] for k < n = min(*count, cap): the cell kernel emits runs of
+// entries with the same row, which would make 32 lanes of the list walk add to one gradient
+// address; a multiplicative permutation spreads every run over the whole list
+int launch_list_shuffle(const unsigned long long *src, unsigned long long *dst,
+                        const unsigned long long *count, unsigned long long cap,
+                        cudaStream_t stream);
 
 }  // namespace b200cv

@@ -737,3 +737,44 @@ def test_handles_are_independent_across_host_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("kind,aniso", [("selfCoordNum", False), ("coordNum", False),
+                                        ("coordNum", True)])
+def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso):
+    """Once a rebuild has shown the list to be sparse (< 2 % of the pairs), later rebuilds only
+    visit pairs in neighbouring cells (csrc/cells.cu); everything else is exactly zero in the
+    reference as well (l2 > tolerance_l2_max returns before anything is evaluated), so value,
+    gradients and list must not change."""
+    cb = _cb()
+    rng = np.random.default_rng(77)
+    n1, n2 = (3000, 0) if kind == "selfCoordNum" else (700, 5000)
+    L = 70.0  # ~0.01 atoms / A^3: a few listed pairs per atom
+    pos = rng.random((n1 + n2, 3)) * L
+    pos[:5] += 3.0 * L  # a few atoms far outside the box of the others
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32) if n2 else None
+    cutoff3 = (3.0, 5.0, 4.0) if aniso else (4.0, 4.0, 4.0)
+    tol, freq = 0.01, 2
+    cv = cb.CoordNum(kind, i1, i2, cutoff3=cutoff3, tolerance=tol, pairlist_freq=freq)
+    p = O.make_params(cutoff3, tolerance=tol)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    used_cells = 0
+    for step in range(7):
+        frame = pos + rng.normal(0, 0.15, pos.shape) * step
+        v = cv.calc_host(np.ascontiguousarray(frame), step=step)
+        rebuild = step % freq == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(cv.gradients(2), og2)
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
+            assert pl.sum() * 50 < npairs  # sparse, as intended
+            if cv.last_stats()[0] >= 6:  # grid, keys, sort, offsets, pairs, shuffle (+ final sum)
+                used_cells += 1
+    assert used_cells == 3  # every rebuild after the first one
