@@ -23,6 +23,59 @@ from tests import oracle_lib as O
 
 kind = sys.argv[1]
 n1, n2 = int(sys.argv[2]), int(sys.argv[3])
+if kind.endswith("-pairlist"):
+    # sparse pair list, rebuilt every 2 steps: the first rebuild is a sharded sweep, the later
+    # ones go through the cell list on each rank's rows (csrc/cells.cu)
+    kind = kind[:-len("-pairlist")]
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    rng = np.random.default_rng(23)
+    pos0 = np.ascontiguousarray(rng.random((n1 + n2, 3)) * 75.0)
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    self_ = kind == "selfCoordNum"
+    cv = cb.CoordNum(kind, i1, None if self_ else i2, cutoff=4.0, tolerance=0.01, pairlist_freq=2,
+                     device=int(os.environ["LOCAL_RANK"]))
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(cb.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    cv.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    p = O.make_params(tolerance=0.01)
+    npairs = n1 * (n1 - 1) // 2 if self_ else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    cells_used = 0
+    for step in range(5):
+        pos = pos0 + 0.1 * step * np.sin(pos0 + step)
+        d_pos = torch.tensor(np.ascontiguousarray(pos.T), device=dev)
+        cv.read_data(d_pos)
+        cv.calc_value(step=step)
+        v = cv.value()
+        rebuild = step % 2 == 0
+        if self_:
+            ov, og1 = O.selfcoordnum(p, pos, pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, pos[i1], pos[i2], pairlist=pl, rebuild=rebuild)
+            g2 = cv.gradients(2)
+            assert np.max(np.abs(g2 - og2)) <= 1e-12 * np.max(np.abs(og2)), (rank, step)
+        assert abs(v - ov) <= 1e-12 * abs(ov), (rank, step, v, ov)
+        g1 = cv.gradients(1)
+        assert np.max(np.abs(g1 - og1)) <= 1e-12 * np.max(np.abs(og1)), (rank, step)
+        if rebuild and cv.last_stats()[0] >= 6:
+            cells_used += 1
+    assert cells_used == 2, cells_used
+    # the ranks' lists together are the reference's list
+    mine = torch.tensor(cv.pairlist().astype(np.int64), device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.numel()], device=dev))
+    total = int(sum(int(x.item()) for x in sizes))
+    assert total == int(pl.sum()), (total, int(pl.sum()))
+    print(f"MULTI-OK rank {rank} {kind} pair list value {v:.15e}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
@@ -82,7 +135,9 @@ def _free_port():
 
 @pytest.mark.parametrize("kind,n1,n2", [("coordNum", 5000, 20000), ("coordNum", 300, 30000),
                                         ("selfCoordNum", 9000, 0),
-                                        ("distanceInv", 3000, 40000)])
+                                        ("distanceInv", 3000, 40000),
+                                        ("selfCoordNum-pairlist", 4000, 0),
+                                        ("coordNum-pairlist", 900, 5000)])
 def test_sharded_run_matches_oracle_on_every_rank(kind, n1, n2, tmp_path):
     import torch
     ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
