@@ -778,3 +778,42 @@ def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso):
             if cv.last_stats()[0] >= 6:  # grid, keys, sort, offsets, pairs, shuffle (+ final sum)
                 used_cells += 1
     assert used_cells == 3  # every rebuild after the first one
+
+
+def test_cell_list_rebuild_inside_the_fused_step_graph():
+    """b200cv_step keeps one captured graph per flag set; a rebuild exists in two forms (tile
+    sweep for the first one, cell list once the list is known to be sparse) and both have to
+    replay correctly, CUB's radix sort included."""
+    import torch
+    cb = _cb()
+    rng = np.random.default_rng(5)
+    n1, n2 = 600, 4000
+    pos = np.ascontiguousarray(rng.random((n1 + n2, 3)) * 70.0)
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    kw = dict(cutoff=4.0, tolerance=0.01, pairlist_freq=2)
+    a = cb.CoordNum("coordNum", i1, i2, **kw)   # plain calls
+    b = cb.CoordNum("coordNum", i1, i2, **kw)   # fused graph
+    d_pos = torch.tensor(np.ascontiguousarray(pos.T), device="cuda")
+    cells = 0
+    for step in range(9):
+        d_pos += 0.02 * torch.sin(d_pos + step)
+        a.read_data(d_pos)
+        a.calc_value(step=step)
+        va = a.value()
+        b.step(d_pos, step=step)
+        vb = b.value()
+        close_val(vb, va, 1e-13)
+        close_arr(b.gradients(1), a.gradients(1), 1e-13)
+        close_arr(b.gradients(2), a.gradients(2), 1e-13)
+        if step % 2 == 0:
+            assert np.array_equal(np.sort(a.pairlist()), np.sort(b.pairlist()))
+            cells += int(a.last_stats()[0] >= 6)
+    assert cells == 4
+    p = O.make_params(tolerance=0.01)
+    frame = d_pos.cpu().numpy().T
+    pl = np.zeros(n1 * n2, dtype=np.uint8)
+    pl[a.pairlist()] = 1
+    ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=False)
+    close_val(va, ov)
+    close_arr(a.gradients(1), og1)
