@@ -543,12 +543,18 @@ bool sparse_list(const b200cv_cvc *h)
   return h->pl_n * 50ull < pairs;
 }
 
-// rebuild through the cell list (cells.cuh) instead of the all-pairs sweep?
+// the cell list (cells.cuh) is set up and applies: non-periodic, a list has been built before
+bool cells_usable(const b200cv_cvc *h)
+{
+  return h->cells_ready && h->d_pl_scratch && h->P.bc_type == 0 && h->pl_n > 0 &&
+         !std::getenv("B200CV_NO_CELLS");
+}
+
+// rebuild through the cell list instead of the all-pairs sweep?
 bool rebuild_with_cells(const b200cv_cvc *h, int flags)
 {
   return (flags & B200CV_EF_REBUILD_PAIRLIST) && (flags & B200CV_EF_USE_PAIRLIST) &&
-         h->cells_ready && h->d_pl_scratch && h->P.bc_type == 0 && h->pl_valid && !(h->gated) &&
-         sparse_list(h) && !std::getenv("B200CV_NO_CELLS");
+         cells_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
 }
 
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
@@ -785,26 +791,13 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       return B200CV_OK;
     };
 
-    if (gated) {
-      // captured evaluation with a pair list: the graph holds the rebuild sweep AND the list
-      // walk; the mode word decides on the device which of the two does any work
-      int nparts = 0;
-      int rc = enqueue_all_pairs(flags | B200CV_EF_REBUILD_PAIRLIST, true, h->gate(), nparts);
-      if (rc) return rc;
-      rc = enqueue_walk(h->d_partials + nparts, h->gate());
-      if (rc) return rc;
-      npart = nparts + EXACT_BLOCKS;
-    } else if (walk_list) {
-      int rc = enqueue_walk(h->d_partials, nullptr);
-      if (rc) return rc;
-      npart = EXACT_BLOCKS;
-    } else if (rebuild_with_cells(h, flags)) {
-      // rebuild of a list that the previous rebuild showed to be sparse: only pairs in
-      // neighbouring cells can be within tolerance_l2_max, everything else is exactly zero
+    // rebuild of a list that a previous rebuild showed to be sparse: only pairs in neighbouring
+    // cells can be within tolerance_l2_max, everything else is exactly zero (cells.cuh)
+    auto enqueue_cells = [&](int cell_flags, const int *gate) -> int {
       static_assert(CELL_BLOCKS <= 2 * EXACT_BLOCKS, "partials are sized for 2 * EXACT_BLOCKS");
       double cut[3];
       for (int d = 0; d < 3; d++) cut[d] = std::sqrt(h->P.l2_max) / h->P.inv_r0[d];
-      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut, stream));
+      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut, gate, stream));
       h->launches += 4;
       CellPairArgs C{};
       C.x1 = x1; C.y1 = y1; C.z1 = z1; C.x2 = x2; C.y2 = y2; C.z2 = z2;
@@ -820,12 +813,40 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.pl_cap = h->pl_cap;
       C.pl_count = h->pl_count();
       C.partials = h->d_partials;
-      C.flags = flags;
+      C.flags = cell_flags;
       C.fast_exp = (h->exp_special == 3) ? 3 : 0;
+      C.gate = gate;
       C.P = h->P;
       CUDA_OK(h, launch_cell_pairs(C, stream));
-      CUDA_OK(h, launch_list_shuffle(h->d_pl_scratch, h->d_pl, h->pl_count(), h->pl_cap, stream));
+      CUDA_OK(h, launch_list_shuffle(h->d_pl_scratch, h->d_pl, h->pl_count(), h->pl_cap, gate,
+                                     stream));
       h->launches += 2;
+      return B200CV_OK;
+    };
+
+    if (gated) {
+      // captured evaluation with a pair list: the graph holds the rebuild sweep AND the list
+      // walk; the mode word decides on the device which of the two does any work
+      int nparts = 0;
+      int rc;
+      if (cells_usable(h) && sparse_list(h)) {
+        // sized and found sparse by b200cv_pairlist_reserve before the capture
+        rc = enqueue_cells(flags | B200CV_EF_REBUILD_PAIRLIST, h->gate());
+        nparts = CELL_BLOCKS;
+      } else {
+        rc = enqueue_all_pairs(flags | B200CV_EF_REBUILD_PAIRLIST, true, h->gate(), nparts);
+      }
+      if (rc) return rc;
+      rc = enqueue_walk(h->d_partials + nparts, h->gate());
+      if (rc) return rc;
+      npart = nparts + EXACT_BLOCKS;
+    } else if (walk_list) {
+      int rc = enqueue_walk(h->d_partials, nullptr);
+      if (rc) return rc;
+      npart = EXACT_BLOCKS;
+    } else if (rebuild_with_cells(h, flags)) {
+      int rc = enqueue_cells(flags, nullptr);
+      if (rc) return rc;
       npart = CELL_BLOCKS;
     } else {
       int rc = enqueue_all_pairs(flags, rebuild, nullptr, npart);
@@ -1590,8 +1611,8 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
     }
     h->pl_cap = want;
   }
-  h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1)
-  h->pl_n = 0;
+  h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1);
+                        // pl_n stays: it tells the capture whether the list is sparse
   *h->h_mode = 1;
   return B200CV_OK;
 }

@@ -17,9 +17,10 @@ constexpr int GRID_THREADS = 1024;
 __global__ void __launch_bounds__(GRID_THREADS)
 grid_kernel(const double *__restrict__ x, const double *__restrict__ y,
             const double *__restrict__ z, int n, double cutx, double cuty, double cutz,
-            CellGrid *grid)
+            CellGrid *grid, const int *gate)
 {
   __shared__ double red[6][GRID_THREADS / 32];
+  if (gate != nullptr && *gate != 1) return;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int i = threadIdx.x; i < n; i += GRID_THREADS) {
     double const p[3] = {x[i], y[i], z[i]};
@@ -76,10 +77,12 @@ __device__ __forceinline__ int cell_coord(double p, double origin, double inv_ce
 
 __global__ void cell_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                 const double *__restrict__ z, int n,
-                                const CellGrid *__restrict__ grid, int *key, int *val)
+                                const CellGrid *__restrict__ grid, int *key, int *val,
+                                const int *gate)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (gate != nullptr && *gate != 1) return;  // keys of the last rebuild stay: still sortable
   CellGrid const g = *grid;
   int const cx = min(max(cell_coord(x[i], g.origin[0], g.inv_cell[0], g.dim[0]), 0), g.dim[0] - 1);
   int const cy = min(max(cell_coord(y[i], g.origin[1], g.inv_cell[1], g.dim[1]), 0), g.dim[1] - 1);
@@ -90,9 +93,11 @@ __global__ void cell_key_kernel(const double *__restrict__ x, const double *__re
 
 // cell_start[c] = first position of the sorted keys with key >= c, for c in [0, ncells]
 __global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
-                                  const CellGrid *__restrict__ grid, int *cell_start)
+                                  const CellGrid *__restrict__ grid, int *cell_start,
+                                  const int *gate)
 {
   int const c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gate != nullptr && *gate != 1) return;
   if (c > grid->ncells) return;
   int lo = 0, hi = n;
   while (lo < hi) {
@@ -108,6 +113,10 @@ __global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
 __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
 {
   __shared__ double red[CELL_THREADS / 32];
+  if (A.gate != nullptr && *A.gate != 1) {
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
+    return;
+  }
   CellGrid const g = *A.grid;
   int const lane = threadIdx.x & 31;
   int const warps_per_block = CELL_THREADS / 32;
@@ -209,8 +218,9 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
 __global__ void list_shuffle_kernel(const unsigned long long *__restrict__ src,
                                     unsigned long long *__restrict__ dst,
                                     const unsigned long long *__restrict__ count,
-                                    unsigned long long cap)
+                                    unsigned long long cap, const int *gate)
 {
+  if (gate != nullptr && *gate != 1) return;
   unsigned long long n = *count;
   if (n > cap) n = cap;
   // a prime above any list length: k -> k * PRIME mod n is a permutation of [0, n).  Measured
@@ -227,10 +237,10 @@ __global__ void list_shuffle_kernel(const unsigned long long *__restrict__ src,
 }  // namespace
 
 int launch_list_shuffle(const unsigned long long *src, unsigned long long *dst,
-                        const unsigned long long *count, unsigned long long cap,
+                        const unsigned long long *count, unsigned long long cap, const int *gate,
                         cudaStream_t stream)
 {
-  list_shuffle_kernel<<<1184, 256, 0, stream>>>(src, dst, count, cap);
+  list_shuffle_kernel<<<1184, 256, 0, stream>>>(src, dst, count, cap, gate);
   note_launch();
   return (int)cudaGetLastError();
 }
@@ -271,11 +281,13 @@ void cells_free(CellBuffers &B)
 }
 
 int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
-                const double cut[3], cudaStream_t stream)
+                const double cut[3], const int *gate, cudaStream_t stream)
 {
-  grid_kernel<<<1, GRID_THREADS, 0, stream>>>(x2, y2, z2, n2, cut[0], cut[1], cut[2], B.d_grid);
+  grid_kernel<<<1, GRID_THREADS, 0, stream>>>(x2, y2, z2, n2, cut[0], cut[1], cut[2], B.d_grid,
+                                              gate);
   note_launch();
-  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, B.d_val);
+  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, B.d_val,
+                                                        gate);
   note_launch();
   size_t bytes = B.temp_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(B.d_temp, bytes, B.d_key, B.d_key_sorted,
@@ -283,7 +295,7 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
   if (e != cudaSuccess) return (int)e;
   note_launch();
   cell_start_kernel<<<(CELL_MAX + 1 + 255) / 256, 256, 0, stream>>>(B.d_key_sorted, n2, B.d_grid,
-                                                                   B.d_cell_start);
+                                                                   B.d_cell_start, gate);
   note_launch();
   return (int)cudaGetLastError();
 }

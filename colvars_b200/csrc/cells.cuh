@@ -54,6 +54,7 @@ struct CellPairArgs {
   double *partials;  // [CELL_BLOCKS]
   int flags;
   int fast_exp;  // 3: candidates may use the sweep's fast 6/12 form (see ExactArgs::fast_exp)
+  const int *gate;  // captured pair-list graphs: work only when *gate == 1 (see SweepArgs::gate)
   PairParams P;
 };
 
@@ -61,14 +62,15 @@ struct CellPairArgs {
 int cells_setup(CellBuffers &B, int n2);
 void cells_free(CellBuffers &B);
 // grid + sort of the group2 atoms; cut[d] = cut-off radius along axis d
+// gate (may be NULL): see CellPairArgs::gate; the radix sort itself always runs
 int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
-                const double cut[3], cudaStream_t stream);
+                const double cut[3], const int *gate, cudaStream_t stream);
 int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream);
 // dst[(k * PRIME) mod n] = src[k] for k < n = min(*count, cap): the cell kernel emits runs of
 // entries with the same row, which would make 32 lanes of the list walk add to one gradient
 // address; a multiplicative permutation spreads every run over the whole list
 int launch_list_shuffle(const unsigned long long *src, unsigned long long *dst,
-                        const unsigned long long *count, unsigned long long cap,
+                        const unsigned long long *count, unsigned long long cap, const int *gate,
                         cudaStream_t stream);
 
 }  // namespace b200cv

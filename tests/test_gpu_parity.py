@@ -817,3 +817,60 @@ def test_cell_list_rebuild_inside_the_fused_step_graph():
     ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=False)
     close_val(va, ov)
     close_arr(a.gradients(1), og1)
+
+
+@pytest.mark.parametrize("kind", ["selfCoordNum", "coordNum"])
+def test_captured_pairlist_graph_on_a_sparse_system_uses_the_cell_list(kind):
+    """The `smp gpu` form (one captured graph, mode word) with a sparse list: the rebuild branch
+    of the graph is the gated cell-list pipeline; replays for rebuild and walk steps against the
+    synchronous path and the oracle."""
+    import torch
+    cb = _cb()
+    rng = np.random.default_rng(15)
+    n1, n2 = (2500, 0) if kind == "selfCoordNum" else (500, 4000)
+    pos = rng.random((n1 + n2, 3)) * 70.0
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32) if n2 else None
+    freq, tol = 3, 0.01
+    kw = dict(cutoff=4.0, tolerance=tol, pairlist_freq=freq)
+    cv = cb.CoordNum(kind, i1, i2, **kw)
+    p1 = torch.tensor(np.ascontiguousarray(pos[i1].T), device="cuda")
+    p2 = torch.tensor(np.ascontiguousarray(pos[i2].T), device="cuda") if n2 else None
+    g1 = torch.zeros_like(p1)
+    g2 = torch.zeros_like(p2) if n2 else None
+    flags = cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST
+    side = torch.cuda.Stream()
+    cv.pairlist_reserve(p1, p2, headroom=2.0, stream=side)
+    side.synchronize()
+    launches_before = cb.kernel_launches()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        cv.eval_async(p1, p2, flags, stream=side)
+        cv.accumulate_gradients(g1, g2, stream=side)
+    # fetch, grid, keys, sort (>= 1), offsets, pairs, shuffle, walk, final sum, repacks ...
+    assert cb.kernel_launches() - launches_before >= 10
+    p = O.make_params((4.0,) * 3, tolerance=tol)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    for step in range(7):
+        frame = pos + rng.normal(0, 0.1, pos.shape) * step
+        p1.copy_(torch.tensor(np.ascontiguousarray(frame[i1].T)))
+        g1.zero_()
+        if n2:
+            p2.copy_(torch.tensor(np.ascontiguousarray(frame[i2].T)))
+            g2.zero_()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        v = cv.value()
+        cv.pairlist_set_rebuild((step + 1) % freq == 0)
+        rebuild = step % freq == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(g2.cpu().numpy().T, og2)
+        close_val(v, ov)
+        close_arr(g1.cpu().numpy().T, og1)
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
