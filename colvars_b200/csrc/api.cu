@@ -543,11 +543,26 @@ bool sparse_list(const b200cv_cvc *h)
   return h->pl_n * 50ull < pairs;
 }
 
-// the cell list (cells.cuh) is set up and applies: non-periodic, a list has been built before
+// cut-off radius per axis: beyond it l2 > tolerance_l2_max whatever the other two components are
+void cell_cutoffs(const b200cv_cvc *h, double cut[3])
+{
+  for (int d = 0; d < 3; d++) cut[d] = std::sqrt(h->P.l2_max) / h->P.inv_r0[d];
+}
+
+// the cell list (cells.cuh) is set up and applies: a list has been built before, and the system
+// is non-periodic or orthorhombic with at least three cells per axis
 bool cells_usable(const b200cv_cvc *h)
 {
-  return h->cells_ready && h->d_pl_scratch && h->P.bc_type == 0 && h->pl_n > 0 &&
-         !std::getenv("B200CV_NO_CELLS");
+  if (!(h->cells_ready && h->d_pl_scratch && h->pl_n > 0) || std::getenv("B200CV_NO_CELLS")) {
+    return false;
+  }
+  if (h->P.bc_type == 0) return true;
+  if (h->P.bc_type != 2) return false;
+  double cut[3], edges[3] = {std::fabs(h->P.cell[0][0]), std::fabs(h->P.cell[1][1]),
+                             std::fabs(h->P.cell[2][2])};
+  int dim[3];
+  cell_cutoffs(h, cut);
+  return cells_periodic_dims(cut, edges, dim);
 }
 
 // rebuild through the cell list instead of the all-pairs sweep?
@@ -796,8 +811,11 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     auto enqueue_cells = [&](int cell_flags, const int *gate) -> int {
       static_assert(CELL_BLOCKS <= 2 * EXACT_BLOCKS, "partials are sized for 2 * EXACT_BLOCKS");
       double cut[3];
-      for (int d = 0; d < 3; d++) cut[d] = std::sqrt(h->P.l2_max) / h->P.inv_r0[d];
-      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut, gate, stream));
+      cell_cutoffs(h, cut);
+      double const edges[3] = {std::fabs(h->P.cell[0][0]), std::fabs(h->P.cell[1][1]),
+                               std::fabs(h->P.cell[2][2])};
+      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut,
+                             h->P.bc_type == 2 ? edges : nullptr, gate, stream));
       h->launches += 4;
       CellPairArgs C{};
       C.x1 = x1; C.y1 = y1; C.z1 = z1; C.x2 = x2; C.y2 = y2; C.z2 = z2;
@@ -814,7 +832,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.pl_count = h->pl_count();
       C.partials = h->d_partials;
       C.flags = cell_flags;
-      C.fast_exp = (h->exp_special == 3) ? 3 : 0;
+      C.fast_exp = (h->exp_special == 3 && h->P.bc_type == 0) ? 3 : 0;
       C.gate = gate;
       C.P = h->P;
       CUDA_OK(h, launch_cell_pairs(C, stream));

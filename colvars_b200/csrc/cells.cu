@@ -2,6 +2,9 @@
 // offsets) and the neighbour-cell pair kernel of the pair-list rebuild.
 #include "cells.cuh"
 
+#include <algorithm>
+#include <cmath>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
@@ -65,7 +68,15 @@ grid_kernel(const double *__restrict__ x, const double *__restrict__ y,
       ncells *= dim;
     }
     grid->ncells = ncells;
+    grid->periodic = 0;
+    grid->inv_len[0] = grid->inv_len[1] = grid->inv_len[2] = 0.0;
   }
+}
+
+__global__ void set_grid_kernel(CellGrid value, CellGrid *grid, const int *gate)
+{
+  if (gate != nullptr && *gate != 1) return;
+  *grid = value;
 }
 
 __device__ __forceinline__ int cell_coord(double p, double origin, double inv_cell, int dim)
@@ -73,6 +84,14 @@ __device__ __forceinline__ int cell_coord(double p, double origin, double inv_ce
   // clamped in floating point first: a query atom may be arbitrarily far outside the grid
   double const c = floor((p - origin) * inv_cell);
   return (int)fmin(fmax(c, -2.0), (double)dim + 1.0);
+}
+
+// periodic: cell of the atom's image inside the unit cell
+__device__ __forceinline__ int cell_coord_periodic(double p, double inv_len, int dim)
+{
+  double const t = p * inv_len;
+  double const f = t - floor(t);  // [0, 1]; 1.0 only by rounding for tiny negative t
+  return min((int)(f * (double)dim), dim - 1);
 }
 
 __global__ void cell_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
@@ -84,9 +103,16 @@ __global__ void cell_key_kernel(const double *__restrict__ x, const double *__re
   if (i >= n) return;
   if (gate != nullptr && *gate != 1) return;  // keys of the last rebuild stay: still sortable
   CellGrid const g = *grid;
-  int const cx = min(max(cell_coord(x[i], g.origin[0], g.inv_cell[0], g.dim[0]), 0), g.dim[0] - 1);
-  int const cy = min(max(cell_coord(y[i], g.origin[1], g.inv_cell[1], g.dim[1]), 0), g.dim[1] - 1);
-  int const cz = min(max(cell_coord(z[i], g.origin[2], g.inv_cell[2], g.dim[2]), 0), g.dim[2] - 1);
+  int cx, cy, cz;
+  if (g.periodic) {
+    cx = cell_coord_periodic(x[i], g.inv_len[0], g.dim[0]);
+    cy = cell_coord_periodic(y[i], g.inv_len[1], g.dim[1]);
+    cz = cell_coord_periodic(z[i], g.inv_len[2], g.dim[2]);
+  } else {
+    cx = min(max(cell_coord(x[i], g.origin[0], g.inv_cell[0], g.dim[0]), 0), g.dim[0] - 1);
+    cy = min(max(cell_coord(y[i], g.origin[1], g.inv_cell[1], g.dim[1]), 0), g.dim[1] - 1);
+    cz = min(max(cell_coord(z[i], g.origin[2], g.inv_cell[2], g.dim[2]), 0), g.dim[2] - 1);
+  }
   key[i] = (cz * g.dim[1] + cy) * g.dim[0] + cx;
   val[i] = i;
 }
@@ -126,16 +152,36 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
   double fsum = 0.0;
   for (int i = A.i_begin + gwarp; i < A.i_end; i += nwarps) {
     double const xi = A.x1[i], yi = A.y1[i], zi = A.z1[i];
-    int const cx = cell_coord(xi, g.origin[0], g.inv_cell[0], g.dim[0]);
-    int const cy = cell_coord(yi, g.origin[1], g.inv_cell[1], g.dim[1]);
-    int const cz = cell_coord(zi, g.origin[2], g.inv_cell[2], g.dim[2]);
-    int const x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    bool const per = g.periodic != 0;
+    int const cx = per ? cell_coord_periodic(xi, g.inv_len[0], g.dim[0])
+                       : cell_coord(xi, g.origin[0], g.inv_cell[0], g.dim[0]);
+    int const cy = per ? cell_coord_periodic(yi, g.inv_len[1], g.dim[1])
+                       : cell_coord(yi, g.origin[1], g.inv_cell[1], g.dim[1]);
+    int const cz = per ? cell_coord_periodic(zi, g.inv_len[2], g.dim[2])
+                       : cell_coord(zi, g.origin[2], g.inv_cell[2], g.dim[2]);
     double gx = 0.0, gy = 0.0, gz = 0.0;
-    if (x0 <= x1) {
-      for (int nz = max(cz - 1, 0); nz <= min(cz + 1, g.dim[2] - 1); nz++) {
-        for (int ny = max(cy - 1, 0); ny <= min(cy + 1, g.dim[1] - 1); ny++) {
-          int const row = (nz * g.dim[1] + ny) * g.dim[0];
-          int const begin = A.cell_start[row + x0], end = A.cell_start[row + x1 + 1];
+    // neighbouring cells: non-periodic -- clipped to the grid, the three x-cells as one span;
+    // periodic -- wrapped around (dim >= 3, so the three are distinct), one cell at a time
+    for (int dzc = -1; dzc <= 1; dzc++) {
+      int nz = cz + dzc;
+      if (per) nz = (nz + g.dim[2]) % g.dim[2];
+      else if (nz < 0 || nz >= g.dim[2]) continue;
+      for (int dyc = -1; dyc <= 1; dyc++) {
+        int ny = cy + dyc;
+        if (per) ny = (ny + g.dim[1]) % g.dim[1];
+        else if (ny < 0 || ny >= g.dim[1]) continue;
+        int const row = (nz * g.dim[1] + ny) * g.dim[0];
+        int const nspans = per ? 3 : 1;
+        for (int sxc = 0; sxc < nspans; sxc++) {
+          int xa, xb;
+          if (per) {
+            xa = xb = (cx + sxc - 1 + g.dim[0]) % g.dim[0];
+          } else {
+            xa = max(cx - 1, 0);
+            xb = min(cx + 1, g.dim[0] - 1);
+            if (xa > xb) continue;
+          }
+          int const begin = A.cell_start[row + xa], end = A.cell_start[row + xb + 1];
           for (int p0 = begin; p0 < end; p0 += 32) {
             int const p = p0 + lane;
             double F = 0.0, Gx = 0.0, Gy = 0.0, Gz = 0.0;
@@ -280,11 +326,39 @@ void cells_free(CellBuffers &B)
   B = CellBuffers();
 }
 
-int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
-                const double cut[3], const int *gate, cudaStream_t stream)
+bool cells_periodic_dims(const double cut[3], const double edges[3], int dim[3])
 {
-  grid_kernel<<<1, GRID_THREADS, 0, stream>>>(x2, y2, z2, n2, cut[0], cut[1], cut[2], B.d_grid,
-                                              gate);
+  for (int d = 0; d < 3; d++) {
+    if (!(edges[d] > 0.0) || !(cut[d] > 0.0)) return false;
+    double const n = std::floor(edges[d] / (cut[d] * (1.0 + 1.0e-9)));
+    if (n < 3.0) return false;  // the three neighbours of a cell must be distinct
+    dim[d] = (int)std::min(n, (double)CELL_MAX_DIM);
+  }
+  return true;
+}
+
+int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
+                const double cut[3], const double *periodic_edges, const int *gate,
+                cudaStream_t stream)
+{
+  if (periodic_edges != nullptr) {
+    CellGrid g{};
+    int dim[3];
+    if (!cells_periodic_dims(cut, periodic_edges, dim)) return (int)cudaErrorInvalidValue;
+    g.ncells = 1;
+    for (int d = 0; d < 3; d++) {
+      g.origin[d] = 0.0;
+      g.dim[d] = dim[d];
+      g.inv_len[d] = 1.0 / periodic_edges[d];
+      g.inv_cell[d] = (double)dim[d] / periodic_edges[d];
+      g.ncells *= dim[d];
+    }
+    g.periodic = 1;
+    set_grid_kernel<<<1, 1, 0, stream>>>(g, B.d_grid, gate);
+  } else {
+    grid_kernel<<<1, GRID_THREADS, 0, stream>>>(x2, y2, z2, n2, cut[0], cut[1], cut[2], B.d_grid,
+                                                gate);
+  }
   note_launch();
   cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, B.d_val,
                                                         gate);

@@ -26,6 +26,10 @@ struct CellGrid {
   double inv_cell[3];
   int dim[3];
   int ncells;
+  // orthorhombic periodic cell: atoms are wrapped into the unit cell (inv_len = 1 / edge),
+  // neighbours wrap around; dim >= 3 per axis so that the three neighbours are distinct
+  int periodic;
+  double inv_len[3];
 };
 
 struct CellBuffers {
@@ -62,9 +66,14 @@ struct CellPairArgs {
 int cells_setup(CellBuffers &B, int n2);
 void cells_free(CellBuffers &B);
 // grid + sort of the group2 atoms; cut[d] = cut-off radius along axis d
-// gate (may be NULL): see CellPairArgs::gate; the radix sort itself always runs
+// gate (may be NULL): see CellPairArgs::gate; the radix sort itself always runs.
+// periodic_edges: NULL for a non-periodic system (grid = bounding box of group2, found on the
+// device), else the three edge lengths of an orthorhombic cell (grid fixed by the host;
+// cells_periodic_dims tells whether the cell is large enough: >= 3 cells per axis)
 int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
-                const double cut[3], const int *gate, cudaStream_t stream);
+                const double cut[3], const double *periodic_edges, const int *gate,
+                cudaStream_t stream);
+bool cells_periodic_dims(const double cut[3], const double edges[3], int dim[3]);
 int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream);
 // dst[(k * PRIME) mod n] = src[k] for k < n = min(*count, cap): the cell kernel emits runs of
 // entries with the same row, which would make 32 lanes of the list walk add to one gradient

@@ -874,3 +874,52 @@ def test_captured_pairlist_graph_on_a_sparse_system_uses_the_cell_list(kind):
         close_arr(g1.cpu().numpy().T, og1)
         if rebuild:
             assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
+
+
+@pytest.mark.parametrize("kind", ["selfCoordNum", "coordNum"])
+def test_sparse_pairlist_rebuild_through_the_cell_list_periodic(kind):
+    """Orthorhombic periodic cell: atoms are wrapped into the unit cell for binning, neighbour
+    cells wrap around, candidates go through the reference-order minimum-image pair function."""
+    cb = _cb()
+    rng = np.random.default_rng(78)
+    n1, n2 = (3000, 0) if kind == "selfCoordNum" else (700, 5000)
+    edges = np.array([70.0, 75.0, 65.0])
+    cell = ((1, 1, 1), (edges[0], 0, 0), (0, edges[1], 0), (0, 0, edges[2]))
+    pos = (rng.random((n1 + n2, 3)) * 3.0 - 1.0) * edges  # images in the neighbouring cells too
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32) if n2 else None
+    tol, freq = 0.01, 2
+    cv = cb.CoordNum(kind, i1, i2, cutoff3=(4.0, 3.5, 4.5), tolerance=tol, pairlist_freq=freq)
+    cv.set_boundaries(*cell)
+    p = O.make_params((4.0, 3.5, 4.5), tolerance=tol, boundaries=cell)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    used_cells = 0
+    for step in range(5):
+        frame = pos + rng.normal(0, 0.15, pos.shape) * step
+        v = cv.calc_host(np.ascontiguousarray(frame), step=step)
+        rebuild = step % freq == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(cv.gradients(2), og2)
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
+            used_cells += int(cv.last_stats()[0] >= 6)
+    assert used_cells == 2
+    # a cell too small for three cells per axis falls back to the sweep (and stays correct)
+    small = ((1, 1, 1), (20.0, 0, 0), (0, 75.0, 0), (0, 0, 65.0))
+    cv.set_boundaries(*small)
+    p2 = O.make_params((4.0, 3.5, 4.5), tolerance=tol, boundaries=small)
+    v = cv.calc_host(np.ascontiguousarray(pos), step=0)
+    pl2 = np.ones(npairs, dtype=np.uint8)
+    if kind == "selfCoordNum":
+        ov, og1 = O.selfcoordnum(p2, pos[i1], pairlist=pl2, rebuild=True)
+    else:
+        ov, og1, _ = O.coordnum(p2, pos[i1], pos[i2], pairlist=pl2, rebuild=True)
+    assert cv.last_stats()[0] < 6
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
