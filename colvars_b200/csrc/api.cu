@@ -832,7 +832,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.pl_count = h->pl_count();
       C.partials = h->d_partials;
       C.flags = cell_flags;
-      C.fast_exp = (h->exp_special == 3 && h->P.bc_type == 0) ? 3 : 0;
+      C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // bc_type is 0 or 2 here, both have a fast form
       C.gate = gate;
       C.P = h->P;
       CUDA_OK(h, launch_cell_pairs(C, stream));

@@ -194,7 +194,17 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
                 if (A.fast_exp == 3) {
                   // 6/12: the sweep's fast form for every pair that is not next to a decision
                   // threshold (same windows as the sweep), reference order otherwise
-                  double const dx = xj - xi, dy = yj - yi, dz = zj - zi;
+                  double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+                  if (A.P.bc_type == 2) {
+                    // orthorhombic minimum image, image index in the reference's operation
+                    // order (src/colvars_system.h:176-184), as in the tile sweep
+                    double const shx = floor(__dadd_rn(__dmul_rn(A.P.recip[0][0], dx), 0.5));
+                    double const shy = floor(__dadd_rn(__dmul_rn(A.P.recip[1][1], dy), 0.5));
+                    double const shz = floor(__dadd_rn(__dmul_rn(A.P.recip[2][2], dz), 0.5));
+                    dx = fma(-shx, A.P.cell[0][0], dx);
+                    dy = fma(-shy, A.P.cell[1][1], dy);
+                    dz = fma(-shz, A.P.cell[2][2], dz);
+                  }
                   double const sx = dx * A.P.inv_r0[0], sy = dy * A.P.inv_r0[1],
                                sz = dz * A.P.inv_r0[2];
                   double const u = fma(sz, sz, fma(sy, sy, sx * sx));
