@@ -131,7 +131,6 @@ struct b200cv_cvc {
   unsigned long long *d_rare = nullptr;
   unsigned int rare_cap = 0;
   unsigned long long *d_pl = nullptr;
-  unsigned long long *d_pl_scratch = nullptr;  // cell-list rebuild writes here, then shuffles
   unsigned long long pl_cap = 0;
   unsigned long long pl_n = 0;  // entries of the current list
   bool pl_valid = false;        // a rebuild has happened
@@ -553,7 +552,7 @@ void cell_cutoffs(const b200cv_cvc *h, double cut[3])
 // is non-periodic or orthorhombic with at least three cells per axis
 bool cells_usable(const b200cv_cvc *h)
 {
-  if (!(h->cells_ready && h->d_pl_scratch && h->pl_n > 0) || std::getenv("B200CV_NO_CELLS")) {
+  if (!(h->cells_ready && h->d_pl && h->pl_n > 0) || std::getenv("B200CV_NO_CELLS")) {
     return false;
   }
   if (h->P.bc_type == 0) return true;
@@ -576,13 +575,9 @@ int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->pl_cap && h->d_pl) return B200CV_OK;
   free_dev(h->d_pl);
-  free_dev(h->d_pl_scratch);
   h->epoch++;
   unsigned long long cap = std::max<unsigned long long>(need + need / 2, 1ull << 20);
   CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * cap));
-  if (h->cells_ready) {
-    CUDA_OK(h, cudaMalloc(&h->d_pl_scratch, sizeof(unsigned long long) * cap));
-  }
   h->pl_cap = cap;
   return B200CV_OK;
 }
@@ -721,7 +716,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.cap = h->pl_cap;
       E.partials = partials;
       E.flags = flags & ~B200CV_EF_REBUILD_PAIRLIST;
-      E.fast_exp = (h->exp_special == 3 && h->P.bc_type == 0) ? 3 : 0;
+      E.fast_exp = (h->exp_special == 3 && (h->P.bc_type == 0 || h->P.bc_type == 2)) ? 3 : 0;
       E.gate = gate;
       E.gate_on = 0;
       if (fuse) {
@@ -827,7 +822,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.sorted2 = h->cells.d_sorted;
       C.cell_start = h->cells.d_cell_start;
       C.grid = h->cells.d_grid;
-      C.pl = h->d_pl_scratch;
+      C.pl = h->d_pl;
       C.pl_cap = h->pl_cap;
       C.pl_count = h->pl_count();
       C.partials = h->d_partials;
@@ -836,9 +831,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.gate = gate;
       C.P = h->P;
       CUDA_OK(h, launch_cell_pairs(C, stream));
-      CUDA_OK(h, launch_list_shuffle(h->d_pl_scratch, h->d_pl, h->pl_count(), h->pl_cap, gate,
-                                     stream));
-      h->launches += 2;
+      h->launches++;
       return B200CV_OK;
     };
 
@@ -1131,7 +1124,6 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_partials);
   free_dev(h->d_rare);
   free_dev(h->d_pl);
-  free_dev(h->d_pl_scratch);
   free_dev(h->d_pl_center);
   free_dev(h->d_items);
   cells_free(h->cells);
@@ -1621,12 +1613,8 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
   if (want > h->pl_cap) {
     // ensure_pairlist_capacity over-allocates by 1.5x: ask for exactly `want`
     free_dev(h->d_pl);
-    free_dev(h->d_pl_scratch);
     h->epoch++;
     CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * want));
-    if (h->cells_ready) {
-      CUDA_OK(h, cudaMalloc(&h->d_pl_scratch, sizeof(unsigned long long) * want));
-    }
     h->pl_cap = want;
   }
   h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1);

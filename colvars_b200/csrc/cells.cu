@@ -139,12 +139,35 @@ __global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
 __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
 {
   __shared__ double red[CELL_THREADS / 32];
+  // listed neighbours of the warp's current row: written to the list as ONE contiguous run per
+  // row (one counter atomic per run, coalesced stores); the list walk sums the row's gradient
+  // over such a run before it touches memory
+  constexpr int ROW_BUF = 480;
+  __shared__ int jbuf[CELL_THREADS / 32][ROW_BUF];
   if (A.gate != nullptr && *A.gate != 1) {
     if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
     return;
   }
   CellGrid const g = *A.grid;
   int const lane = threadIdx.x & 31;
+  int *const mybuf = jbuf[threadIdx.x >> 5];
+  int nbuf = 0;  // warp-uniform
+  auto flush_row = [&](int row_i) {
+    if (nbuf > 0 && A.pl != nullptr) {
+      __syncwarp();
+      unsigned long long base = 0ull;
+      if (lane == 0) base = atomicAdd(A.pl_count, (unsigned long long)nbuf);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int k = lane; k < nbuf; k += 32) {
+        unsigned long long const slot = base + (unsigned long long)k;
+        if (slot < A.pl_cap) {
+          A.pl[slot] = ((unsigned long long)(unsigned)row_i << 32) | (unsigned)mybuf[k];
+        }
+      }
+      __syncwarp();
+    }
+    nbuf = 0;
+  };
   int const warps_per_block = CELL_THREADS / 32;
   int const gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   int const nwarps = gridDim.x * warps_per_block;
@@ -231,21 +254,16 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
               atomicAdd(&A.g2z[j], Gz);
             }
             unsigned const m = __ballot_sync(0xffffffffu, listed);
-            if (m != 0u && A.pl != nullptr) {
-              unsigned long long base = 0ull;
-              if (lane == 0) base = atomicAdd(A.pl_count, (unsigned long long)__popc(m));
-              base = __shfl_sync(0xffffffffu, base, 0);
-              if (listed) {
-                unsigned long long const slot = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-                if (slot < A.pl_cap) {
-                  A.pl[slot] = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
-                }
-              }
+            if (m != 0u) {
+              if (listed) mybuf[nbuf + __popc(m & ((1u << lane) - 1u))] = j;
+              nbuf += __popc(m);
+              if (nbuf > ROW_BUF - 32) flush_row(i);
             }
           }
         }
       }
     }
+    flush_row(i);
     if (grad) {
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) {
@@ -271,35 +289,7 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
   }
 }
 
-__global__ void list_shuffle_kernel(const unsigned long long *__restrict__ src,
-                                    unsigned long long *__restrict__ dst,
-                                    const unsigned long long *__restrict__ count,
-                                    unsigned long long cap, const int *gate)
-{
-  if (gate != nullptr && *gate != 1) return;
-  unsigned long long n = *count;
-  if (n > cap) n = cap;
-  // a prime above any list length: k -> k * PRIME mod n is a permutation of [0, n).  Measured
-  // on the 50 k-atom case (list-walk step): unshuffled 425 us, 32 x 256 block transpose 407 us,
-  // this permutation 316 us (a list built by the tile sweep: 256 us)
-  constexpr unsigned long long PRIME = 1099511628211ull;
-  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-       k += (unsigned long long)gridDim.x * blockDim.x) {
-    unsigned long long const to = (unsigned long long)(((unsigned __int128)k * PRIME) % n);
-    dst[to] = src[k];
-  }
-}
-
 }  // namespace
-
-int launch_list_shuffle(const unsigned long long *src, unsigned long long *dst,
-                        const unsigned long long *count, unsigned long long cap, const int *gate,
-                        cudaStream_t stream)
-{
-  list_shuffle_kernel<<<1184, 256, 0, stream>>>(src, dst, count, cap, gate);
-  note_launch();
-  return (int)cudaGetLastError();
-}
 
 int cells_setup(CellBuffers &B, int n2)
 {

@@ -75,11 +75,5 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
                 cudaStream_t stream);
 bool cells_periodic_dims(const double cut[3], const double edges[3], int dim[3]);
 int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream);
-// dst[(k * PRIME) mod n] = src[k] for k < n = min(*count, cap): the cell kernel emits runs of
-// entries with the same row, which would make 32 lanes of the list walk add to one gradient
-// address; a multiplicative permutation spreads every run over the whole list
-int launch_list_shuffle(const unsigned long long *src, unsigned long long *dst,
-                        const unsigned long long *count, unsigned long long cap, const int *gate,
-                        cudaStream_t stream);
 
 }  // namespace b200cv

@@ -79,42 +79,87 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
   bool const grad = A.flags & EF_GRADIENTS;
   bool const rebuild = (A.flags & EF_REBUILD_PAIRLIST) && A.pl;
   double fsum = 0.0;
-  for (unsigned long long e = (unsigned long long)blockIdx.x * EXACT_THREADS + threadIdx.x; e < n;
-       e += (unsigned long long)gridDim.x * EXACT_THREADS) {
-    unsigned long long const ent = A.list[e];
-    int const i = (int)(ent >> 32), j = (int)(ent & 0xffffffffu);
-    double const x1 = A.x1[i], y1 = A.y1[i], z1 = A.z1[i];
-    double const x2 = A.x2[j], y2 = A.y2[j], z2 = A.z2[j];
-    double Gx, Gy, Gz, F;
-    bool done = false;
-    if (A.fast_exp == 3) {
-      // pair-list walk, non-periodic, 6/12: the sweep's fast form for every pair that is not
-      // next to a decision threshold (same windows as the sweep), reference order otherwise
-      double const dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
-      double const sx = dx * A.P.inv_r0[0], sy = dy * A.P.inv_r0[1], sz = dz * A.P.inv_r0[2];
-      double const u = fma(sz, sz, fma(sy, sy, sx * sx));
-      if (!pair_is_rare<true>(u, A.P)) {
-        double gq;
-        switching_fast<3, true>(u, false, A.P, F, gq);
-        Gx = A.P.c_grad[0] * gq * dx;
-        Gy = A.P.c_grad[1] * gq * dy;
-        Gz = A.P.c_grad[2] * gq * dz;
-        done = true;
+  // warp-uniform trip count: the group1 gradients of a warp's 32 entries are summed per run of
+  // equal rows before they go to memory (a list rebuilt through the cell list is made of such
+  // runs; 32 lanes adding to one address would serialise, and 3 of the 6 atomics per pair go away)
+  int const lane = threadIdx.x & 31;
+  unsigned long long const first = ((unsigned long long)blockIdx.x * EXACT_THREADS + threadIdx.x) -
+                                   (unsigned long long)lane;
+  for (unsigned long long e0 = first; e0 < n; e0 += (unsigned long long)gridDim.x * EXACT_THREADS) {
+    unsigned long long const e = e0 + (unsigned long long)lane;
+    bool const valid = e < n;
+    int i = -1 - lane, j = 0;
+    double Gx = 0.0, Gy = 0.0, Gz = 0.0, F = 0.0;
+    unsigned long long ent = 0ull;
+    if (valid) {
+      ent = A.list[e];
+      i = (int)(ent >> 32);
+      j = (int)(ent & 0xffffffffu);
+      double const x1 = A.x1[i], y1 = A.y1[i], z1 = A.z1[i];
+      double const x2 = A.x2[j], y2 = A.y2[j], z2 = A.z2[j];
+      bool done = false;
+      if (A.fast_exp == 3) {
+        // 6/12, non-periodic or orthorhombic: the sweep's fast form for every pair that is not
+        // next to a decision threshold (same windows as the sweep), reference order otherwise
+        double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+        if (A.P.bc_type == 2) {
+          double const shx = floor(__dadd_rn(__dmul_rn(A.P.recip[0][0], dx), 0.5));
+          double const shy = floor(__dadd_rn(__dmul_rn(A.P.recip[1][1], dy), 0.5));
+          double const shz = floor(__dadd_rn(__dmul_rn(A.P.recip[2][2], dz), 0.5));
+          dx = fma(-shx, A.P.cell[0][0], dx);
+          dy = fma(-shy, A.P.cell[1][1], dy);
+          dz = fma(-shz, A.P.cell[2][2], dz);
+        }
+        double const sx = dx * A.P.inv_r0[0], sy = dy * A.P.inv_r0[1], sz = dz * A.P.inv_r0[2];
+        double const u = fma(sz, sz, fma(sy, sy, sx * sx));
+        if (!pair_is_rare<true>(u, A.P)) {
+          double gq;
+          switching_fast<3, true>(u, false, A.P, F, gq);
+          Gx = A.P.c_grad[0] * gq * dx;
+          Gy = A.P.c_grad[1] * gq * dy;
+          Gz = A.P.c_grad[2] * gq * dz;
+          done = true;
+        }
       }
+      if (!done) F = pair_exact(A.P, x1, y1, z1, x2, y2, z2, A.flags, Gx, Gy, Gz);
     }
-    if (!done) F = pair_exact(A.P, x1, y1, z1, x2, y2, z2, A.flags, Gx, Gy, Gz);
     fsum += F;
-    if (grad && F > 0.0) {
-      atomicAdd(&A.g1x[i], -Gx);
-      atomicAdd(&A.g1y[i], -Gy);
-      atomicAdd(&A.g1z[i], -Gz);
-      atomicAdd(&A.g2x[j], Gx);
-      atomicAdd(&A.g2y[j], Gy);
-      atomicAdd(&A.g2z[j], Gz);
-    }
-    if (rebuild && F > 0.0) {
+    bool const counts = valid && F > 0.0;
+    if (rebuild && counts) {
       unsigned long long const slot = atomicAdd(A.pl_count, 1ull);
       if (slot < A.pl_cap) A.pl[slot] = ent;
+    }
+    if (grad) {
+      if (counts) {
+        atomicAdd(&A.g2x[j], Gx);
+        atomicAdd(&A.g2y[j], Gy);
+        atomicAdd(&A.g2z[j], Gz);
+      } else {
+        Gx = Gy = Gz = 0.0;
+      }
+      // runs of equal i -> segment numbers -> segmented inclusive scan -> the last lane of a
+      // run holds its sum
+      int const prev = __shfl_up_sync(0xffffffffu, i, 1);
+      unsigned const heads = __ballot_sync(0xffffffffu, lane == 0 || prev != i);
+      int const seg = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        double const px = __shfl_up_sync(0xffffffffu, Gx, d);
+        double const py = __shfl_up_sync(0xffffffffu, Gy, d);
+        double const pz = __shfl_up_sync(0xffffffffu, Gz, d);
+        int const ps = __shfl_up_sync(0xffffffffu, seg, d);
+        if (lane >= d && ps == seg) {
+          Gx += px;
+          Gy += py;
+          Gz += pz;
+        }
+      }
+      bool const tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+      if (tail && valid && (Gx != 0.0 || Gy != 0.0 || Gz != 0.0)) {
+        atomicAdd(&A.g1x[i], -Gx);
+        atomicAdd(&A.g1y[i], -Gy);
+        atomicAdd(&A.g1z[i], -Gz);
+      }
     }
   }
   double const s = block_sum<EXACT_THREADS>(fsum, red);
