@@ -482,7 +482,7 @@ int build_items(b200cv_cvc *h)
     CUDA_OK(h, cudaMemcpy(h->d_items, mine.data(), sizeof(SweepItem) * mine.size(),
                           cudaMemcpyHostToDevice));
   }
-  int rc = ensure_partials(h, std::max(h->nitems, 1) + 2 * EXACT_BLOCKS);
+  int rc = ensure_partials(h, std::max(h->nitems, 1) + PARTIALS_TAIL);
   if (rc) return rc;
   h->items_dirty = false;
   return B200CV_OK;
@@ -630,7 +630,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
 
   if (h->center1() || h->center2()) {
     // COM variants (src/colvarcomp_coordnums.cpp:190-247): O(N) work, reference-order pairs
-    int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
+    int rc = ensure_partials(h, PARTIALS_TAIL);
     if (rc) return rc;
     CenterArgs A{};
     A.P = h->P;
@@ -721,11 +721,11 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.gate_on = 0;
       if (fuse) {
         E.fin_ticket = h->fin_ticket();
-        E.fin = finalize_args(EXACT_BLOCKS);
+        E.fin = finalize_args(WALK_BLOCKS);
         finalized = true;
       }
       E.P = h->P;
-      CUDA_OK(h, launch_exact(E, stream));
+      CUDA_OK(h, launch_exact(E, stream, WALK_BLOCKS));
       h->launches++;
       return B200CV_OK;
     };
@@ -804,7 +804,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     // rebuild of a list that a previous rebuild showed to be sparse: only pairs in neighbouring
     // cells can be within tolerance_l2_max, everything else is exactly zero (cells.cuh)
     auto enqueue_cells = [&](int cell_flags, const int *gate) -> int {
-      static_assert(CELL_BLOCKS <= 2 * EXACT_BLOCKS, "partials are sized for 2 * EXACT_BLOCKS");
+      static_assert(CELL_BLOCKS + WALK_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
       double cut[3];
       cell_cutoffs(h, cut);
       double const edges[3] = {std::fabs(h->P.cell[0][0]), std::fabs(h->P.cell[1][1]),
@@ -850,11 +850,11 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       if (rc) return rc;
       rc = enqueue_walk(h->d_partials + nparts, h->gate());
       if (rc) return rc;
-      npart = nparts + EXACT_BLOCKS;
+      npart = nparts + WALK_BLOCKS;
     } else if (walk_list) {
       int rc = enqueue_walk(h->d_partials, nullptr);
       if (rc) return rc;
-      npart = EXACT_BLOCKS;
+      npart = WALK_BLOCKS;
     } else if (rebuild_with_cells(h, flags)) {
       int rc = enqueue_cells(flags, nullptr);
       if (rc) return rc;
@@ -1393,7 +1393,7 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
       if (rc) return rc;
     }
   } else {
-    int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
+    int rc = ensure_partials(h, PARTIALS_TAIL);
     if (rc) return rc;
   }
   // a rebuild is captured in two forms: all-pairs sweep (first rebuild) and cell list
@@ -1572,7 +1572,7 @@ int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
       int rc = build_items(h);
       if (rc) return rc;
     } else {
-      int rc = ensure_partials(h, 2 * EXACT_BLOCKS);
+      int rc = ensure_partials(h, PARTIALS_TAIL);
       if (rc) return rc;
     }
   }
@@ -1595,7 +1595,7 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
     // no compacted list to size (dense flags of fixed length, or none); still make sure
     // nothing is left to allocate inside a capture
     CUDA_OK(h, cudaSetDevice(h->cfg.device));
-    if (h->center1() || h->center2()) return ensure_partials(h, 2 * EXACT_BLOCKS);
+    if (h->center1() || h->center2()) return ensure_partials(h, PARTIALS_TAIL);
     if (h->items_dirty) return build_items(h);
     return B200CV_OK;
   }

@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
   }
 }
 
-int launch_exact(const ExactArgs &args, cudaStream_t stream)
+int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks)
 {
-  exact_kernel<<<EXACT_BLOCKS, EXACT_THREADS, 0, stream>>>(args);
+  exact_kernel<<<blocks, EXACT_THREADS, 0, stream>>>(args);
   note_launch();
   return (int)cudaGetLastError();
 }

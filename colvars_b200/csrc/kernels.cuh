@@ -60,7 +60,7 @@ struct ExactArgs {
   const unsigned int *count32;         // number of entries (device), or NULL
   const unsigned long long *count64;   // ... 64-bit variant (pair list), or NULL
   unsigned long long cap;              // entries beyond cap were never written
-  double *partials;                    // [EXACT_BLOCKS]
+  double *partials;                    // one per CTA
   unsigned long long *pl;              // pair list to append to on rebuild (or NULL)
   unsigned long long pl_cap;
   unsigned long long *pl_count;
@@ -76,7 +76,12 @@ struct ExactArgs {
 };
 constexpr int EXACT_BLOCKS = 296;
 constexpr int EXACT_THREADS = 128;
-int launch_exact(const ExactArgs &args, cudaStream_t stream);
+// the pair-list walk is a latency-bound gather (6 coordinate loads per entry): it wants every
+// warp slot the register file allows (58 registers -> 8 CTAs per SM)
+constexpr int WALK_BLOCKS = 1184;
+// partial sums behind the sweep items: [rare queue | walk] or [cell kernel (592) | walk]
+constexpr int PARTIALS_TAIL = 2 * WALK_BLOCKS;
+int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks = EXACT_BLOCKS);
 
 // Dense fallback for boundary conditions the tile sweep does not specialise (mixed /
 // triclinic): every pair through pair_exact, gradients by atomics.  self: i < j only.
