@@ -341,6 +341,36 @@ void reset_boundaries(PairParams &P)
   std::memset(P.periodic, 0, sizeof(P.periodic));
   std::memset(P.cell, 0, sizeof(P.cell));
   std::memset(P.recip, 0, sizeof(P.recip));
+  std::memset(P.cell2, 0, sizeof(P.cell2));
+  std::memset(P.tri_n, 0, sizeof(P.tri_n));
+  std::memset(P.tri_shift, 0, sizeof(P.tri_shift));
+  P.tri_margin = 0.0;
+}
+
+// tables of the tile sweep's image search in mixed / triclinic cells (general_image,
+// pair_math.cuh): the 13 shift vectors in the operation order of get_triclinic_shift
+// (src/colvars_system.h:207), their squared lengths, and the decision margin
+void fill_general_cell_tables(PairParams &P)
+{
+  double max_n = 0.0;
+  for (int k = 0; k < 13; k++) {
+    int const ix = tri_dir(k, 0), iy = tri_dir(k, 1), iz = tri_dir(k, 2);
+    bool const allowed = (ix == 0 || P.periodic[0]) && (iy == 0 || P.periodic[1]) &&
+                         (iz == 0 || P.periodic[2]);
+    double n2 = 0.0;
+    for (int d = 0; d < 3; d++) {
+      double const sd = ((double)ix * P.cell[0][d] + (double)iy * P.cell[1][d]) +
+                        (double)iz * P.cell[2][d];
+      P.tri_shift[k][d] = allowed ? sd : 0.0;
+      n2 += sd * sd;
+    }
+    P.tri_n[k] = (allowed && n2 > 0.0) ? n2 : 1.0e300;
+    if (allowed) max_n = std::max(max_n, n2);
+  }
+  for (int a = 0; a < 3; a++) {
+    for (int d = 0; d < 3; d++) P.cell2[a][d] = 2.0 * P.cell[a][d];
+  }
+  P.tri_margin = std::ldexp(max_n, -26);
 }
 
 int alloc_group(b200cv_cvc *h, Group &G, int n)
@@ -702,7 +732,10 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     double *x2 = G2.d_pos, *y2 = G2.d_pos + G2.stride, *z2 = G2.d_pos + 2 * G2.stride;
     double *g1x = G1.d_grad, *g1y = G1.d_grad + G1.stride, *g1z = G1.d_grad + 2 * G1.stride;
     double *g2x = G2.d_grad, *g2y = G2.d_grad + G2.stride, *g2z = G2.d_grad + 2 * G2.stride;
-    bool const general_bc = (h->P.bc_type == 1 || h->P.bc_type == 3);
+    // mixed / triclinic cells: the tile sweep's general image search; B200CV_DENSE=1 keeps the
+    // reference-order dense kernel (one pair per thread) for comparison
+    bool const general_cell = (h->P.bc_type == 1 || h->P.bc_type == 3);
+    bool const general_bc = general_cell && std::getenv("B200CV_DENSE") != nullptr;
     bool const walk_list = use_pl && !rebuild && h->pl_valid;
 
     // non-rebuild step: only listed pairs (src/colvarcomp_coordnums.cpp:219-228)
@@ -771,7 +804,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       S.gate = gate;
       S.gate_on = 1;
       S.P = h->P;
-      int const pbc = h->P.bc_type == 2 ? BC_ORTHO : BC_NONE;
+      int const pbc = h->P.bc_type == 2 ? BC_ORTHO : (general_cell ? BC_GENERAL : BC_NONE);
       CUDA_OK(h, launch_sweep(S, h->nitems, h->exp_special, h->aniso, pbc, use_pl, stream));
       if (h->nitems > 0) h->launches++;
       // pairs next to a decision threshold: reference-order arithmetic (distanceInv has none:
@@ -1295,6 +1328,7 @@ int b200cv_set_boundaries(b200cv_cvc *h, int px, int py, int pz, const double A[
     }
     if (!exact_diag) P.bc_type = 3;
   }
+  if (P.bc_type == 1 || P.bc_type == 3) fill_general_cell_tables(P);
   return B200CV_OK;
 }
 

@@ -48,7 +48,23 @@ struct PairParams {
   int periodic[3];
   double cell[3][3];   // unit_cell_x/y/z
   double recip[3][3];  // reciprocal_cell_x/y/z
+  // general (mixed / triclinic) cells, image search of the tile sweep (general_image below);
+  // filled by b200cv_set_boundaries for bc_type 1 and 3
+  double cell2[3][3];        // 2 * unit cell vectors
+  double tri_n[13];          // |s_k|^2 of the 13 directions TRI_DIRS (1e300: not periodic)
+  double tri_shift[13][3];   // s_k = ix a + iy b + iz c in the reference's operation order
+  double tri_margin;         // image decisions closer than this go to the exact-pair queue
 };
+
+// the 13 lattice directions of get_triclinic_shift (src/colvars_system.h:194-219) up to sign:
+// the 26 neighbouring images are +-s_k
+__host__ __device__ constexpr int tri_dir(int k, int axis)
+{
+  constexpr int D[13][3] = {{1, 0, 0}, {0, 1, 0},  {0, 0, 1},  {1, 1, 0},  {1, -1, 0},
+                            {1, 0, 1}, {1, 0, -1}, {0, 1, 1},  {0, 1, -1}, {1, 1, 1},
+                            {1, 1, -1}, {1, -1, 1}, {1, -1, -1}};
+  return D[k][axis];
+}
 
 // ---- reciprocal --------------------------------------------------------------------
 // MUFU.RCP64H seed (>= 20 good bits, PTX rcp.approx.ftz.f64) + one cubic
@@ -296,6 +312,63 @@ __device__ inline void position_distance_exact(PairParams const &P, double x1, d
     dy = __dadd_rn(dy, ry);
     dz = __dadd_rn(dz, rz);
   }
+}
+
+// position_distance for mixed / triclinic cells on the tile sweep.  Steps 1-2 (fractional
+// rounding, subtraction of the lattice combination) run in the reference's operation order, so
+// the reduced vector is bit-identical to the reference's.  Step 3, get_triclinic_shift
+// (src/colvars_system.h:194-219: the shortest of the 27 neighbouring images, zero shift and
+// then loop order winning ties), is decided on
+//     |d +- s_k|^2 - |d|^2 = |s_k|^2 +- 2 d.s_k ,   min over the sign = |s_k|^2 - |2 d.s_k|
+// for the 13 directions s_k (three dot products, ten sums, thirteen differences, a running
+// minimum that carries k in the four lowest mantissa bits).  The chosen shift is added as the
+// reference adds it (tab[k] holds s_k in the reference's operation order; the sign flip is
+// exact), so the image vector is bit-identical whenever the decision is.  A decision that
+// another candidate -- or the zero shift -- comes within tri_margin (2^-26 of the largest
+// |s_k|^2, nine orders of magnitude above the rounding of either evaluation) of overturning is
+// not taken here: the function returns true and the pair goes to the exact-pair queue, where
+// pair_exact runs the reference's loop.
+// tab: 14 x 3 doubles in shared memory, rows 0..12 = P.tri_shift, row 13 = 0.
+__device__ __forceinline__ bool general_image(PairParams const &P, const double *tab, double &dx,
+                                              double &dy, double &dz)
+{
+  double const xs = floor(__dadd_rn(dot3_exact(P.recip[0], dx, dy, dz), 0.5));
+  double const ys = floor(__dadd_rn(dot3_exact(P.recip[1], dx, dy, dz), 0.5));
+  double const zs = floor(__dadd_rn(dot3_exact(P.recip[2], dx, dy, dz), 0.5));
+  dx = __dsub_rn(dx, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][0]), __dmul_rn(ys, P.cell[1][0])),
+                               __dmul_rn(zs, P.cell[2][0])));
+  dy = __dsub_rn(dy, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][1]), __dmul_rn(ys, P.cell[1][1])),
+                               __dmul_rn(zs, P.cell[2][1])));
+  dz = __dsub_rn(dz, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][2]), __dmul_rn(ys, P.cell[1][2])),
+                               __dmul_rn(zs, P.cell[2][2])));
+  double const pa = fma(dz, P.cell2[0][2], fma(dy, P.cell2[0][1], dx * P.cell2[0][0]));
+  double const pb = fma(dz, P.cell2[1][2], fma(dy, P.cell2[1][1], dx * P.cell2[1][0]));
+  double const pc = fma(dz, P.cell2[2][2], fma(dy, P.cell2[2][1], dx * P.cell2[2][0]));
+  double const pab = pa + pb, pamb = pa - pb;
+  double const q[13] = {pa,      pb,      pc,       pab,      pamb,      pa + pc,  pa - pc,
+                        pb + pc, pb - pc, pab + pc, pab - pc, pamb + pc, pamb - pc};
+  double m[13];
+  double best = __hiloint2double(0x7e37e43c, 0x8800759d);  // 1e300, index bits 13
+#pragma unroll
+  for (int k = 0; k < 13; k++) {
+    double const v = P.tri_n[k] - fabs(q[k]);
+    m[k] = __hiloint2double(__double2hiint(v), (__double2loint(v) & ~15) | k);
+    best = fmin(best, m[k]);
+  }
+  double const thr = best + P.tri_margin;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 13; k++) cnt += (m[k] < thr) ? 1 : 0;
+  bool const shifted = best < P.tri_margin;
+  bool const ambiguous = shifted && (cnt >= 2 || best > -P.tri_margin);
+  int const idx = shifted ? (__double2loint(best) & 15) : 13;
+  double const sx = tab[3 * idx], sy = tab[3 * idx + 1], sz = tab[3 * idx + 2];
+  double const t = fma(dz, sz, fma(dy, sy, dx * sx));
+  double const sgn = t > 0.0 ? -1.0 : 1.0;
+  dx = fma(sgn, sx, dx);
+  dy = fma(sgn, sy, dy);
+  dz = fma(sgn, sz, dz);
+  return ambiguous;
 }
 
 // switching_function<flags> (src/colvarcomp_coordnums.h:168-224)

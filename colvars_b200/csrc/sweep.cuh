@@ -165,10 +165,13 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
                                            const double *__restrict__ sz, double *ax, double *ay,
                                            double *az, const double (&xi)[R], const double (&yi)[R],
                                            const double (&zi)[R], double (&a1x)[R],
-                                           double (&a1y)[R], double (&a1z)[R], double &fsum)
+                                           double (&a1y)[R], double (&a1z)[R], double &fsum,
+                                           const double *__restrict__ tritab)
 {
-  constexpr bool UNDO = (EXP > 0) && !PL && !MASKED;
-  constexpr bool UNDO_PL = (EXP > 0) && PL && !MASKED;
+  // general cells take the select path: an ambiguous image decision is one more reason to
+  // queue a pair, known only per pair
+  constexpr bool UNDO = (EXP > 0) && !PL && !MASKED && (PBC != BC_GENERAL);
+  constexpr bool UNDO_PL = (EXP > 0) && PL && !MASKED && (PBC != BC_GENERAL);
   PairParams const &P = A.P;
   double b2x = 0.0, b2y = 0.0, b2z = 0.0;
   unsigned plm[R];
@@ -288,10 +291,13 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
         double dx = xj - xi[k];
         double dy = yj - yi[k];
         double dz = zj - zi[k];
-        double const u = pair_l2<ANISO, PBC, (EXP < 0)>(P, dx, dy, dz);
+        bool ambiguous = false;
+        if constexpr (PBC == BC_GENERAL) ambiguous = general_image(P, tritab, dx, dy, dz);
+        double const u =
+            pair_l2<ANISO, (PBC == BC_GENERAL ? BC_NONE : PBC), (EXP < 0)>(P, dx, dy, dz);
         // branch-free: a rare pair contributes nothing here and is remembered in a mask, so
         // that the R pairs of this step stay one basic block for the instruction scheduler
-        bool rare = (EXP < 0) ? false : pair_is_rare<PL>(u, P);
+        bool rare = ((EXP < 0) ? false : pair_is_rare<PL>(u, P)) || ambiguous;
         bool off = rare;
         if constexpr (MASKED) {
           int const iglob = ibase + k * 32;
@@ -398,6 +404,13 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
   double *az = ay + JCMAX;
   __shared__ __align__(8) uint64_t mbar;
   __shared__ double red[W];
+  // general cells: the 13 image shifts (+ a zero row), indexed per lane (general_image)
+  __shared__ double tritab[PBC == BC_GENERAL ? 42 : 1];
+  if constexpr (PBC == BC_GENERAL) {
+    if (threadIdx.x < 42) {
+      tritab[threadIdx.x] = threadIdx.x < 39 ? A.P.tri_shift[threadIdx.x / 3][threadIdx.x % 3] : 0.0;
+    }
+  }
 
   if constexpr (PL) {
     if (A.gate != nullptr && *A.gate != A.gate_on) {
@@ -475,10 +488,10 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
                         (item.diag && (jt0 < iw1));
     if (masked) {
       sweep_tile<EXP, ANISO, PBC, PL, R, true>(A, item, tile, lane, ibase, sx, sy, sz, ax, ay, az,
-                                                xi, yi, zi, a1x, a1y, a1z, fsum);
+                                                xi, yi, zi, a1x, a1y, a1z, fsum, tritab);
     } else {
       sweep_tile<EXP, ANISO, PBC, PL, R, false>(A, item, tile, lane, ibase, sx, sy, sz, ax, ay,
-                                                 az, xi, yi, zi, a1x, a1y, a1z, fsum);
+                                                 az, xi, yi, zi, a1x, a1y, a1z, fsum, tritab);
     }
   }
 

@@ -37,8 +37,20 @@ static int launch_sweep_ea(const SweepArgs &a, int n, int pbc, bool pl, cudaStre
     return pl ? launch_sweep_t<EXP, ANISO, BC_NONE, true>(a, n, s)
               : launch_sweep_t<EXP, ANISO, BC_NONE, false>(a, n, s);
   }
-  return pl ? launch_sweep_t<EXP, ANISO, BC_ORTHO, true>(a, n, s)
-            : launch_sweep_t<EXP, ANISO, BC_ORTHO, false>(a, n, s);
+  if (pbc == BC_ORTHO) {
+    return pl ? launch_sweep_t<EXP, ANISO, BC_ORTHO, true>(a, n, s)
+              : launch_sweep_t<EXP, ANISO, BC_ORTHO, false>(a, n, s);
+  }
+  return pl ? launch_sweep_t<EXP, ANISO, BC_GENERAL, true>(a, n, s)
+            : launch_sweep_t<EXP, ANISO, BC_GENERAL, false>(a, n, s);
+}
+
+template <int EXP>
+static int launch_sweep_dinv(const SweepArgs &a, int n, int pbc, cudaStream_t s)
+{
+  if (pbc == BC_NONE) return launch_sweep_t<EXP, false, BC_NONE, false>(a, n, s);
+  if (pbc == BC_ORTHO) return launch_sweep_t<EXP, false, BC_ORTHO, false>(a, n, s);
+  return launch_sweep_t<EXP, false, BC_GENERAL, false>(a, n, s);
 }
 
 int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso, int pbc,
@@ -47,12 +59,8 @@ int launch_sweep(const SweepArgs &args, int nitems, int exp_special, bool aniso,
   if (nitems <= 0) return 0;
   if (exp_special < 0) {
     // distanceInv: exponent 6 (the default) compiled in, any other even exponent at run time
-    if (exp_special == -3) {
-      return pbc == BC_NONE ? launch_sweep_t<-3, false, BC_NONE, false>(args, nitems, stream)
-                            : launch_sweep_t<-3, false, BC_ORTHO, false>(args, nitems, stream);
-    }
-    return pbc == BC_NONE ? launch_sweep_t<-1, false, BC_NONE, false>(args, nitems, stream)
-                          : launch_sweep_t<-1, false, BC_ORTHO, false>(args, nitems, stream);
+    if (exp_special == -3) return launch_sweep_dinv<-3>(args, nitems, pbc, stream);
+    return launch_sweep_dinv<-1>(args, nitems, pbc, stream);
   }
   if (exp_special == 3) {
     return aniso ? launch_sweep_ea<3, true>(args, nitems, pbc, pairlist, stream)

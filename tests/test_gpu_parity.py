@@ -923,3 +923,129 @@ def test_sparse_pairlist_rebuild_through_the_cell_list_periodic(kind):
     assert cv.last_stats()[0] < 6
     close_val(v, ov)
     close_arr(cv.gradients(1), og1)
+
+
+# ---- mixed / triclinic cells on the tile sweep (src/colvars_system.h:161-219) ----------------
+
+_SQ2, _SQ6 = np.sqrt(2.0), np.sqrt(6.0)
+GENERAL_CELLS = {
+    # GROMACS rhombic dodecahedron and truncated octahedron as triclinic cells: strongly skewed,
+    # a large share of the reduced vectors has a shorter neighbouring image
+    "dodecahedron": ((1, 1, 1), (1.0, 0, 0), (0, 1.0, 0), (0.5, 0.5, 0.5 * _SQ2)),
+    "octahedron": ((1, 1, 1), (1.0, 0, 0), (1 / 3, 2 * _SQ2 / 3, 0), (-1 / 3, _SQ2 / 3, _SQ6 / 3)),
+    "skewed": ((1, 1, 1), (1.0, 0, 0), (0.45, 0.9, 0), (-0.4, 0.42, 0.8)),
+    # two periodic axes, the second one off-diagonal: type "mixed", where the reference leaves
+    # the reciprocal vectors of off-diagonal axes at zero and relies on the image search alone
+    "mixed-skewed": ((1, 1, 0), (1.0, 0, 0), (0.4, 1.0, 0), (0, 0, 1.0)),
+    "mixed-z": ((0, 0, 1), (1.0, 0, 0), (0, 1.0, 0), (0, 0, 1.0)),
+}
+
+
+def _scaled_cell(name, L):
+    per, A, B, Cc = GENERAL_CELLS[name]
+    return per, tuple(L * np.array(A)), tuple(L * np.array(B)), tuple(L * np.array(Cc))
+
+
+@pytest.mark.parametrize("cell", list(GENERAL_CELLS))
+@pytest.mark.parametrize("kind,tol", [("coordNum", 0.0), ("selfCoordNum", 0.0),
+                                      ("coordNum", 0.01), ("selfCoordNum", 0.001)])
+def test_general_cells_through_the_tile_sweep(cell, kind, tol):
+    """Values, gradients and pair lists in mixed / triclinic cells (image search of the sweep,
+    general_image) against the oracle's reference-order position_distance; atoms up to two
+    cells outside the unit cell."""
+    cb = _cb()
+    L = 21.0
+    per, A, B, Cc = _scaled_cell(cell, L)
+    n1, n2 = (300, 2100) if kind == "coordNum" else (1100, 0)
+    rng = np.random.default_rng(97)
+    frac = rng.random((n1 + n2, 3)) * 4.0 - 2.0
+    proxy = np.ascontiguousarray(frac @ np.array([A, B, Cc]))
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    cv = cb.CoordNum(kind, i1, i2 if kind == "coordNum" else None, cutoff3=(4.0, 5.0, 3.5),
+                     tolerance=tol, pairlist_freq=2)
+    cv.set_boundaries(per, A, B, Cc)
+    p = O.make_params((4.0, 5.0, 3.5), 6, 12, tol, boundaries=(per, A, B, Cc))
+    npairs = n1 * n2 if kind == "coordNum" else n1 * (n1 - 1) // 2
+    pl = np.ones(npairs, dtype=np.uint8) if tol > 0 else None
+    for step in range(3):
+        frame = np.ascontiguousarray(proxy + rng.normal(0, 0.04, proxy.shape) * step)
+        v = cv.calc_host(frame, step=step)
+        rebuild = tol > 0 and step % 2 == 0
+        if kind == "coordNum":
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(cv.gradients(2), og2)
+        else:
+            ov, og1 = O.selfcoordnum(p, frame, pairlist=pl, rebuild=rebuild)
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        if tol > 0:
+            assert np.array_equal(cv.pairlist(), np.flatnonzero(pl).astype(np.uint64))
+
+
+def test_general_cell_image_ties_follow_the_reference():
+    """Pairs whose reduced vector lies on (or an ulp or two beside) a plane where two images are
+    equally long: the reference keeps the zero shift, then the first candidate in loop order.
+    A wrong image flips the sign of the pair's gradient, so the gradients tell."""
+    cb = _cb()
+    L = 16.0
+    per, A, B, Cc = _scaled_cell("skewed", L)
+    lat = np.array([A, B, Cc])
+    dirs = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, -1, 0), (1, 0, 1), (1, 0, -1),
+            (0, 1, 1), (0, 1, -1), (1, 1, 1), (1, 1, -1), (1, -1, 1), (1, -1, -1)]
+    rng = np.random.default_rng(5)
+    p1, p2 = [], []
+    for d in dirs:
+        s = np.array(d, dtype=float) @ lat
+        for sign in (1.0, -1.0):
+            for ulps in (-2, -1, 0, 1, 2):
+                # half a lattice vector plus a component inside the bisector plane
+                t = rng.normal(size=3)
+                t -= s * (t @ s) / (s @ s)
+                t *= 0.8 / np.linalg.norm(t)
+                base = rng.random(3) * L
+                vec = sign * 0.5 * s * (1.0 + ulps * 2.0 ** -52) + t
+                p1.append(base)
+                p2.append(base + vec)
+    p1, p2 = np.array(p1), np.array(p2)
+    n = len(p1)
+    proxy = np.ascontiguousarray(np.concatenate([p1, p2]))
+    i1 = np.arange(n, dtype=np.int32)
+    i2 = i1 + n
+    # a cut-off of the order of the cell, so that the half-lattice pairs weigh in
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=9.0)
+    cv.set_boundaries(per, A, B, Cc)
+    v = cv.calc_host(proxy)
+    p = O.make_params((9.0,) * 3, boundaries=(per, A, B, Cc))
+    ov, og1, og2 = O.coordnum(p, p1, p2)
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
+    close_arr(cv.gradients(2), og2)
+
+
+def test_general_cell_sweep_equals_the_dense_reference_order_kernel(monkeypatch):
+    """B200CV_DENSE=1 keeps the one-pair-per-thread kernel that runs the reference's loop for
+    every pair: same value and gradients as the sweep's image search, on a full tile grid."""
+    cb = _cb()
+    L = 40.0
+    per, A, B, Cc = _scaled_cell("octahedron", L)
+    n1, n2 = 1500, 5000
+    rng = np.random.default_rng(3)
+    proxy = np.ascontiguousarray((rng.random((n1 + n2, 3)) * 3.0 - 1.0) @ np.array([A, B, Cc]))
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    out = []
+    for dense in (False, True):
+        if dense:
+            monkeypatch.setenv("B200CV_DENSE", "1")
+        else:
+            monkeypatch.delenv("B200CV_DENSE", raising=False)
+        cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
+        cv.set_boundaries(per, A, B, Cc)
+        v = cv.calc_host(proxy)
+        out.append((v, cv.gradients(1).copy(), cv.gradients(2).copy(), cv.last_stats()))
+        cv.close()
+    (vs, g1s, g2s, st_s), (vd, g1d, g2d, st_d) = out
+    close_val(vs, vd)
+    close_arr(g1s, g1d)
+    close_arr(g2s, g2d)

@@ -33,12 +33,16 @@ cells = {
     "ortho": ((1, 1, 1), (L, 0, 0), (0, L, 0), (0, 0, L)),
     "triclinic": ((1, 1, 1), (L, 0, 0), (0.3 * L, 0.95 * L, 0), (-0.2 * L, 0.25 * L, 0.9 * L)),
     "mixed-xy": ((1, 1, 0), (L, 0, 0), (0, L, 0), (0, 0, L)),
+    "dodecahedron": ((1, 1, 1), (L, 0, 0), (0, L, 0), (0.5 * L, 0.5 * L, 0.5 * 2 ** 0.5 * L)),
 }
+import os
+if len(sys.argv) > 3 and sys.argv[3] == "dense":
+    os.environ["B200CV_DENSE"] = "1"  # the one-pair-per-thread reference-order kernel
 for name, c in cells.items():
     cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0)
     if c is not None:
         cv.set_boundaries(*c)
     t = time_calc(cv, d_pos)
-    print(f"{name:10s} {n1} x {n2}: {t:10.1f} us  {n1 * n2 / t / 1e6:8.2f} Gpair/s  "
+    print(f"{name:10s} {n1} x {n2}: {t:10.1f} us  {n1 * n2 / t / 1e3:8.2f} Gpair/s  "
           f"value {cv.value():.12e}", flush=True)
     cv.close()
