@@ -844,7 +844,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
                                std::fabs(h->P.cell[2][2])};
       CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut,
                              h->P.bc_type == 2 ? edges : nullptr, gate, stream));
-      h->launches += 4;
+      h->launches += 5;
       CellPairArgs C{};
       C.x1 = x1; C.y1 = y1; C.z1 = z1; C.x2 = x2; C.y2 = y2; C.z2 = z2;
       C.g1x = g1x; C.g1y = g1y; C.g1z = g1z; C.g2x = g2x; C.g2y = g2y; C.g2z = g2z;
@@ -853,6 +853,9 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.i_begin = (int)((long long)G1.n * h->rank / h->world);
       C.i_end = (int)((long long)G1.n * (h->rank + 1) / h->world);
       C.sorted2 = h->cells.d_sorted;
+      C.xs = h->cells.d_xs;
+      C.ys = h->cells.d_ys;
+      C.zs = h->cells.d_zs;
       C.cell_start = h->cells.d_cell_start;
       C.grid = h->cells.d_grid;
       C.pl = h->d_pl;

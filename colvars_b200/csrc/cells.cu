@@ -134,6 +134,21 @@ __global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
   cell_start[c] = lo;
 }
 
+// coordinates in cell order: the pair kernel's candidate loads become contiguous
+__global__ void cell_gather_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                   const double *__restrict__ z, const int *__restrict__ sorted,
+                                   int n, double *__restrict__ xs, double *__restrict__ ys,
+                                   double *__restrict__ zs, const int *gate)
+{
+  int const p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (gate != nullptr && *gate != 1) return;
+  int const j = sorted[p];
+  xs[p] = x[j];
+  ys[p] = y[j];
+  zs[p] = z[j];
+}
+
 // ---- candidate pairs: one warp per group1 row, lanes over the atoms of the 3 x 3 x-spans of
 // neighbouring cells (cells adjacent in x are contiguous in key order) -------------------------
 __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
@@ -173,7 +188,11 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
   int const nwarps = gridDim.x * warps_per_block;
   bool const grad = A.flags & EF_GRADIENTS;
   double fsum = 0.0;
-  for (int i = A.i_begin + gwarp; i < A.i_end; i += nwarps) {
+  // selfCoordNum: rows in cell order as well (row q of the sorted atoms; any disjoint split of
+  // the rows over warps and ranks lists every pair once), so that the warps of a CTA work on
+  // neighbouring cells and share their candidates' cache lines
+  for (int q = A.i_begin + gwarp; q < A.i_end; q += nwarps) {
+    int const i = A.self ? A.sorted2[q] : q;
     double const xi = A.x1[i], yi = A.y1[i], zi = A.z1[i];
     bool const per = g.periodic != 0;
     int const cx = per ? cell_coord_periodic(xi, g.inv_len[0], g.dim[0])
@@ -212,7 +231,7 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
             if (p < end) {
               j = A.sorted2[p];
               if (!A.self || j > i) {
-                double const xj = A.x2[j], yj = A.y2[j], zj = A.z2[j];
+                double const xj = A.xs[p], yj = A.ys[p], zj = A.zs[p];
                 bool done = false;
                 if (A.fast_exp == 3) {
                   // 6/12: the sweep's fast form for every pair that is not next to a decision
@@ -303,6 +322,10 @@ int cells_setup(CellBuffers &B, int n2)
   if ((e = cudaMalloc(&B.d_key_sorted, nb)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_val, nb)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_sorted, nb)) != cudaSuccess) return (int)e;
+  size_t const nbd = sizeof(double) * (size_t)std::max(n2, 1);
+  if ((e = cudaMalloc(&B.d_xs, nbd)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_ys, nbd)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_zs, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_cell_start, sizeof(int) * ((size_t)CELL_MAX + 2))) != cudaSuccess) {
     return (int)e;
   }
@@ -321,6 +344,9 @@ void cells_free(CellBuffers &B)
   cudaFree(B.d_key_sorted);
   cudaFree(B.d_val);
   cudaFree(B.d_sorted);
+  cudaFree(B.d_xs);
+  cudaFree(B.d_ys);
+  cudaFree(B.d_zs);
   cudaFree(B.d_cell_start);
   cudaFree(B.d_temp);
   B = CellBuffers();
@@ -370,6 +396,9 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
   note_launch();
   cell_start_kernel<<<(CELL_MAX + 1 + 255) / 256, 256, 0, stream>>>(B.d_key_sorted, n2, B.d_grid,
                                                                    B.d_cell_start, gate);
+  note_launch();
+  cell_gather_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, B.d_sorted, n2, B.d_xs,
+                                                           B.d_ys, B.d_zs, gate);
   note_launch();
   return (int)cudaGetLastError();
 }

@@ -37,6 +37,7 @@ struct CellBuffers {
   int *d_key = nullptr, *d_key_sorted = nullptr;  // cell id per group2 atom
   int *d_val = nullptr, *d_sorted = nullptr;      // atom index, sorted by cell
   int *d_cell_start = nullptr;                    // [CELL_MAX + 1]
+  double *d_xs = nullptr, *d_ys = nullptr, *d_zs = nullptr;  // group2 coordinates in cell order
   void *d_temp = nullptr;                         // radix-sort scratch
   size_t temp_bytes = 0;
   int n2 = 0;
@@ -50,6 +51,7 @@ struct CellPairArgs {
   int n2, self;
   int i_begin, i_end;  // group1 rows of this rank
   const int *sorted2;
+  const double *xs, *ys, *zs;  // group2 coordinates in cell order: xs[p] = x2[sorted2[p]]
   const int *cell_start;
   const CellGrid *grid;
   unsigned long long *pl;

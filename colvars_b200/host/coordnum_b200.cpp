@@ -34,6 +34,7 @@ struct component_registry : public colvar {
     global_cvc_map["selfCoordNum"] = []() -> colvar::cvc * { return new selfcoordnum_b200(); };
     global_cvc_map["groupCoord"] = []() -> colvar::cvc * { return new groupcoordnum_b200(); };
     global_cvc_map["distanceInv"] = []() -> colvar::cvc * { return new distanceinv_b200(); };
+    global_cvc_map["hBond"] = []() -> colvar::cvc * { return new hbond_b200(); };
   }
 };
 
@@ -227,6 +228,102 @@ int distanceinv_b200::init(std::string const &conf)
   cfg.device = 0;
   return error_code | create_engine(cfg);
 }
+
+// ---- hBond (src/colvarcomp_coordnums.cpp:323-469) -------------------------------------------
+
+hbond_b200::hbond_b200() : coordnum_b200("hBond")
+{
+  cvm::real const r0 = cvmodule->proxy->angstrom_to_internal(3.3);
+  r0_vec = cvm::rvector(r0, r0, r0);
+  en = 6;
+  ed = 8;
+  init_scalar_boundaries(0.0, 1.0);
+}
+
+int hbond_b200::init(std::string const &conf)
+{
+  int error_code = cvc::init(conf);
+  set_function_type("hBond");
+  x.type(colvarvalue::type_scalar);
+  init_scalar_boundaries(0.0, 1.0);
+
+  int a_num = -1, d_num = -1;
+  get_keyval(conf, "acceptor", a_num, a_num);
+  get_keyval(conf, "donor", d_num, a_num);  // the reference's default, src/...coordnums.cpp:349
+  if ((a_num == -1) || (d_num == -1)) {
+    return error_code |
+           cvmodule->error("Error: either acceptor or donor undefined.\n", COLVARS_INPUT_ERROR);
+  }
+  register_atom_group(new cvm::atom_group);
+  {
+    colvarproxy *const p = cvmodule->proxy;
+    auto modify_atom = atom_groups[0]->get_atom_modifier();
+    modify_atom.add_atom(cvm::atom_group::init_atom_from_proxy(p, a_num));
+    modify_atom.add_atom(cvm::atom_group::init_atom_from_proxy(p, d_num));
+  }
+  group1 = atom_groups[0];  // acceptor = row, donor = column of the 1 x 1 problem
+  num_pairs = 1;
+
+  cvm::real r0 = r0_vec[0];
+  if (get_keyval(conf, "cutoff", r0, r0)) r0_vec = cvm::rvector(r0, r0, r0);
+  get_keyval(conf, "expNumer", en, en);
+  get_keyval(conf, "expDenom", ed, ed);
+  if (error_code != COLVARS_OK) return error_code;
+
+  // odd / non-positive exponents are rejected behind the C ABI with the reference's messages
+  b200cv_config cfg;
+  b200cv_config_defaults(&cfg);
+  cfg.kind = B200CV_COORDNUM;
+  cfg.n1 = 1;
+  cfg.n2 = 1;
+  cfg.cutoff3[0] = r0_vec.x;
+  cfg.cutoff3[1] = r0_vec.y;
+  cfg.cutoff3[2] = r0_vec.z;
+  cfg.exp_numer = en;
+  cfg.exp_denom = ed;
+  cfg.device = 0;
+  int rc = b200cv_create(&cfg, &engine);
+  if (rc != B200CV_OK) {
+    return error_code | cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
+  }
+  int const id1 = group1->id(0), id2 = group1->id(1);
+  double const m1 = group1->mass(0), m2 = group1->mass(1);
+  rc = b200cv_set_group(engine, 1, &id1, &m1, 1);
+  if (rc == B200CV_OK) rc = b200cv_set_group(engine, 2, &id2, &m2, 1);
+  if (rc != B200CV_OK) return error_code | b200_error(rc);
+  return error_code;
+}
+
+void hbond_b200::evaluate(int flags)
+{
+  static_cast<boundaries_view const &>(boundary_conditions).push(engine);
+  cvm::atom_group *g = atom_groups[0];
+  double const p1[3] = {g->pos_x(0), g->pos_y(0), g->pos_z(0)};
+  double const p2[3] = {g->pos_x(1), g->pos_y(1), g->pos_z(1)};
+  double g1[3] = {0.0, 0.0, 0.0}, g2[3] = {0.0, 0.0, 0.0};
+  double value = 0.0;
+  int const rc = b200cv_eval_host(engine, p1, p2, flags, g1, g2, &value);
+  if (rc != B200CV_OK) {
+    b200_error(rc);
+    return;
+  }
+  if (flags & B200CV_EF_GRADIENTS) {
+    g->grad_x(0) += g1[0];
+    g->grad_y(0) += g1[1];
+    g->grad_z(0) += g1[2];
+    g->grad_x(1) += g2[0];
+    g->grad_y(1) += g2[1];
+    g->grad_z(1) += g2[2];
+  } else {
+    x.real_value = value;
+  }
+}
+
+// value without gradients, then the gradients by a second evaluation whose value is dropped
+// (src/colvarcomp_coordnums.cpp:404-469)
+void hbond_b200::calc_value() { evaluate(B200CV_EF_NULL); }
+
+void hbond_b200::calc_gradients() { evaluate(B200CV_EF_GRADIENTS); }
 
 void coordnum_b200::calc_value()
 {

@@ -90,4 +90,24 @@ protected:
   int exponent = 6;
 };
 
+/// colvar::h_bond, "hBond" (src/colvarcomp_coordnums.h:147-166, .cpp:323-469): ONE
+/// acceptor-donor pair through the same pair function (cutoff 3.3 A, exponents 6 / 8 by
+/// default), both atoms in one atom group; value in calc_value(), gradients in
+/// calc_gradients(), as the reference splits them.  Keywords acceptor, donor, cutoff,
+/// expNumer, expDenom.  A single pair has nothing to put on a graph: under `smp gpu` it takes
+/// the reference's CPU-buffer route.
+class hbond_b200 : public coordnum_b200 {
+public:
+  hbond_b200();
+  int init(std::string const &conf) override;
+  void calc_value() override;
+  void calc_gradients() override;
+#if defined(COLVARS_CUDA)
+  bool has_gpu_implementation() const override { return false; }
+#endif
+
+private:
+  void evaluate(int flags);
+};
+
 #endif

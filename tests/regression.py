@@ -31,8 +31,8 @@ CASES = [
 
 # colvar::h_bond (src/colvarcomp_coordnums.cpp:323-469): ONE pair through compute_pair_coordnum
 # (acceptor = first atom, donor = second, r0 = 3.3, 6/8 by default).  Its golden pins the pair
-# function with general exponents; it is evaluated as a 1 x 1 coordNum here.  Not part of
-# CASES: the host shim leaves "hBond" to the reference (nothing to accelerate in one pair).
+# function with general exponents; it is evaluated as a 1 x 1 coordNum behind the C ABI
+# (hbond_b200 in the host shim).
 PAIR_CASES = ["hbond"]
 
 KIND = {"coordNum": 0, "selfCoordNum": 1, "groupCoord": 2, "distanceInv": 3}

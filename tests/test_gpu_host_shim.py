@@ -33,7 +33,7 @@ EXTRA_CASES = sorted(p.name[:-len("_harmonic-fixed")] for p in EXTRA.glob("*_har
 
 
 @pytest.mark.parametrize("route", ["cpu-proxy", "smp-gpu"])
-@pytest.mark.parametrize("case", R.CASES + ["extra:" + c for c in EXTRA_CASES])
+@pytest.mark.parametrize("case", R.CASES + R.PAIR_CASES + ["extra:" + c for c in EXTRA_CASES])
 def test_reference_host_with_b200_components(case, route, tmp_path):
     """route = cpu-proxy: CPU proxy arrays, components call b200cv_eval_host.
     route = smp-gpu: the reference built with COLVARS_CUDA, device-resident proxy, the
@@ -90,7 +90,8 @@ def test_reference_host_with_b200_components(case, route, tmp_path):
         assert "atom-group kernels: b200" in r.stdout
         assert "optimal-rotation kernels: b200" in r.stdout
         on_graph = "graph route: yes" in r.stdout
-        assert on_graph == ("dummy" not in case), r.stdout[-500:]
+        # one acceptor-donor pair (hBond) and a dummy-atom group2 stay on the CPU-buffer route
+        assert on_graph == ("dummy" not in case and case != "hbond"), r.stdout[-500:]
 
 
 @pytest.mark.parametrize("case", ["coordnum", "selfcoordnum-pairlist", "coordnum-aniso"])
