@@ -59,6 +59,12 @@ WORKLOADS = {
                  freq=100, exponent=6, flop_per_pair=synth.FLOP_PER_PAIR_DISTANCEINV,
                  name="distanceInv 10k x 500k exponent=6"),
 }
+# the same pair sweep in a triclinic cell (GROMACS rhombic
+# dodecahedron of the solvent cube's edge), image search of the 27 neighbours per pair
+WORKLOADS["tric"] = dict(kind="coordNum", n1=10000, n2=100000, cutoff3=(4.0, 4.0, 4.0), tol=0.0,
+                         freq=100, cell="dodecahedron",
+                         name="coordNum 10k x 100k iso r0=4 n=6 m=12 in a rhombic-dodecahedron "
+                              "(triclinic) cell")
 METRIC = "coordNum pair-evals/sec (value+grad)"
 UNIT = "pair-evals/s"
 
@@ -263,6 +269,9 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     dev = torch.device("cuda", device)
     cv = cb.CoordNum(w["kind"], i1, i2, cutoff3=w["cutoff3"], tolerance=w["tol"],
                      pairlist_freq=w["freq"], device=device, exponent=w.get("exponent"))
+    if w.get("cell") == "dodecahedron":
+        L = synth.box_length(w["n2"])
+        cv.set_boundaries((1, 1, 1), (L, 0, 0), (0, L, 0), (0.5 * L, 0.5 * L, 0.5 * 2 ** 0.5 * L))
     fitted = bool(w.get("fit"))
     if fitted:
         ref = proxy[i1].copy()
@@ -339,7 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5",
-                    choices=sorted(k for k in WORKLOADS if k != "dinv"))
+                    choices=sorted(k for k in WORKLOADS if k not in ("dinv", "tric")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
@@ -553,7 +562,7 @@ def main():
         # the other single-GPU configurations of BASELINE.json, device-resident step only
         # (same timing rules; not the headline): BASELINE config 2 is the 1-GPU case
         others = {}
-        for key in ("c2", "c4", "c3", "dinv"):
+        for key in ("c2", "c4", "c3", "dinv", "tric"):
             try:
                 others[key] = quick_workload(cb, torch, key, local_rank, fp64_tflops)
             except Exception as e:
