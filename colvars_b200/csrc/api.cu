@@ -134,6 +134,9 @@ struct b200cv_cvc {
   unsigned long long pl_cap = 0;
   unsigned long long pl_n = 0;  // entries of the current list
   bool pl_valid = false;        // a rebuild has happened
+  // entries of the current list are in cell order (built by the cell kernel with
+  // sorted_entries): the walk runs on the cell-ordered copies (cells.cuh, launch_cell_gather)
+  bool pl_sorted = false;
   unsigned char *d_pl_center = nullptr;  // dense flags for the centre-only variants
 
   // cell-list rebuild of the pair list (cells.cuh); used once a rebuild has shown the list to
@@ -564,6 +567,9 @@ int centers_after_read(b200cv_cvc *h, Group &G, cudaStream_t s)
     if (rc_ != B200CV_OK) return rc_; \
   } while (0)
 
+// lists built by the cell kernel are kept, and walked, in cell order (cells.cuh)
+bool sorted_walk_enabled() { return std::getenv("B200CV_NO_SORTED_WALK") == nullptr; }
+
 // the last rebuild listed fewer than 2 % of this rank's pairs
 bool sparse_list(const b200cv_cvc *h)
 {
@@ -744,6 +750,20 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       ExactArgs E{};
       E.x1 = x1; E.y1 = y1; E.z1 = z1; E.x2 = x2; E.y2 = y2; E.z2 = z2;
       E.g1x = g1x; E.g1y = g1y; E.g1z = g1z; E.g2x = g2x; E.g2y = g2y; E.g2z = g2z;
+      if (h->pl_sorted) {
+        // list in cell order: walk the cell-ordered copy of group2 (positions refreshed in the
+        // order of the last rebuild), gradients go back through the same order afterwards
+        CellBuffers &B = h->cells;
+        CUDA_OK(h, launch_cell_gather(B, x2, y2, z2, G2.n, gate, 0, stream));
+        CUDA_OK(h, cudaMemsetAsync(B.d_gs, 0, sizeof(double) * 3 * (size_t)G2.n, stream));
+        h->launches++;
+        E.x2 = B.d_xs; E.y2 = B.d_ys; E.z2 = B.d_zs;
+        E.g2x = B.d_gs; E.g2y = B.d_gs + G2.n; E.g2z = B.d_gs + 2 * (size_t)G2.n;
+        if (h->self()) {
+          E.x1 = E.x2; E.y1 = E.y2; E.z1 = E.z2;
+          E.g1x = E.g2x; E.g1y = E.g2y; E.g1z = E.g2z;
+        }
+      }
       E.list = h->d_pl;
       E.count64 = h->pl_count() + 1;  // persistent copy of the list length
       E.cap = h->pl_cap;
@@ -760,12 +780,17 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.P = h->P;
       CUDA_OK(h, launch_exact(E, stream, WALK_BLOCKS));
       h->launches++;
+      if (h->pl_sorted && grad) {
+        CUDA_OK(h, launch_cell_scatter_add(h->cells, g2x, g2y, g2z, G2.n, gate, 0, stream));
+        h->launches++;
+      }
       return B200CV_OK;
     };
     // every pair: tile sweep (+ exact-pair queue) or, for mixed / triclinic cells, the dense
     // kernel; records the pair list when `record`.  Returns the number of partial sums.
     auto enqueue_all_pairs = [&](int sweep_flags, bool record, const int *gate,
                                  int &nparts) -> int {
+      if (record) h->pl_sorted = false;  // the sweep and the dense kernel list (i, j) as they are
       if (general_bc) {
         DenseArgs D{};
         D.x1 = x1; D.y1 = y1; D.z1 = z1; D.x2 = x2; D.y2 = y2; D.z2 = z2;
@@ -864,6 +889,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.partials = h->d_partials;
       C.flags = cell_flags;
       C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // bc_type is 0 or 2 here, both have a fast form
+      h->pl_sorted = sorted_walk_enabled();
+      C.sorted_entries = h->pl_sorted ? 1 : 0;
       C.gate = gate;
       C.P = h->P;
       CUDA_OK(h, launch_cell_pairs(C, stream));
@@ -1434,7 +1461,12 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
     if (rc) return rc;
   }
   // a rebuild is captured in two forms: all-pairs sweep (first rebuild) and cell list
-  int const graph_key = flags | (rebuild_with_cells(h, flags) ? (1 << 30) : 0);
+  // (the host does not run enqueue_calc on a replay: what it would have noted -- the index
+  // space of the list a rebuild leaves behind -- is noted below), a list walk in two as well:
+  // entries as atom indices or in cell order
+  bool const cells_rebuild = rebuild_with_cells(h, flags);
+  int graph_key = flags | (cells_rebuild ? (1 << 30) : 0);
+  if (use_pl && !rebuild && h->pl_sorted) graph_key |= (1 << 29);
   b200cv_cvc::StepGraph *hit = nullptr;
   for (auto &g : h->step_graphs) {
     if (g.flags == graph_key && g.pos == d_proxy_pos && g.stride == proxy_stride &&
@@ -1474,6 +1506,9 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
     (void)nodes;
   }
   CUDA_OK(h, cudaGraphLaunch(hit->exec, user));
+  if (use_pl && rebuild && !(h->center1() || h->center2())) {
+    h->pl_sorted = cells_rebuild && sorted_walk_enabled();
+  }
   h->launches = hit->launches;
   h->async_eval = false;
   h->gated = false;
@@ -1966,8 +2001,19 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
   std::vector<unsigned long long> ent(count);
   CUDA_OK(h, cudaMemcpy(ent.data(), h->d_pl, sizeof(unsigned long long) * count,
                         cudaMemcpyDeviceToHost));
+  std::vector<int> order;
+  if (h->pl_sorted) {
+    // entries in cell order: back to atom indices through the order of the last rebuild
+    order.resize((size_t)n2);
+    CUDA_OK(h, cudaMemcpy(order.data(), h->cells.d_sorted, sizeof(int) * (size_t)n2,
+                          cudaMemcpyDeviceToHost));
+  }
   for (size_t k = 0; k < count; k++) {
-    unsigned long long const i = ent[k] >> 32, j = ent[k] & 0xffffffffull;
+    unsigned long long i = ent[k] >> 32, j = ent[k] & 0xffffffffull;
+    if (h->pl_sorted) {
+      j = (unsigned long long)order[(size_t)j];
+      if (h->self()) i = (unsigned long long)order[(size_t)i];
+    }
     // canonical index of the reference's dense bool array
     // (src/colvarcomp_coordnums.cpp:197-238 / :481-520)
     out[k] = h->self() ? i * (2 * n1 - i - 1) / 2 + (j - i - 1) : i * n2 + j;

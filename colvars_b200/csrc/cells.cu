@@ -138,15 +138,30 @@ __global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
 __global__ void cell_gather_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                    const double *__restrict__ z, const int *__restrict__ sorted,
                                    int n, double *__restrict__ xs, double *__restrict__ ys,
-                                   double *__restrict__ zs, const int *gate)
+                                   double *__restrict__ zs, const int *gate, int gate_on)
 {
   int const p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  if (gate != nullptr && *gate != 1) return;
+  if (gate != nullptr && *gate != gate_on) return;
   int const j = sorted[p];
   xs[p] = x[j];
   ys[p] = y[j];
   zs[p] = z[j];
+}
+
+// gradients accumulated in cell order go back to the group's planes (one thread per atom, plain
+// read-modify-write: every atom appears once in the order)
+__global__ void cell_scatter_add_kernel(const double *__restrict__ gs, const int *__restrict__ sorted,
+                                        int n, double *gx, double *gy, double *gz,
+                                        const int *gate, int gate_on)
+{
+  int const p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (gate != nullptr && *gate != gate_on) return;
+  int const j = sorted[p];
+  gx[j] += gs[p];
+  gy[j] += gs[n + p];
+  gz[j] += gs[2 * n + p];
 }
 
 // ---- candidate pairs: one warp per group1 row, lanes over the atoms of the 3 x 3 x-spans of
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
   // neighbouring cells and share their candidates' cache lines
   for (int q = A.i_begin + gwarp; q < A.i_end; q += nwarps) {
     int const i = A.self ? A.sorted2[q] : q;
+    int const row_id = A.sorted_entries ? q : i;  // q == i unless selfCoordNum
     double const xi = A.x1[i], yi = A.y1[i], zi = A.z1[i];
     bool const per = g.periodic != 0;
     int const cx = per ? cell_coord_periodic(xi, g.inv_len[0], g.dim[0])
@@ -274,15 +290,15 @@ __global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_c
             }
             unsigned const m = __ballot_sync(0xffffffffu, listed);
             if (m != 0u) {
-              if (listed) mybuf[nbuf + __popc(m & ((1u << lane) - 1u))] = j;
+              if (listed) mybuf[nbuf + __popc(m & ((1u << lane) - 1u))] = A.sorted_entries ? p : j;
               nbuf += __popc(m);
-              if (nbuf > ROW_BUF - 32) flush_row(i);
+              if (nbuf > ROW_BUF - 32) flush_row(row_id);
             }
           }
         }
       }
     }
-    flush_row(i);
+    flush_row(row_id);
     if (grad) {
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) {
@@ -326,6 +342,7 @@ int cells_setup(CellBuffers &B, int n2)
   if ((e = cudaMalloc(&B.d_xs, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_ys, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_zs, nbd)) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_gs, 3 * nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_cell_start, sizeof(int) * ((size_t)CELL_MAX + 2))) != cudaSuccess) {
     return (int)e;
   }
@@ -347,6 +364,7 @@ void cells_free(CellBuffers &B)
   cudaFree(B.d_xs);
   cudaFree(B.d_ys);
   cudaFree(B.d_zs);
+  cudaFree(B.d_gs);
   cudaFree(B.d_cell_start);
   cudaFree(B.d_temp);
   B = CellBuffers();
@@ -397,8 +415,23 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
   cell_start_kernel<<<(CELL_MAX + 1 + 255) / 256, 256, 0, stream>>>(B.d_key_sorted, n2, B.d_grid,
                                                                    B.d_cell_start, gate);
   note_launch();
+  return launch_cell_gather(B, x2, y2, z2, n2, gate, 1, stream);
+}
+
+int launch_cell_gather(CellBuffers &B, const double *x2, const double *y2, const double *z2,
+                       int n2, const int *gate, int gate_on, cudaStream_t stream)
+{
   cell_gather_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, B.d_sorted, n2, B.d_xs,
-                                                           B.d_ys, B.d_zs, gate);
+                                                           B.d_ys, B.d_zs, gate, gate_on);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_cell_scatter_add(CellBuffers &B, double *g2x, double *g2y, double *g2z, int n2,
+                            const int *gate, int gate_on, cudaStream_t stream)
+{
+  cell_scatter_add_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(B.d_gs, B.d_sorted, n2, g2x, g2y,
+                                                                g2z, gate, gate_on);
   note_launch();
   return (int)cudaGetLastError();
 }

@@ -38,6 +38,7 @@ struct CellBuffers {
   int *d_val = nullptr, *d_sorted = nullptr;      // atom index, sorted by cell
   int *d_cell_start = nullptr;                    // [CELL_MAX + 1]
   double *d_xs = nullptr, *d_ys = nullptr, *d_zs = nullptr;  // group2 coordinates in cell order
+  double *d_gs = nullptr;  // 3 planes of n2: group2 gradients in cell order (list walk)
   void *d_temp = nullptr;                         // radix-sort scratch
   size_t temp_bytes = 0;
   int n2 = 0;
@@ -60,6 +61,9 @@ struct CellPairArgs {
   double *partials;  // [CELL_BLOCKS]
   int flags;
   int fast_exp;  // 3: candidates may use the sweep's fast 6/12 form (see ExactArgs::fast_exp)
+  // list entries in cell order: (row << 32 | p) with p the sorted position of the group2 atom
+  // (and row the sorted position of the group1 atom for selfCoordNum), see launch_cell_gather
+  int sorted_entries;
   const int *gate;  // captured pair-list graphs: work only when *gate == 1 (see SweepArgs::gate)
   PairParams P;
 };
@@ -76,6 +80,15 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
                 const double cut[3], const double *periodic_edges, const int *gate,
                 cudaStream_t stream);
 bool cells_periodic_dims(const double cut[3], const double edges[3], int dim[3]);
+// A list with sorted_entries is walked in cell order: the neighbours of a row are a few
+// contiguous spans there, so the walk's coordinate loads and gradient atomics coalesce instead
+// of scattering over the group.  Per walk step: refresh B.d_xs/ys/zs from the current positions
+// (the order is that of the last rebuild), zero B.d_gs, walk, add B.d_gs back to the group's
+// gradient planes.  gate / gate_on as in SweepArgs (gate NULL: always).
+int launch_cell_gather(CellBuffers &B, const double *x2, const double *y2, const double *z2,
+                       int n2, const int *gate, int gate_on, cudaStream_t stream);
+int launch_cell_scatter_add(CellBuffers &B, double *g2x, double *g2y, double *g2z, int n2,
+                            const int *gate, int gate_on, cudaStream_t stream);
 int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream);
 
 }  // namespace b200cv
