@@ -775,7 +775,7 @@ def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso):
         if rebuild:
             assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
             assert pl.sum() * 50 < npairs  # sparse, as intended
-            if cv.last_stats()[0] >= 6:  # grid, keys, sort, offsets, pairs, shuffle (+ final sum)
+            if cv.last_stats()[0] >= 6:  # grid, keys, sort, offsets, gather, pairs, final sum
                 used_cells += 1
     assert used_cells == 3  # every rebuild after the first one
 
