@@ -337,6 +337,13 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     flop = w.get("flop_per_pair", synth.FLOP_PER_PAIR_VALUE_GRAD)
     out["flop_per_pair"] = flop
     out["roofline_frac"] = npairs / (kern * 1e-3) * flop / 1e12 / fp64_tflops
+    if w["tol"] > 0:
+        # a pair list exists to NOT evaluate most pairs (rebuilds go through a cell list, the
+        # other steps walk the list): pair-evals/s counts the reference's pairs, and a flop
+        # roofline over them would mean nothing
+        out["roofline_frac"] = None
+        out["note"] = ("value counts the reference's N(N-1)/2 pairs per step; rebuilds "
+                       "evaluate cell-list candidates only, list steps the listed pairs")
     cv.close()
     return out
 

@@ -14,6 +14,10 @@ namespace b200cv {
 namespace {
 
 constexpr int GRID_THREADS = 1024;
+#ifndef B200CV_CELL_MINB
+#define B200CV_CELL_MINB 2
+#endif
+constexpr int CELL_MINB = B200CV_CELL_MINB;  // CTAs per SM the register allocation targets
 
 // ---- bounding box of group2 -> grid parameters (one CTA; a rebuild happens every
 // pairListFrequency steps, this is not on the per-step path) -------------------------------
@@ -166,7 +170,7 @@ __global__ void cell_scatter_add_kernel(const double *__restrict__ gs, const int
 
 // ---- candidate pairs: one warp per group1 row, lanes over the atoms of the 3 x 3 x-spans of
 // neighbouring cells (cells adjacent in x are contiguous in key order) -------------------------
-__global__ void __launch_bounds__(CELL_THREADS) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
+__global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
 {
   __shared__ double red[CELL_THREADS / 32];
   // listed neighbours of the warp's current row: written to the list as ONE contiguous run per

@@ -348,13 +348,16 @@ __device__ __forceinline__ bool general_image(PairParams const &P, const double 
   double const q[13] = {pa,      pb,      pc,       pab,      pamb,      pa + pc,  pa - pc,
                         pb + pc, pb - pc, pab + pc, pab - pc, pamb + pc, pamb - pc};
   double m[13];
-  double best = __hiloint2double(0x7e37e43c, 0x8800759d);  // 1e300, index bits 13
 #pragma unroll
   for (int k = 0; k < 13; k++) {
     double const v = P.tri_n[k] - fabs(q[k]);
     m[k] = __hiloint2double(__double2hiint(v), (__double2loint(v) & ~15) | k);
-    best = fmin(best, m[k]);
   }
+  // minimum as a tree (depth 4): the search of one pair is a single dependency chain otherwise
+  double const b0 = fmin(m[0], m[1]), b1 = fmin(m[2], m[3]), b2 = fmin(m[4], m[5]);
+  double const b3 = fmin(m[6], m[7]), b4 = fmin(m[8], m[9]), b5 = fmin(m[10], m[11]);
+  double const c0 = fmin(b0, b1), c1 = fmin(b2, b3), c2 = fmin(b4, b5);
+  double const best = fmin(fmin(c0, c1), fmin(c2, m[12]));
   double const thr = best + P.tri_margin;
   int cnt = 0;
 #pragma unroll

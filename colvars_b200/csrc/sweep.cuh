@@ -286,13 +286,45 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
         }
       }
     } else {
+      // general cells: the image search is ~300 instructions per pair; unrolled R times (and
+      // again for the masked variant) the loop body outgrows the instruction cache (ncu: the
+      // warps then wait for instructions 2 cycles out of 3).  So the R searches run as a
+      // rolled loop over a small per-thread array (local memory, L1-resident), and only the
+      // light part of the pair stays unrolled.
+      double gdx[PBC == BC_GENERAL ? R : 1], gdy[PBC == BC_GENERAL ? R : 1],
+          gdz[PBC == BC_GENERAL ? R : 1];
+      unsigned ambmask = 0u;
+      if constexpr (PBC == BC_GENERAL) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          gdx[k] = xj - xi[k];
+          gdy[k] = yj - yi[k];
+          gdz[k] = zj - zi[k];
+        }
+#pragma unroll 1
+        for (int k = 0; k < R; k++) {
+          double ex = gdx[k], ey = gdy[k], ez = gdz[k];
+          bool const amb = general_image(P, tritab, ex, ey, ez);
+          gdx[k] = ex;
+          gdy[k] = ey;
+          gdz[k] = ez;
+          ambmask |= (amb ? 1u : 0u) << k;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < R; k++) {
-        double dx = xj - xi[k];
-        double dy = yj - yi[k];
-        double dz = zj - zi[k];
+        double dx, dy, dz;
         bool ambiguous = false;
-        if constexpr (PBC == BC_GENERAL) ambiguous = general_image(P, tritab, dx, dy, dz);
+        if constexpr (PBC == BC_GENERAL) {
+          dx = gdx[k];
+          dy = gdy[k];
+          dz = gdz[k];
+          ambiguous = (ambmask >> k) & 1u;
+        } else {
+          dx = xj - xi[k];
+          dy = yj - yi[k];
+          dz = zj - zi[k];
+        }
         double const u =
             pair_l2<ANISO, (PBC == BC_GENERAL ? BC_NONE : PBC), (EXP < 0)>(P, dx, dy, dz);
         // branch-free: a rare pair contributes nothing here and is remembered in a mask, so
