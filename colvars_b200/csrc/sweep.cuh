@@ -41,6 +41,9 @@ namespace b200cv {
 #define B200CV_JCMAX 1024
 #endif
 constexpr int JCMAX = B200CV_JCMAX;
+#ifndef B200CV_GEN_UNROLL
+#define B200CV_GEN_UNROLL 2  // image searches (general cells) interleaved per loop trip
+#endif
 #ifndef B200CV_TUNROLL
 #define B200CV_TUNROLL 1  // unroll factor of the 32-step rotation loop of a tile
 #endif  // group2 atoms per chunk (24 B coordinates + 24 B accumulators each)
@@ -301,7 +304,8 @@ __device__ __forceinline__ void sweep_tile(SweepArgs const &A, SweepItem const &
           gdy[k] = yj - yi[k];
           gdz[k] = zj - zi[k];
         }
-#pragma unroll 1
+        constexpr int GEN_UNROLL = B200CV_GEN_UNROLL;
+#pragma unroll GEN_UNROLL
         for (int k = 0; k < R; k++) {
           double ex = gdx[k], ey = gdy[k], ez = gdz[k];
           bool const amb = general_image(P, tritab, ex, ey, ez);
