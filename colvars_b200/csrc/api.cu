@@ -2012,7 +2012,10 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
     unsigned long long i = ent[k] >> 32, j = ent[k] & 0xffffffffull;
     if (h->pl_sorted) {
       j = (unsigned long long)order[(size_t)j];
-      if (h->self()) i = (unsigned long long)order[(size_t)i];
+      if (h->self()) {
+        i = (unsigned long long)order[(size_t)i];
+        if (i > j) std::swap(i, j);  // listed by the row that comes first in cell order
+      }
     }
     // canonical index of the reference's dense bool array
     // (src/colvarcomp_coordnums.cpp:197-238 / :481-520)

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(con
   int const gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   int const nwarps = gridDim.x * warps_per_block;
   bool const grad = A.flags & EF_GRADIENTS;
+  bool const self_sorted = A.self && A.sorted_entries;
   double fsum = 0.0;
   // selfCoordNum: rows in cell order as well (row q of the sorted atoms; any disjoint split of
   // the rows over warps and ranks lists every pair once), so that the warps of a CTA work on
@@ -243,14 +244,20 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(con
             xb = min(cx + 1, g.dim[0] - 1);
             if (xa > xb) continue;
           }
-          int const begin = A.cell_start[row + xa], end = A.cell_start[row + xb + 1];
+          int begin = A.cell_start[row + xa];
+          int const end = A.cell_start[row + xb + 1];
+          // selfCoordNum in cell order: a pair belongs to the row that comes first in that order
+          // (any strict order lists every pair once; b200cv_pairlist puts the smaller atom index
+          // first again), so everything up to the row's own position is skipped -- half of the
+          // neighbourhood goes away without being looked at
+          if (self_sorted) begin = max(begin, q + 1);
           for (int p0 = begin; p0 < end; p0 += 32) {
             int const p = p0 + lane;
             double F = 0.0, Gx = 0.0, Gy = 0.0, Gz = 0.0;
             int j = -1;
             if (p < end) {
               j = A.sorted2[p];
-              if (!A.self || j > i) {
+              if (!A.self || self_sorted || j > i) {
                 double const xj = A.xs[p], yj = A.ys[p], zj = A.zs[p];
                 bool done = false;
                 if (A.fast_exp == 3) {
