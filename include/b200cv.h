@@ -119,7 +119,10 @@ int b200cv_set_fitting(b200cv_cvc *h, int which, int center, int rotate,
                        const int *fit_proxy_index, int nfit, const double *ref_pos_soa,
                        int enable_fit_gradients);
 
-/* Periodic flags and Bravais vectors; all-zero flags = non-periodic. */
+/* Periodic flags and Bravais vectors; all-zero flags = non-periodic.  The four kinds of
+ * system_boundary_conditions::position_distance (src/colvars_system.h:161-219: non-periodic,
+ * orthogonal, mixed, triclinic with its search over the 27 neighbouring images) all run inside
+ * the pair sweep. */
 int b200cv_set_boundaries(b200cv_cvc *h, int periodic_x, int periodic_y, int periodic_z,
                           const double A[3], const double B[3], const double C[3]);
 
