@@ -769,7 +769,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.cap = h->pl_cap;
       E.partials = partials;
       E.flags = flags & ~B200CV_EF_REBUILD_PAIRLIST;
-      E.fast_exp = (h->exp_special == 3 && (h->P.bc_type == 0 || h->P.bc_type == 2)) ? 3 : 0;
+      E.fast_exp = (h->exp_special == 3) ? 3 : 0;  // every kind of cell has a fast form
       E.gate = gate;
       E.gate_on = 0;
       if (fuse) {

@@ -67,12 +67,23 @@ __device__ __forceinline__ void finalize_body(FinalizeArgs const &A, double *red
 
 // ============================ exact pair queue / pair-list walk ================================
 
+// GENERAL: the walk's fast form in mixed / triclinic cells as well (image search of the sweep,
+// general_image; ambiguous decisions fall through to the reference-order pair).  A variant of
+// its own because the search costs registers the other walks should not pay for.
+template <bool GENERAL>
 __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_constant__ ExactArgs A)
 {
   __shared__ double red[EXACT_THREADS / 32];
+  __shared__ double tritab[GENERAL ? 42 : 1];
   if (A.gate != nullptr && *A.gate != A.gate_on) {
     if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
     return;
+  }
+  if constexpr (GENERAL) {
+    if (threadIdx.x < 42) {
+      tritab[threadIdx.x] = threadIdx.x < 39 ? A.P.tri_shift[threadIdx.x / 3][threadIdx.x % 3] : 0.0;
+    }
+    __syncthreads();
   }
   unsigned long long n = A.count32 ? (unsigned long long)*A.count32 : *A.count64;
   if (n > A.cap) n = A.cap;
@@ -102,7 +113,10 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
         // 6/12, non-periodic or orthorhombic: the sweep's fast form for every pair that is not
         // next to a decision threshold (same windows as the sweep), reference order otherwise
         double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
-        if (A.P.bc_type == 2) {
+        bool ambiguous = false;
+        if constexpr (GENERAL) {
+          ambiguous = general_image(A.P, tritab, dx, dy, dz);
+        } else if (A.P.bc_type == 2) {
           double const shx = floor(__dadd_rn(__dmul_rn(A.P.recip[0][0], dx), 0.5));
           double const shy = floor(__dadd_rn(__dmul_rn(A.P.recip[1][1], dy), 0.5));
           double const shz = floor(__dadd_rn(__dmul_rn(A.P.recip[2][2], dz), 0.5));
@@ -112,7 +126,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
         }
         double const sx = dx * A.P.inv_r0[0], sy = dy * A.P.inv_r0[1], sz = dz * A.P.inv_r0[2];
         double const u = fma(sz, sz, fma(sy, sy, sx * sx));
-        if (!pair_is_rare<true>(u, A.P)) {
+        if (!ambiguous && !pair_is_rare<true>(u, A.P)) {
           double gq;
           switching_fast<3, true>(u, false, A.P, F, gq);
           Gx = A.P.c_grad[0] * gq * dx;
@@ -183,7 +197,9 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
 
 int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks)
 {
-  exact_kernel<<<blocks, EXACT_THREADS, 0, stream>>>(args);
+  bool const general = args.fast_exp == 3 && (args.P.bc_type == 1 || args.P.bc_type == 3);
+  if (general) exact_kernel<true><<<blocks, EXACT_THREADS, 0, stream>>>(args);
+  else exact_kernel<false><<<blocks, EXACT_THREADS, 0, stream>>>(args);
   note_launch();
   return (int)cudaGetLastError();
 }
