@@ -584,20 +584,38 @@ void cell_cutoffs(const b200cv_cvc *h, double cut[3])
   for (int d = 0; d < 3; d++) cut[d] = std::sqrt(h->P.l2_max) / h->P.inv_r0[d];
 }
 
+// reciprocal vectors for the cell list's fractional binning: diag(1 / |edge|) for an orthorhombic
+// cell, the reference's reciprocal cell vectors for a triclinic one; false for any other kind
+bool cell_list_frac(const b200cv_cvc *h, double frac[9])
+{
+  for (int k = 0; k < 9; k++) frac[k] = 0.0;
+  if (h->P.bc_type == 2) {
+    for (int d = 0; d < 3; d++) frac[4 * d] = 1.0 / std::fabs(h->P.cell[d][d]);
+    return true;
+  }
+  if (h->P.bc_type == 3) {
+    for (int a = 0; a < 3; a++) {
+      for (int d = 0; d < 3; d++) frac[3 * a + d] = h->P.recip[a][d];
+    }
+    return true;
+  }
+  return false;
+}
+
 // the cell list (cells.cuh) is set up and applies: a list has been built before, and the system
-// is non-periodic or orthorhombic with at least three cells per axis
+// is non-periodic, orthorhombic or triclinic with at least three cells per axis (mixed cells keep
+// the all-pairs sweep)
 bool cells_usable(const b200cv_cvc *h)
 {
   if (!(h->cells_ready && h->d_pl && h->pl_n > 0) || std::getenv("B200CV_NO_CELLS")) {
     return false;
   }
   if (h->P.bc_type == 0) return true;
-  if (h->P.bc_type != 2) return false;
-  double cut[3], edges[3] = {std::fabs(h->P.cell[0][0]), std::fabs(h->P.cell[1][1]),
-                             std::fabs(h->P.cell[2][2])};
+  double cut[3], frac[9];
   int dim[3];
+  if (!cell_list_frac(h, frac)) return false;
   cell_cutoffs(h, cut);
-  return cells_periodic_dims(cut, edges, dim);
+  return cells_periodic_dims(cut, frac, dim);
 }
 
 // rebuild through the cell list instead of the all-pairs sweep?
@@ -865,10 +883,10 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       static_assert(CELL_BLOCKS + WALK_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
       double cut[3];
       cell_cutoffs(h, cut);
-      double const edges[3] = {std::fabs(h->P.cell[0][0]), std::fabs(h->P.cell[1][1]),
-                               std::fabs(h->P.cell[2][2])};
-      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut,
-                             h->P.bc_type == 2 ? edges : nullptr, gate, stream));
+      double frac[9];
+      bool const periodic = cell_list_frac(h, frac);
+      CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut, periodic ? frac : nullptr, gate,
+                             stream));
       h->launches += 5;
       CellPairArgs C{};
       C.x1 = x1; C.y1 = y1; C.z1 = z1; C.x2 = x2; C.y2 = y2; C.z2 = z2;
@@ -888,7 +906,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.pl_count = h->pl_count();
       C.partials = h->d_partials;
       C.flags = cell_flags;
-      C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // bc_type is 0 or 2 here, both have a fast form
+      C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // every kind of cell has a fast form
       h->pl_sorted = sorted_walk_enabled();
       C.sorted_entries = h->pl_sorted ? 1 : 0;
       C.gate = gate;

@@ -73,7 +73,9 @@ grid_kernel(const double *__restrict__ x, const double *__restrict__ y,
     }
     grid->ncells = ncells;
     grid->periodic = 0;
-    grid->inv_len[0] = grid->inv_len[1] = grid->inv_len[2] = 0.0;
+    for (int a = 0; a < 3; a++) {
+      for (int d = 0; d < 3; d++) grid->frac[a][d] = 0.0;
+    }
   }
 }
 
@@ -90,12 +92,13 @@ __device__ __forceinline__ int cell_coord(double p, double origin, double inv_ce
   return (int)fmin(fmax(c, -2.0), (double)dim + 1.0);
 }
 
-// periodic: cell of the atom's image inside the unit cell
-__device__ __forceinline__ int cell_coord_periodic(double p, double inv_len, int dim)
+// periodic: cell of the atom's image inside the unit cell, along fractional axis a
+__device__ __forceinline__ int cell_coord_periodic(CellGrid const &g, int a, double x, double y,
+                                                   double z)
 {
-  double const t = p * inv_len;
+  double const t = fma(z, g.frac[a][2], fma(y, g.frac[a][1], x * g.frac[a][0]));
   double const f = t - floor(t);  // [0, 1]; 1.0 only by rounding for tiny negative t
-  return min((int)(f * (double)dim), dim - 1);
+  return min((int)(f * (double)g.dim[a]), g.dim[a] - 1);
 }
 
 __global__ void cell_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
@@ -109,9 +112,9 @@ __global__ void cell_key_kernel(const double *__restrict__ x, const double *__re
   CellGrid const g = *grid;
   int cx, cy, cz;
   if (g.periodic) {
-    cx = cell_coord_periodic(x[i], g.inv_len[0], g.dim[0]);
-    cy = cell_coord_periodic(y[i], g.inv_len[1], g.dim[1]);
-    cz = cell_coord_periodic(z[i], g.inv_len[2], g.dim[2]);
+    cx = cell_coord_periodic(g, 0, x[i], y[i], z[i]);
+    cy = cell_coord_periodic(g, 1, x[i], y[i], z[i]);
+    cz = cell_coord_periodic(g, 2, x[i], y[i], z[i]);
   } else {
     cx = min(max(cell_coord(x[i], g.origin[0], g.inv_cell[0], g.dim[0]), 0), g.dim[0] - 1);
     cy = min(max(cell_coord(y[i], g.origin[1], g.inv_cell[1], g.dim[1]), 0), g.dim[1] - 1);
@@ -170,9 +173,19 @@ __global__ void cell_scatter_add_kernel(const double *__restrict__ gs, const int
 
 // ---- candidate pairs: one warp per group1 row, lanes over the atoms of the 3 x 3 x-spans of
 // neighbouring cells (cells adjacent in x are contiguous in key order) -------------------------
+// GENERAL: triclinic cell, candidates through the sweep's image search (general_image) with the
+// reference-order pair as the fallback for ambiguous decisions and threshold neighbours
+template <bool GENERAL>
 __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(const __grid_constant__ CellPairArgs A)
 {
   __shared__ double red[CELL_THREADS / 32];
+  __shared__ double tritab[GENERAL ? 42 : 1];
+  if constexpr (GENERAL) {
+    if (threadIdx.x < 42) {
+      tritab[threadIdx.x] = threadIdx.x < 39 ? A.P.tri_shift[threadIdx.x / 3][threadIdx.x % 3] : 0.0;
+    }
+    __syncthreads();
+  }
   // listed neighbours of the warp's current row: written to the list as ONE contiguous run per
   // row (one counter atomic per run, coalesced stores); the list walk sums the row's gradient
   // over such a run before it touches memory
@@ -216,11 +229,11 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(con
     int const row_id = A.sorted_entries ? q : i;  // q == i unless selfCoordNum
     double const xi = A.x1[i], yi = A.y1[i], zi = A.z1[i];
     bool const per = g.periodic != 0;
-    int const cx = per ? cell_coord_periodic(xi, g.inv_len[0], g.dim[0])
+    int const cx = per ? cell_coord_periodic(g, 0, xi, yi, zi)
                        : cell_coord(xi, g.origin[0], g.inv_cell[0], g.dim[0]);
-    int const cy = per ? cell_coord_periodic(yi, g.inv_len[1], g.dim[1])
+    int const cy = per ? cell_coord_periodic(g, 1, xi, yi, zi)
                        : cell_coord(yi, g.origin[1], g.inv_cell[1], g.dim[1]);
-    int const cz = per ? cell_coord_periodic(zi, g.inv_len[2], g.dim[2])
+    int const cz = per ? cell_coord_periodic(g, 2, xi, yi, zi)
                        : cell_coord(zi, g.origin[2], g.inv_cell[2], g.dim[2]);
     double gx = 0.0, gy = 0.0, gz = 0.0;
     // neighbouring cells: non-periodic -- clipped to the grid, the three x-cells as one span;
@@ -264,7 +277,10 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(con
                   // 6/12: the sweep's fast form for every pair that is not next to a decision
                   // threshold (same windows as the sweep), reference order otherwise
                   double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-                  if (A.P.bc_type == 2) {
+                  bool ambiguous = false;
+                  if constexpr (GENERAL) {
+                    ambiguous = general_image(A.P, tritab, dx, dy, dz);
+                  } else if (A.P.bc_type == 2) {
                     // orthorhombic minimum image, image index in the reference's operation
                     // order (src/colvars_system.h:176-184), as in the tile sweep
                     double const shx = floor(__dadd_rn(__dmul_rn(A.P.recip[0][0], dx), 0.5));
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) cell_pairs_kernel(con
                   double const sx = dx * A.P.inv_r0[0], sy = dy * A.P.inv_r0[1],
                                sz = dz * A.P.inv_r0[2];
                   double const u = fma(sz, sz, fma(sy, sy, sx * sx));
-                  if (!pair_is_rare<true>(u, A.P)) {
+                  if (!ambiguous && !pair_is_rare<true>(u, A.P)) {
                     double gq;
                     switching_fast<3, true>(u, false, A.P, F, gq);
                     Gx = A.P.c_grad[0] * gq * dx;
@@ -381,31 +397,38 @@ void cells_free(CellBuffers &B)
   B = CellBuffers();
 }
 
-bool cells_periodic_dims(const double cut[3], const double edges[3], int dim[3])
+bool cells_periodic_dims(const double cut[3], const double frac[9], int dim[3])
 {
-  for (int d = 0; d < 3; d++) {
-    if (!(edges[d] > 0.0) || !(cut[d] > 0.0)) return false;
-    double const n = std::floor(edges[d] / (cut[d] * (1.0 + 1.0e-9)));
+  bool const diagonal = frac[1] == 0.0 && frac[2] == 0.0 && frac[3] == 0.0 && frac[5] == 0.0 &&
+                        frac[6] == 0.0 && frac[7] == 0.0;
+  double const cmax = std::max(cut[0], std::max(cut[1], cut[2]));
+  for (int a = 0; a < 3; a++) {
+    double const len = std::sqrt(frac[3 * a] * frac[3 * a] + frac[3 * a + 1] * frac[3 * a + 1] +
+                                 frac[3 * a + 2] * frac[3 * a + 2]);
+    double const c = diagonal ? cut[a] : cmax;
+    if (!(len > 0.0) || !(c > 0.0)) return false;
+    double const width = 1.0 / len;  // of the unit cell, perpendicular to the faces of axis a
+    double const n = std::floor(width / (c * (1.0 + 1.0e-9)));
     if (n < 3.0) return false;  // the three neighbours of a cell must be distinct
-    dim[d] = (int)std::min(n, (double)CELL_MAX_DIM);
+    dim[a] = (int)std::min(n, (double)CELL_MAX_DIM);
   }
   return true;
 }
 
 int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
-                const double cut[3], const double *periodic_edges, const int *gate,
+                const double cut[3], const double *periodic_frac, const int *gate,
                 cudaStream_t stream)
 {
-  if (periodic_edges != nullptr) {
+  if (periodic_frac != nullptr) {
     CellGrid g{};
     int dim[3];
-    if (!cells_periodic_dims(cut, periodic_edges, dim)) return (int)cudaErrorInvalidValue;
+    if (!cells_periodic_dims(cut, periodic_frac, dim)) return (int)cudaErrorInvalidValue;
     g.ncells = 1;
     for (int d = 0; d < 3; d++) {
       g.origin[d] = 0.0;
       g.dim[d] = dim[d];
-      g.inv_len[d] = 1.0 / periodic_edges[d];
-      g.inv_cell[d] = (double)dim[d] / periodic_edges[d];
+      g.inv_cell[d] = 0.0;  // unused: cells are counted in fractional coordinates
+      for (int k = 0; k < 3; k++) g.frac[d][k] = periodic_frac[3 * d + k];
       g.ncells *= dim[d];
     }
     g.periodic = 1;
@@ -449,7 +472,9 @@ int launch_cell_scatter_add(CellBuffers &B, double *g2x, double *g2y, double *g2
 
 int launch_cell_pairs(const CellPairArgs &args, cudaStream_t stream)
 {
-  cell_pairs_kernel<<<CELL_BLOCKS, CELL_THREADS, 0, stream>>>(args);
+  bool const general = args.fast_exp == 3 && (args.P.bc_type == 1 || args.P.bc_type == 3);
+  if (general) cell_pairs_kernel<true><<<CELL_BLOCKS, CELL_THREADS, 0, stream>>>(args);
+  else cell_pairs_kernel<false><<<CELL_BLOCKS, CELL_THREADS, 0, stream>>>(args);
   note_launch();
   return (int)cudaGetLastError();
 }

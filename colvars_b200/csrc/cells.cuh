@@ -1,4 +1,4 @@
-// cells.cuh -- cell-list rebuild of the pair list (non-periodic).
+// cells.cuh -- cell-list rebuild of the pair list (open systems, orthorhombic and triclinic cells).
 //
 // On a rebuild step the reference visits every pair (src/colvarcomp_coordnums.cpp:219-232), but a
 // pair with l2 > tolerance_l2_max returns 0 before anything is evaluated and is not listed
@@ -26,10 +26,11 @@ struct CellGrid {
   double inv_cell[3];
   int dim[3];
   int ncells;
-  // orthorhombic periodic cell: atoms are wrapped into the unit cell (inv_len = 1 / edge),
+  // periodic cell (orthorhombic or triclinic): atoms are binned by their fractional coordinates
+  // frac[a] . p wrapped into [0, 1) (frac = reciprocal vectors; diag(1 / edge) when orthorhombic),
   // neighbours wrap around; dim >= 3 per axis so that the three neighbours are distinct
   int periodic;
-  double inv_len[3];
+  double frac[3][3];
 };
 
 struct CellBuffers {
@@ -73,13 +74,18 @@ int cells_setup(CellBuffers &B, int n2);
 void cells_free(CellBuffers &B);
 // grid + sort of the group2 atoms; cut[d] = cut-off radius along axis d
 // gate (may be NULL): see CellPairArgs::gate; the radix sort itself always runs.
-// periodic_edges: NULL for a non-periodic system (grid = bounding box of group2, found on the
-// device), else the three edge lengths of an orthorhombic cell (grid fixed by the host;
-// cells_periodic_dims tells whether the cell is large enough: >= 3 cells per axis)
+// periodic_frac: NULL for a non-periodic system (grid = bounding box of group2, found on the
+// device), else the reciprocal vectors of the cell, row by row (diag(1 / edge) for an
+// orthorhombic cell); the grid is then fixed by the host.  cells_periodic_dims tells whether the
+// cell is large enough (>= 3 cells per axis): a fractional cell must be at least one cut-off wide
+// measured perpendicular to its faces, width_a = 1 / |frac_a| -- per-axis cut-offs for an
+// orthorhombic cell, the largest of the three otherwise (|d| <= max cut for every listed pair,
+// so |frac_a . d| <= 1 / dim_a: the two atoms sit in the same or in adjacent cells whatever
+// image of the pair the reference ends up using).
 int cells_build(CellBuffers &B, const double *x2, const double *y2, const double *z2, int n2,
-                const double cut[3], const double *periodic_edges, const int *gate,
+                const double cut[3], const double *periodic_frac, const int *gate,
                 cudaStream_t stream);
-bool cells_periodic_dims(const double cut[3], const double edges[3], int dim[3]);
+bool cells_periodic_dims(const double cut[3], const double frac[9], int dim[3]);
 // A list with sorted_entries is walked in cell order: the neighbours of a row are a few
 // contiguous spans there, so the walk's coordinate loads and gradient atomics coalesce instead
 // of scattering over the group.  Per walk step: refresh B.d_xs/ys/zs from the current positions

@@ -1049,3 +1049,42 @@ def test_general_cell_sweep_equals_the_dense_reference_order_kernel(monkeypatch)
     close_val(vs, vd)
     close_arr(g1s, g1d)
     close_arr(g2s, g2d)
+
+
+@pytest.mark.parametrize("cell", ["dodecahedron", "octahedron", "skewed"])
+@pytest.mark.parametrize("kind", ["selfCoordNum", "coordNum"])
+def test_sparse_pairlist_rebuild_through_the_cell_list_triclinic(kind, cell):
+    """Triclinic cells: atoms are binned by their wrapped fractional coordinates, a fractional
+    cell is at least one (largest) cut-off wide perpendicular to its faces, every candidate goes
+    through the reference's own position_distance (27-image search); list walks use the image
+    search of the sweep.  Values, gradients and bit-exact lists over rebuild and list steps."""
+    cb = _cb()
+    rng = np.random.default_rng(79)
+    n1, n2 = (3000, 0) if kind == "selfCoordNum" else (700, 5000)
+    per, A, B, Cc = _scaled_cell(cell, 80.0)
+    lat = np.array([A, B, Cc])
+    pos = (rng.random((n1 + n2, 3)) * 3.0 - 1.0) @ lat  # images in the neighbouring cells too
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32) if n2 else None
+    tol, freq = 0.01, 2
+    cv = cb.CoordNum(kind, i1, i2, cutoff3=(4.0, 3.5, 4.5), tolerance=tol, pairlist_freq=freq)
+    cv.set_boundaries(per, A, B, Cc)
+    p = O.make_params((4.0, 3.5, 4.5), tolerance=tol, boundaries=(per, A, B, Cc))
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    used_cells = 0
+    for step in range(5):
+        frame = pos + rng.normal(0, 0.15, pos.shape) * step
+        v = cv.calc_host(np.ascontiguousarray(frame), step=step)
+        rebuild = step % freq == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(cv.gradients(2), og2)
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
+            used_cells += int(cv.last_stats()[0] >= 6)
+    assert used_cells == 2

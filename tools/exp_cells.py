@@ -11,8 +11,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
 proxy, i1, L = synth.selfcoordnum_case(N, seed=1234)
 cv = cb.CoordNum("selfCoordNum", i1, cutoff=4.0, tolerance=1e-3, pairlist_freq=10)
 if len(sys.argv) > 2 and sys.argv[2] == "tric":
-    # rhombic dodecahedron: rebuilds stay on the tile sweep (no cell list in general cells), the
-    # list steps use the walk's general-cell fast form
+    # rhombic dodecahedron: cell list in fractional coordinates, image search per candidate
     cv.set_boundaries((1, 1, 1), (L, 0, 0), (0, L, 0), (0.5 * L, 0.5 * L, 0.5 * 2 ** 0.5 * L))
 d_pos = torch.tensor(np.ascontiguousarray(proxy.T), device="cuda")
 s = torch.cuda.current_stream()
