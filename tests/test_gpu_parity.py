@@ -819,11 +819,13 @@ def test_cell_list_rebuild_inside_the_fused_step_graph():
     close_arr(a.gradients(1), og1)
 
 
+@pytest.mark.parametrize("cell", ["open", "octahedron"])
 @pytest.mark.parametrize("kind", ["selfCoordNum", "coordNum"])
-def test_captured_pairlist_graph_on_a_sparse_system_uses_the_cell_list(kind):
+def test_captured_pairlist_graph_on_a_sparse_system_uses_the_cell_list(kind, cell):
     """The `smp gpu` form (one captured graph, mode word) with a sparse list: the rebuild branch
     of the graph is the gated cell-list pipeline; replays for rebuild and walk steps against the
-    synchronous path and the oracle."""
+    synchronous path and the oracle.  Open system, and a triclinic cell (fractional binning, image
+    search in the cell kernel and in the walk, all gated)."""
     import torch
     cb = _cb()
     rng = np.random.default_rng(15)
@@ -834,6 +836,10 @@ def test_captured_pairlist_graph_on_a_sparse_system_uses_the_cell_list(kind):
     freq, tol = 3, 0.01
     kw = dict(cutoff=4.0, tolerance=tol, pairlist_freq=freq)
     cv = cb.CoordNum(kind, i1, i2, **kw)
+    boundaries = None
+    if cell != "open":
+        boundaries = _scaled_cell(cell, 75.0)
+        cv.set_boundaries(*boundaries)
     p1 = torch.tensor(np.ascontiguousarray(pos[i1].T), device="cuda")
     p2 = torch.tensor(np.ascontiguousarray(pos[i2].T), device="cuda") if n2 else None
     g1 = torch.zeros_like(p1)
@@ -849,7 +855,7 @@ def test_captured_pairlist_graph_on_a_sparse_system_uses_the_cell_list(kind):
         cv.accumulate_gradients(g1, g2, stream=side)
     # fetch, grid, keys, sort (>= 1), offsets, pairs, shuffle, walk, final sum, repacks ...
     assert cb.kernel_launches() - launches_before >= 10
-    p = O.make_params((4.0,) * 3, tolerance=tol)
+    p = O.make_params((4.0,) * 3, tolerance=tol, boundaries=boundaries)
     npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
     pl = np.ones(npairs, dtype=np.uint8)
     for step in range(7):
