@@ -5,9 +5,10 @@
 // (src/colvarcomp_coordnums.h:256-261).  With cells at least one cut-off radius wide per axis
 // (|d_axis| > cell_axis  =>  (d_axis / r0_axis)^2 > l2_max  =>  l2 > l2_max) every pair outside
 // the 27 neighbouring cells is such a pair, so it can be skipped without changing any number:
-// value, gradients and list are those of the full sweep.  Candidates are evaluated in the
-// reference's operation order (pair_exact), so every listed / not-listed decision is the
-// reference's own.
+// value, gradients and list are those of the full sweep.  Candidates next to a decision threshold
+// (and ambiguous images in a triclinic cell) are evaluated in the reference's operation order
+// (pair_exact), so every listed / not-listed decision is the reference's own; the others use the
+// sweep's fast form.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -25,9 +25,13 @@
 //   pair list   : on rebuild sweeps each lane records one 32-bit mask per register atom
 //                 and tile; masks are compacted into a global (i,j) list by a warp
 //                 prefix sum and one atomicAdd per warp and tile (stream compaction).
-//   rare pairs  : pairs within 2^-4 of l2 = 1 (or next to a pair-list threshold) are
-//                 appended to a queue and evaluated in the reference's operation order by
-//                 exact_kernel; they contribute nothing here.
+//   rare pairs  : pairs within 2^-4 of l2 = 1 (or next to a pair-list threshold, or with an
+//                 ambiguous image in a mixed / triclinic cell) are appended to a queue and
+//                 evaluated in the reference's operation order by exact_kernel; they
+//                 contribute nothing here.
+//   cells       : PBC = BC_NONE, BC_ORTHO (minimum image per axis, inside pair_l2) or BC_GENERAL
+//                 (mixed / triclinic: general_image, pair_math.cuh -- the reference's search
+//                 over the 27 neighbouring images, decided on 13 dot-product scores).
 //
 // FP64-pipe cost of the specialised n=6/m=12 isotropic pair: 3 (diff) + 3 (d2) + 1 (l2)
 // + 2 (l2^2, 1+l2^3) + 3 (reciprocal refinement) + 2 (r^2, gq) + 1 (F sum) + 6 (two
