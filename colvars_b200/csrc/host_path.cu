@@ -1,0 +1,166 @@
+// host_path.cu -- entries for group / proxy arrays that live in HOST memory (a CPU proxy):
+// b200cv_eval_host (atom_group arrays after the reference's own read_data) and the whole step
+// b200cv_calc_host / b200cv_apply_force_host on AoS proxy arrays.  Host<->device copies happen
+// here; the arithmetic is the same kernels as the device-resident step.
+#include "engine.h"
+
+using namespace b200cv;
+
+extern "C" {
+
+int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, int flags,
+                     double *h_grad1, double *h_grad2, double *value)
+{
+  if (!h || !value) return B200CV_BUG_ERROR;
+  if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
+  if (!h_pos1 || (!h->self() && !h_pos2)) return fail(h, B200CV_BUG_ERROR, "null positions");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->own_stream;
+  int const ng = h->self() ? 1 : 2;
+  const double *hp[2] = {h_pos1, h_pos2};
+  double *hg[2] = {h_grad1, h_grad2};
+  int rc = reset_gradients(h, s);
+  if (rc) return rc;
+  for (int k = 0; k < ng; k++) {
+    Group &G = h->g[k];
+    // SoA planes of n atoms -> padded planes of the device buffers
+    CUDA_OK(h, cudaMemcpy2DAsync(G.d_pos, sizeof(double) * G.stride, hp[k],
+                                 sizeof(double) * G.n, sizeof(double) * G.n, 3,
+                                 cudaMemcpyHostToDevice, s));
+    CUDA_OK_RC(centers_after_read(h, G, s));
+  }
+  if (!(h->cfg.tolerance > 0) || h->cfg.kind == B200CV_GROUPCOORD) {
+    flags &= ~(B200CV_EF_USE_PAIRLIST | B200CV_EF_REBUILD_PAIRLIST);
+  }
+  h->async_eval = false;
+  h->gated = false;
+  h->last_stream = s;
+  h->last_flags = flags;
+  h->have_calc = true;
+  h->data_read = true;
+  rc = enqueue_calc(h, flags, s);
+  if (rc) return rc;
+  rc = sync_and_check(h);
+  if (rc) return rc;
+  *value = *h->h_value;
+  if (flags & B200CV_EF_GRADIENTS) {
+    if (h->h_stage_count < h->reduce_count) {
+      if (h->h_stage_grad) cudaFreeHost(h->h_stage_grad);
+      h->h_stage_grad = nullptr;
+      CUDA_OK(h, cudaHostAlloc(&h->h_stage_grad, sizeof(double) * h->reduce_count,
+                               cudaHostAllocDefault));
+      h->h_stage_count = h->reduce_count;
+    }
+    CUDA_OK(h, cudaMemcpyAsync(h->h_stage_grad, h->d_reduce, sizeof(double) * h->reduce_count,
+                               cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    for (int k = 0; k < ng; k++) {
+      if (!hg[k]) continue;
+      Group &G = h->g[k];
+      const double *g = h->h_stage_grad + (G.d_grad - h->d_reduce);
+      for (int d = 0; d < 3; d++) {
+        for (int i = 0; i < G.n; i++) hg[k][(size_t)d * G.n + i] += g[(size_t)d * G.stride + i];
+      }
+    }
+  }
+  return B200CV_OK;
+}
+
+// ---- host-buffer step --------------------------------------------------------------------------
+
+int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
+                     long long step_relative, int gradients, double *value)
+{
+  if (!h || !h_proxy_pos || !value) return B200CV_BUG_ERROR;
+  if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->own_stream;
+  if (h->stage_n < n_proxy) {
+    free_dev(h->d_stage_pos);
+    CUDA_OK(h, cudaMalloc(&h->d_stage_pos, sizeof(double) * 3 * n_proxy));
+    h->stage_n = n_proxy;
+  }
+  // the CPU proxy's AoS rvector array (src/colvarproxy.h:275) goes up in one copy; the
+  // gather by atoms_index runs on the device
+  CUDA_OK(h, cudaMemcpyAsync(h->d_stage_pos, h_proxy_pos, sizeof(double) * 3 * n_proxy,
+                             cudaMemcpyHostToDevice, s));
+  int rc = reset_gradients(h, s);
+  if (rc) return rc;
+  int const ng = h->self() ? 1 : 2;
+  for (int k = 0; k < ng; k++) {
+    Group &G = h->g[k];
+    CUDA_OK(h, launch_gather(h->d_stage_pos, n_proxy, 1, G.d_index, G.n, G.d_pos, G.stride, s));
+    std::string err;
+    rc = fit_read_and_apply(G.fit, h->d_stage_pos, n_proxy, 1, G.d_pos, G.stride, G.n, s, err);
+    if (rc) return fail(h, rc, err);
+    CUDA_OK_RC(centers_after_read(h, G, s));
+  }
+  h->data_read = true;
+  rc = b200cv_calc_value(h, step_relative, gradients, s);
+  if (rc) return rc;
+  if (gradients) {
+    rc = b200cv_calc_fit_gradients(h, s);
+    if (rc) return rc;
+  }
+  return b200cv_value(h, value);
+}
+
+int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, size_t n_proxy)
+{
+  if (!h || !h_proxy_force) return B200CV_BUG_ERROR;
+  if (!h->have_calc) return fail(h, B200CV_BUG_ERROR, "apply_force before calc_value");
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->last_stream;
+  // one D2H copy of [grad1 | grad2]; the scatter into the AoS force array is the same
+  // host loop as atom_group::apply_colvar_force (src/colvaratoms.cpp:1637-1704)
+  if (h->h_stage_count < h->reduce_count) {
+    if (h->h_stage_grad) cudaFreeHost(h->h_stage_grad);
+    h->h_stage_grad = nullptr;
+    CUDA_OK(h, cudaHostAlloc(&h->h_stage_grad, sizeof(double) * h->reduce_count,
+                             cudaHostAllocDefault));
+    h->h_stage_count = h->reduce_count;
+  }
+  CUDA_OK(h, cudaMemcpyAsync(h->h_stage_grad, h->d_reduce, sizeof(double) * h->reduce_count,
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_OK(h, cudaStreamSynchronize(s));
+  int const ng = h->self() ? 1 : 2;
+  for (int k = 0; k < ng; k++) {
+    Group &G = h->g[k];
+    const double *g = h->h_stage_grad + (G.d_grad - h->d_reduce);
+    double Rinv[3][3];
+    bool const rot = G.fit.rotate;
+    if (rot) {
+      std::string err;
+      int rc = fit_host_inverse_matrix(G.fit, Rinv, err);
+      if (rc) return fail(h, rc, err);
+    }
+    if (G.max_index >= 0 && (size_t)G.max_index >= n_proxy) {
+      return fail(h, B200CV_BUG_ERROR, "proxy index out of range");
+    }
+    const int *idx = G.h_index.data();
+    size_t const stride = G.stride;
+    int const n = G.n;
+    // distinct atoms of one group: the rows are independent, large groups are split over the
+    // host threads (the reference's loop is sequential, src/colvaratoms.cpp:1637-1704)
+#pragma omp parallel for schedule(static) if (n > 16384)
+    for (int i = 0; i < n; i++) {
+      size_t const p = (size_t)idx[i];
+      double gx = g[i], gy = g[stride + i], gz = g[2 * stride + i];
+      if (rot) {
+        double const tx = Rinv[0][0] * gx + Rinv[0][1] * gy + Rinv[0][2] * gz;
+        double const ty = Rinv[1][0] * gx + Rinv[1][1] * gy + Rinv[1][2] * gz;
+        double const tz = Rinv[2][0] * gx + Rinv[2][1] * gy + Rinv[2][2] * gz;
+        gx = tx; gy = ty; gz = tz;
+      }
+      h_proxy_force[3 * p] += force * gx;
+      h_proxy_force[3 * p + 1] += force * gy;
+      h_proxy_force[3 * p + 2] += force * gz;
+    }
+    std::string err;
+    int rc = fit_scatter_force_host(G.fit, force, h_proxy_force, n_proxy, s, err);
+    if (rc) return fail(h, rc, err);
+  }
+  return B200CV_OK;
+}
+
+}  // extern "C"
