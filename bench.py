@@ -17,8 +17,13 @@ all-reduce when sharded]) -> value() -> apply_force (scatter).  Workload (BASELI
 
 One JSON line is printed by rank 0.  `value` times device-resident inputs; `e2e` goes
 through the host-buffer C-ABI step (H2D of the proxy positions and D2H of value +
-gradients inside the timed region).  roofline: FP64-compute bound:
-achieved = pair-evals/s x 39 algorithmic flop, peak = DFMA microbenchmark run live here.
+gradients inside the timed region; sharded runs move 1/N of both per rank).  roofline:
+FP64-compute bound: achieved = pair-evals/s x 39 algorithmic flop, peak =
+DFMA microbenchmark run live here.  Positions move between timed steps (Gaussian displacements
+of 0.05 A; the fitted solute of c4 also gets a new rigid rotation), outside the timed events.
+`parity` (after the timed region, not timed): gradients of sampled group1 rows and group2
+columns, value + all gradients of a 1024-row slab run through the same sharding, and the
+forces of both routes, against the CPU oracle -- max-norm relative errors.
 """
 import argparse
 import json
@@ -65,6 +70,8 @@ WORKLOADS["tric"] = dict(kind="coordNum", n1=10000, n2=100000, cutoff3=(4.0, 4.0
                          freq=100, cell="dodecahedron",
                          name="coordNum 10k x 100k iso r0=4 n=6 m=12 in a rhombic-dodecahedron "
                               "(triclinic) cell")
+for _k, _w in WORKLOADS.items():
+    _w["key"] = _k
 METRIC = "coordNum pair-evals/sec (value+grad)"
 UNIT = "pair-evals/s"
 
@@ -93,7 +100,12 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_run(w, proxy, i1, i2, budget_s=12.0, threads=None):
+# group1 rows of the slab the CPU arm is timed on (against all of group2), per workload: the
+# same slab for `--impl reference` and for the in-arm `cpu_baseline`
+CPU_SLAB_ROWS = {"c5": 960, "c2": 1000, "c4": 1920, "c3": 12000}
+
+
+def cpu_run(w, proxy, i1, i2, budget_s=12.0, threads=None, one_core=False):
     """Time the CPU path on a slab of group1 rows against all of group2 and scale linearly.
     Returns dict(value=pairs/s, cores, kind, sample)."""
     threads = threads or host_cores()
@@ -102,42 +114,39 @@ def cpu_run(w, proxy, i1, i2, budget_s=12.0, threads=None):
     n2 = w["n2"] if w["kind"] != "selfCoordNum" else w["n1"]
     if ref_driver.exists():
         try:
-            return cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver)
+            out = cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver)
+            if one_core:
+                # also the reference's real behaviour, one component on
+                # one thread, on 1/threads of the slab
+                one = cpu_run_reference(w, proxy, i1, i2, budget_s, 1, ref_driver,
+                                        rows_scale=1.0 / threads)
+                out["value_1core"] = one["value"]
+                out["sample_1core"] = one["sample"]
+            return out
         except Exception as e:  # fall through to the port, say why
             sys.stderr.write(f"[bench] oracle/_ref/ref_driver failed ({e}); using the C port\n")
     from tests import oracle_lib as O
     p = O.make_params(w["cutoff3"], 6, 12, 0.0)
     pos2 = proxy[i2] if i2 is not None else proxy[i1]
-
-    def slab(rows):
-        t0 = time.perf_counter()
-        O.coordnum(p, proxy[i1][:rows], pos2, omp=threads)
-        return time.perf_counter() - t0
-
-    rows = max(min(n1, (2 * 10 ** 8) // max(n2, 1)), 1)  # calibration: ~2e8 pairs
-    t = slab(rows)
-    rate = rows * n2 / t
-    rows2 = int(max(min(n1, budget_s * rate / n2), rows))
-    t2 = slab(rows2)
-    return dict(value=rows2 * n2 / t2, unit=UNIT, cores=threads, kind="port",
-                sample=f"{rows2} rows of group1 x all {n2} atoms of group2 "
-                       f"({rows2 * n2:.3g} pair-evals, {t2:.1f} s), OpenMP over rows, "
+    rows = min(n1, CPU_SLAB_ROWS.get(w.get("key"), 960))
+    t0 = time.perf_counter()
+    O.coordnum(p, proxy[i1][:rows], pos2, omp=threads)
+    t = time.perf_counter() - t0
+    return dict(value=rows * n2 / t, unit=UNIT, cores=threads, kind="port",
+                sample=f"{rows} rows of group1 x all {n2} atoms of group2 "
+                       f"({rows * n2:.3g} pair-evals, {t:.1f} s), OpenMP over rows, "
                        "scaled linearly")
 
 
-def cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver):
+def cpu_run_reference(w, proxy, i1, i2, budget_s, threads, ref_driver, rows_scale=1.0):
     """oracle/_ref/ref_driver: the unmodified reference library driven through
     colvarmodule::calc() with group1 split into `threads` coordNum components under
     `smp cvcs` (the reference's documented way to use several cores)."""
     n1 = w["n1"]
     n2 = w["n2"] if w["kind"] != "selfCoordNum" else w["n1"]
-    # the driver runs 1 warm-up + 2 timed calc() steps: size the slab so that the three of
-    # them take about budget_s at ~4.5e7 pair-evals/s per core
-    rate_guess = 4.5e7 * (threads if w["kind"] != "selfCoordNum" else 1)
-    per_step = budget_s / 3.0
-    rows = int(max(min(n1, per_step * rate_guess / n2), threads))
-    if w["kind"] == "selfCoordNum":
-        rows = min(n1, int((2 * per_step * rate_guess) ** 0.5))
+    # the driver runs 1 warm-up + 2 timed calc() steps on a fixed slab (about 0.5-1 s per calc
+    # on 16 cores)
+    rows = int(max(min(n1, CPU_SLAB_ROWS.get(w.get("key"), 960) * rows_scale), threads))
     with tempfile.TemporaryDirectory() as td:
         inp = Path(td) / "in.bin"
         if w["kind"] == "selfCoordNum":
@@ -230,29 +239,43 @@ class ClockSampler:
         return out
 
 
+def config_block(w, npairs, P, world, last_value, timing):
+    return {"workload": w["name"], "pairs_per_step": npairs, "proxy_atoms": int(P),
+            "sharding": (f"group1 blocks over {world} GPU(s), group2 replicated, ncclAllReduce "
+                         "of [value|grad1|grad2]") if world > 1 else "none",
+            "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+            "positions": "Gaussian displacements of 0.05 A between timed steps (outside the "
+                         "timed events)",
+            "timing": timing, "last_value": last_value}
+
+
 def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     proxy, i1, i2 = make_inputs(w)
     steps = max(args.steps, 1)
-    per = max(4.0, min(30.0, 90.0 / (steps + args.warmup)))
     vals = []
     info = None
     for k in range(args.warmup + steps):
-        info = cpu_run(w, proxy, i1, i2, budget_s=per)
+        # every step times the same fixed slab as the b200 arm's cpu_baseline (CPU_SLAB_ROWS);
+        # the last one also measures the one-core rate
+        info = cpu_run(w, proxy, i1, i2, one_core=(k == args.warmup + steps - 1))
         if k >= args.warmup:
             vals.append(info["value"])
     value = float(np.mean(vals))
     npairs = pairs_of(w)
+    P = proxy.shape[0]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * npairs / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "pairs_per_step": npairs,
-                   "note": "CPU path timed on a bounded sample and scaled linearly to the "
-                           "full step; ms_per_step is the extrapolated full-step time"},
+        # same key set as the b200 arm's config (the driver compares them)
+        "config": config_block(w, npairs, P, 1, None,
+                               timing="host wall clock inside oracle/_ref/ref_driver around "
+                                      "colvarmodule::calc(), bounded slab scaled linearly to the "
+                                      "full step (ms_per_step is that extrapolation)"),
         "cpu_baseline": dict(info, value=value),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -261,9 +284,38 @@ def run_reference_arm(args, w):
     return 0
 
 
+class Mover:
+    """Moves the proxy positions on the device between timed steps: Gaussian
+    displacements of sigma = 0.05 A per step for every atom; a fitted solute (c4) additionally
+    gets a fresh small rigid rotation about its centre, so that the fit has new work every
+    frame.  torch is plumbing here (random numbers + one small matmul), outside the timed events."""
+
+    def __init__(self, torch, d_pos, i1, fitted, seed=4321, sigma=0.05):
+        self.torch, self.d_pos, self.sigma, self.fitted = torch, d_pos, sigma, fitted
+        self.gen = torch.Generator(device=d_pos.device)
+        self.gen.manual_seed(seed)
+        self.i1 = torch.tensor(np.asarray(i1, dtype=np.int64), device=d_pos.device)
+
+    def step(self):
+        t = self.torch
+        self.d_pos += self.sigma * t.randn(self.d_pos.shape, generator=self.gen,
+                                           dtype=self.d_pos.dtype, device=self.d_pos.device)
+        if self.fitted:
+            w = 0.02 * t.randn(3, generator=self.gen, dtype=self.d_pos.dtype,
+                               device=self.d_pos.device)
+            K = t.zeros((3, 3), dtype=self.d_pos.dtype, device=self.d_pos.device)
+            K[0, 1], K[0, 2], K[1, 2] = -w[2], w[1], -w[0]
+            K = K - K.T
+            R = t.linalg.matrix_exp(K)
+            x = self.d_pos[:, self.i1]
+            c = x.mean(dim=1, keepdim=True)
+            self.d_pos[:, self.i1] = R @ (x - c) + c
+
+
 def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     """Device-resident step of another BASELINE configuration: K timed steps, CUDA events, L2
-    flushed between steps.  Returns a small dict (pair-evals/s, ms/step, roofline fraction)."""
+    flushed and positions moved between steps.  Returns a small dict (pair-evals/s, ms/step,
+    roofline fraction)."""
     w = WORKLOADS[key]
     proxy, i1, i2 = make_inputs(w)
     dev = torch.device("cuda", device)
@@ -283,16 +335,18 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     d_force = torch.zeros_like(d_pos)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    mover = Mover(torch, d_pos, i1, fitted)
     if w["tol"] > 0:
         # two full pair-list cycles, after a warm-up that holds the first rebuild (all-pairs
-        # sweep: the list is not known to be sparse yet) and the first cell-list rebuild
-        # (one-time costs: lazy loading of the sort and cell kernels, scratch allocation)
+        # sweep: the list is not known to be sparse yet) and the first sparse rebuild
+        # (one-time costs: lazy loading of the sort and list kernels, scratch allocation)
         steps = 2 * w["freq"]
         warmup = w["freq"] + 3
     ev, kev = [], []
     v = 0.0
     for s in range(warmup + steps):
         flush.fill_(s & 0xFF)
+        mover.step()
         e0, k0, k1, e1 = (torch.cuda.Event(True) for _ in range(4))
         e0.record(stream)
         cv.read_data(d_pos, stream)
@@ -313,12 +367,19 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     npairs = pairs_of(w)
     out = {"workload": w["name"], "pairs_per_step": npairs, "steps": steps, "warmup": warmup,
            "value": npairs * len(ms) / (sum(ms) * 1e-3), "unit": UNIT,
-           "ms_per_step": float(np.mean(ms)), "last_value": v}
+           "ms_per_step": float(np.mean(ms)), "last_value": v,
+           "positions": "moved by 0.05 A (Gaussian) before every step"}
     if w["tol"] > 0:
         reb = [m for s, m in kms if s % w["freq"] == 0]
         lst = [m for s, m in kms if s % w["freq"] != 0]
+        st = cv.pairlist_stats()
         out["pairlist"] = {"rebuild_ms": float(np.mean(reb)), "list_ms": float(np.mean(lst)),
-                           "listed_pairs": int(len(cv.pairlist()))}
+                           "listed_pairs": int(st["pairs"]),
+                           "form": {0: "entries", 1: "entries in cell order",
+                                    2: "masked cluster tiles"}.get(st["form"], "none"),
+                           "tiles": int(st["tiles"]),
+                           "tile_fill": (st["pairs"] - st["entries"]) / (1024.0 * st["tiles"])
+                           if st["tiles"] else None}
         kern = float(np.mean(reb))
     else:
         kern = float(np.mean([m for _, m in kms]))
@@ -327,6 +388,7 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
         gev = []
         for s in range(warmup + steps):
             flush.fill_(s & 0xFF)
+            mover.step()
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
             e0.record(stream)
             cv.step(d_pos, step=s, gradients=True, stream=stream)
@@ -341,6 +403,10 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
     flop = w.get("flop_per_pair", synth.FLOP_PER_PAIR_VALUE_GRAD)
     out["flop_per_pair"] = flop
     out["roofline_frac"] = npairs / (kern * 1e-3) * flop / 1e12 / fp64_tflops
+    if fitted:
+        out["validated"] = ("tests/test_gpu_baseline_sizes.py::test_c4_aniso_fitted_10k_x_500k: "
+                            "geometry 1e-13 vs the oracle's fit, every pair 1e-12 on the device's "
+                            "fitted positions, fit gradients / forces 1e-11")
     if w.get("cell"):
         # the 39-flop contract figure is the open-system pair; in a triclinic cell the reference
         # adds a 27-image search per pair (~600 flop as written, ~230 instructions here), so a
@@ -349,13 +415,116 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
         out["note"] = ("pair-evals/s in a triclinic cell (image search per pair); open system on "
                        "the same kernel: see c4 / the headline")
     if w["tol"] > 0:
-        # a pair list exists to NOT evaluate most pairs (rebuilds go through a cell list, the
+        # a pair list exists to NOT evaluate most pairs (rebuilds go through a cell grid, the
         # other steps walk the list): pair-evals/s counts the reference's pairs, and a flop
         # roofline over them would mean nothing
         out["roofline_frac"] = None
         out["note"] = ("value counts the reference's N(N-1)/2 pairs per step; rebuilds "
-                       "evaluate cell-list candidates only, list steps the listed pairs")
+                       "evaluate grid candidates only, list steps the listed pairs")
     cv.close()
+    return out
+
+
+def ncu_traffic(key, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this
+    workload (profiles/*_sweep_*ncu_raw.csv of the newest round), or (None, None)."""
+    if key != "c5" or world != 1:
+        return None, None
+    import csv
+    import glob
+    for path in sorted(glob.glob(str(ROOT / "profiles" / "r0*_c5_sweep_*ncu_raw.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = next(r for r in rows if "Metric Name" in r)
+            mi, vi, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name")
+            ui = hdr.index("Metric Unit")
+            tot = 0.0
+            for r in rows:
+                if len(r) > vi and "sweep_kernel" in r[ki] and r[mi] in ("dram__bytes_read.sum",
+                                                                       "dram__bytes_write.sum"):
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1.0)
+                    tot += float(r[vi].replace(",", "")) * scale
+            if tot > 0:
+                return tot, str(Path(path).relative_to(ROOT))
+        except Exception:
+            continue
+    return None, None
+
+
+def parity_block(cb, torch, dist, w, proxy, i1, i2, cv, dev, world, rank, local_rank, k_force):
+    """After the timed region (not timed): the sharded run against the CPU oracle on the
+    workload's initial positions.  (1) gradients of 256 group1 rows spread over all ranks'
+    blocks and of 64 group2 columns of the benchmarked component, and the forces both routes
+    scatter for them; (2) a 1024-row slab of group1 against all of group2 as a second component
+    with the same sharding: value, all gradients of both groups.  Max-norm relative errors.
+    Collective: every rank takes part, rank 0 runs the oracle and returns the dict."""
+    from tests import oracle_lib as O
+    if w["kind"] != "coordNum" or w["tol"] > 0 or w.get("fit"):
+        return None
+    n1, n2 = len(i1), len(i2)
+    nthr = host_cores()
+    p = O.make_params(w["cutoff3"], 6, 12, 0.0)
+
+    def rel(a, b):
+        return float(np.max(np.abs(np.asarray(a) - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    d_pos = torch.tensor(np.ascontiguousarray(proxy.T), device=dev)
+    d_force = torch.zeros_like(d_pos)
+    cv.read_data(d_pos)
+    cv.calc_value(step=1, gradients=True)
+    v = cv.value()
+    fa = k_force * (v - 0.1)
+    cv.apply_force(fa, d_force)
+    torch.cuda.synchronize()
+    # host-buffer route: the ranks' force arrays add up to the full force
+    h_pos = torch.tensor(proxy).pin_memory()
+    h_force = torch.zeros_like(h_pos).pin_memory()
+    vh = cv.calc_host(h_pos, step=1)
+    cv.apply_force_host(k_force * (vh - 0.1), h_force)
+    hf = h_force.to(dev)
+    if world > 1:
+        dist.all_reduce(hf)
+    # the slab as a component of its own, sharded like the benchmarked one
+    rows_slab = np.unique(np.linspace(0, n1 - 1, 1024).astype(np.int64))
+    slab = cb.CoordNum(w["kind"], i1[rows_slab], i2, cutoff3=w["cutoff3"], device=local_rank)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(cb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        slab.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    slab.read_data(d_pos)
+    slab.calc_value(step=1, gradients=True)
+    sv = slab.value()
+    out = None
+    if rank == 0:
+        rows = np.unique(np.linspace(0, n1 - 1, 256).astype(np.int64))
+        cols = np.unique(np.linspace(0, n2 - 1, 64).astype(np.int64))
+        pos1, pos2 = proxy[i1], proxy[i2]
+        _, og1, _ = O.coordnum(p, pos1[rows], pos2, omp=nthr)
+        _, _, og2 = O.coordnum(p, pos1, pos2[cols], omp=nthr)
+        g1, g2 = cv.gradients(1), cv.gradients(2)
+        f = d_force.cpu().numpy().T
+        fh = hf.cpu().numpy()
+        errs = {
+            "grad1_rows": rel(g1[rows], og1), "grad2_cols": rel(g2[cols], og2),
+            "force_rows": rel(f[i1[rows]], fa * og1), "force_cols": rel(f[i2[cols]], fa * og2),
+            "e2e_force_rows": rel(fh[i1[rows]], k_force * (vh - 0.1) * og1),
+            "e2e_force_cols": rel(fh[i2[cols]], k_force * (vh - 0.1) * og2),
+            "e2e_value_vs_device": abs(vh - v) / abs(v),
+        }
+        sov, sog1, sog2 = O.coordnum(p, pos1[rows_slab], pos2, omp=nthr)
+        errs["slab_value"] = abs(sv - sov) / abs(sov)
+        errs["slab_grad1"] = rel(slab.gradients(1), sog1)
+        errs["slab_grad2"] = rel(slab.gradients(2), sog2)
+        out = {"max_rel": max(errs.values()), "tolerance": 1e-12, "errors": errs,
+               "rows": int(len(rows)), "cols": int(len(cols)), "slab_rows": int(len(rows_slab)),
+               "oracle": "oracle/liboracle.so (OpenMP row-parallel form, scalar summed in "
+                         "extended precision), max|a-b| / max|b| per array",
+               "positions": "the workload's initial frame"}
+    else:
+        slab.gradients(1)  # same calls on every rank (they synchronise the stream only)
+    slab.close()
     return out
 
 
@@ -370,6 +539,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
 
@@ -416,9 +586,11 @@ def main():
     d_force = torch.zeros_like(d_pos)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
     stream = torch.cuda.current_stream()
+    mover = Mover(torch, d_pos, i1, fitted)  # same seed on every rank: identical frames
     k_force = -0.004
 
     def step(s):
+        mover.step()
         cv.read_data(d_pos, stream)
         cv.calc_value(step=s, gradients=True, stream=stream)
         if fitted:
@@ -451,6 +623,7 @@ def main():
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.fill_(s & 0xFF)  # evict L2 between timed iterations (outside the events)
+        mover.step()           # new frame (outside the events)
         e0, ek0, ek1, e1 = ev[s]
         e0.record(stream)
         cv.read_data(d_pos, stream)
@@ -501,13 +674,29 @@ def main():
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        n_grad = 3 * (len(i1) + (len(i2) if i2 is not None else 0))
+        # bytes each rank moves per step: its block of the AoS position array up (the other
+        # blocks arrive GPU to GPU over NVLink), its share of every group's gradients down
+        per = (P + world - 1) // world
+        share = sum((n * (rank + 1)) // world - (n * rank) // world
+                    for n in (len(i1), len(i2) if i2 is not None else 0))
         e2e = {"value": npairs * args.steps / float(t_e2e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(P * 24), "d2h_bytes_per_step": int(n_grad * 8 + 8),
+               "h2d_bytes_per_step": int(min(per, P) * 24), "d2h_bytes_per_step": int(share * 24 + 8),
+               "bytes_are": "per rank" if world > 1 else "total",
                "ms_per_step": 1e3 * float(t_e2e.item()) / args.steps,
                "timing": "host wall clock around calc_host + apply_force_host (each call "
                          "synchronises), max over ranks"}
+        if world > 1:
+            e2e["exchange"] = ("each rank uploads 1/N of the position array, ncclAllGather over "
+                               "NVLink; forces: rank r scatters its 1/N share of every group")
         assert hf is not None
+
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(cb, torch, dist, w, proxy, i1, i2, cv, dev, world, rank,
+                                  local_rank, k_force)
+        except Exception as e:  # never lose the bench line to the checker
+            parity = {"error": str(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -529,29 +718,29 @@ def main():
     if split and not split["rebuild_ms"]:
         achieved_tflops = float("nan")
     peak = fp64_tflops * world
+    traffic, traffic_src = ncu_traffic(args.workload, world)
     line = {
         "metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": w["name"], "pairs_per_step": npairs, "proxy_atoms": int(P),
-                   "sharding": f"group1 blocks over {world} GPU(s), group2 replicated, "
-                               "ncclAllReduce of [value|grad1|grad2]" if world > 1 else "none",
-                   "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                   "timing": "CUDA events on the launching stream per step, summed; max over "
-                             "ranks", "last_value": value},
+        "config": config_block(w, npairs, P, world, value,
+                               timing="CUDA events on the launching stream per step, summed; "
+                                      "max over ranks"),
         "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved_tflops / peak,
-                     # DRAM bytes per sweep launch from the committed ncu capture
-                     # (profiles/r01_c5_sweep_v3_ncu_raw.csv: 54.44 MB read + 0.51 MB written;
-                     # algorithmic input 26.4 MB -- the kernel is FP64-bound, not HBM-bound)
-                     "traffic": 54941952 if (args.workload == "c5" and world == 1) else None,
+                     # DRAM bytes per sweep launch, read from the committed ncu capture named in
+                     # traffic_source (null when there is none for this workload / rank count)
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "sweep_kernel (+ exact queue with the final sum) = calc_value",
                      "kernel_ms": kern_ms_avg,
                      "flop_per_pair": synth.FLOP_PER_PAIR_VALUE_GRAD,
                      "peak_source": "DFMA microbenchmark run live in this process "
                                     "(b200cv_fp64_peak, 250 ms sustained) x n_gpus; "
                                     "MEASURED_PEAKS.json has no FP64 entry"},
+        # for the driver: what MEASURED_PEAKS.json lacks (dense FP64 FMA, one GPU, TFLOP/s)
+        "measured_peak_fp64": {"tflops": fp64_tflops, "how": "b200cv_fp64_peak: 16 dependent DFMA "
+                               "chains per thread, 8 CTAs x 256 threads per SM, 250 ms"},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "wall_s": t_wall,
@@ -571,9 +760,11 @@ def main():
         line["roofline"]["note"] = roof_note
     if e2e:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity"] = parity
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_run(w, proxy, i1, i2, budget_s=12.0)
+            line["cpu_baseline"] = cpu_run(w, proxy, i1, i2, one_core=True)
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)[:200]}
     if world == 1 and args.workload == "c5" and not args.no_others:

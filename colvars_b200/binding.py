@@ -70,7 +70,7 @@ SYMBOLS = [
     "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
-    "b200cv_pairlist_export", "b200cv_last_stats", "b200cv_kernel_launches", "b200cv_comm_unique_id",
+    "b200cv_pairlist_export", "b200cv_pairlist_stats", "b200cv_last_stats", "b200cv_kernel_launches", "b200cv_comm_unique_id",
     "b200cv_comm_init", "b200cv_set_shard", "b200cv_plan_items", "b200cv_fp64_peak", "b200cv_selftest_rcp",
 ]
 
@@ -118,6 +118,8 @@ def load():
     L.b200cv_get_tolerance_l2_max.argtypes = [H, _dp]
     L.b200cv_pairlist_count.argtypes = [H, C.POINTER(sz)]
     L.b200cv_pairlist_export.argtypes = [H, C.POINTER(C.c_uint64), sz]
+    L.b200cv_pairlist_stats.argtypes = [H, _ip, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz),
+                                        C.POINTER(sz)]
     L.b200cv_last_stats.argtypes = [H, _ip, C.POINTER(sz)]
     L.b200cv_kernel_launches.argtypes = []
     L.b200cv_kernel_launches.restype = C.c_ulonglong
@@ -369,6 +371,14 @@ class CoordNum:
         self._check(self._L.b200cv_pairlist_export(
             self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size))
         return out[:n.value]
+
+    def pairlist_stats(self):
+        """dict(form, pairs, entries, tile_units, tiles); see b200cv_pairlist_stats."""
+        form = C.c_int()
+        v = [C.c_size_t() for _ in range(4)]
+        self._check(self._L.b200cv_pairlist_stats(self._h, C.byref(form), *[C.byref(x) for x in v]))
+        return dict(form=form.value, pairs=v[0].value, entries=v[1].value,
+                    tile_units=v[2].value, tiles=v[3].value)
 
     def last_stats(self):
         k = C.c_int()

@@ -304,12 +304,12 @@ int b200cv_create(const b200cv_config *cfg, b200cv_cvc **out)
     }                                                                                         \
   } while (0)
   CREATE_OK(cudaSetDevice(c.device));
-  CREATE_OK(cudaHostAlloc(&h->h_value, sizeof(double), cudaHostAllocMapped));
+  CREATE_OK(cudaHostAlloc(&h->h_value, 4 * sizeof(double), cudaHostAllocMapped));
   CREATE_OK(cudaHostGetDevicePointer(&h->h_value_dev, h->h_value, 0));
-  CREATE_OK(cudaHostAlloc(&h->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+  CREATE_OK(cudaHostAlloc(&h->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
   CREATE_OK(cudaHostGetDevicePointer(&h->h_counters_dev, h->h_counters, 0));
-  h->h_counters[0] = h->h_counters[1] = h->h_counters[2] = h->h_counters[3] = 0;
-  *h->h_value = 0.0;
+  for (int k = 0; k < 8; k++) h->h_counters[k] = 0;
+  for (int k = 0; k < 4; k++) h->h_value[k] = 0.0;
   CREATE_OK(cudaHostAlloc(&h->h_mode, sizeof(int), cudaHostAllocMapped));
   CREATE_OK(cudaHostGetDevicePointer(&h->h_mode_dev, h->h_mode, 0));
   *h->h_mode = 1;
@@ -347,6 +347,7 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_pl_center);
   free_dev(h->d_items);
   cells_free(h->cells);
+  tiles_free(h->tiles);
   free_dev(h->d_stage_pos);
   if (h->h_value) cudaFreeHost(h->h_value);
   if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -434,6 +435,8 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
         unsigned long long const pairs = h->self() ? n1 * (n1 - 1) / 2 : n1 * n2;
         CUDA_OK(h, cells_setup(h->cells, (int)n2));
         h->cells_ready = true;
+        CUDA_OK(h, tiles_setup(h->tiles, h->self() ? 0 : (int)n1, (int)n2));
+        h->tiles_ready = true;
         rc = ensure_pairlist_capacity(h, std::min<unsigned long long>(pairs, 64ull * (n1 + n2)));
         if (rc) return rc;
       }
@@ -575,13 +578,18 @@ int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, voi
   if (!h) return B200CV_BUG_ERROR;
   if (!h->data_read) return fail(h, B200CV_BUG_ERROR, "calc_value before read_data");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  // the previous evaluation may have left a new list (or an overflow) nobody has looked at
+  if (h->unchecked) CUDA_OK_RC(sync_and_check(h));
   int const flags = calc_flags(h, step_relative, gradients);
   h->async_eval = false;
   h->gated = false;
+  CUDA_OK_RC(prepare_calc(h, flags));
   h->last_stream = (cudaStream_t)stream;
   h->last_step = step_relative;
   h->last_flags = flags;
   h->have_calc = true;
+  h->fit_after_calc = false;
+  h->unchecked = true;
   return enqueue_calc(h, flags, h->last_stream);
 }
 
@@ -597,6 +605,7 @@ int b200cv_calc_fit_gradients(b200cv_cvc *h, void *stream)
     int rc = fit_calc_gradients(G.fit, G.d_grad, G.stride, G.n, (cudaStream_t)stream, err);
     if (rc) return fail(h, rc, err);
   }
+  h->fit_after_calc = true;
   return B200CV_OK;
 }
 
@@ -619,6 +628,9 @@ int b200cv_apply_force(b200cv_cvc *h, double force, double *d_proxy_force, size_
   if (!h) return B200CV_BUG_ERROR;
   if (!h->have_calc) return fail(h, B200CV_BUG_ERROR, "apply_force before calc_value");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  // gradients of an evaluation whose queues overflowed are incomplete: never scatter them
+  // unchecked (a no-op after b200cv_value; captured evaluations are checked there)
+  if (h->unchecked && !h->async_eval) CUDA_OK_RC(sync_and_check(h));
   cudaStream_t s = (cudaStream_t)stream;
   int const ng = h->self() ? 1 : 2;
   bool const one_launch = ng == 2;
@@ -650,6 +662,7 @@ static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2
   if (!d_pos1 || (!h->self() && !d_pos2)) return fail(h, B200CV_BUG_ERROR, "null positions");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (h->unchecked && sync) CUDA_OK_RC(sync_and_check(h));
   int rc = reset_gradients(h, s);
   if (rc) return rc;
   Group &G1 = h->g[0];
@@ -669,6 +682,9 @@ static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2
   h->data_read = true;
   h->async_eval = !sync;
   h->gated = !sync && (flags & B200CV_EF_USE_PAIRLIST);
+  h->fit_after_calc = false;
+  h->unchecked = true;
+  if (sync) CUDA_OK_RC(prepare_calc(h, flags));
   rc = enqueue_calc(h, flags, s);
   if (rc) return rc;
   if (sync) {
@@ -753,6 +769,13 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
     h->epoch++;
     CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * want));
     h->pl_cap = want;
+  }
+  if (tiles_usable(h) && sparse_list(h)) {
+    unsigned const need = (unsigned)std::min(4.0e9, std::ceil(headroom * (double)tile_units_estimate(h)));
+    if (need > h->tiles.cap_units) {
+      h->epoch++;
+      CUDA_OK(h, tiles_reserve(h->tiles, need));
+    }
   }
   h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1);
                         // pl_n stays: it tells the capture whether the list is sparse
@@ -908,6 +931,63 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
     for (size_t k = 0; k < count; k++) out[k] = k;
     return B200CV_OK;
   }
+  // canonical index of the reference's dense bool array
+  // (src/colvarcomp_coordnums.cpp:197-238 / :481-520)
+  auto canonical = [&](unsigned long long i, unsigned long long j) {
+    if (h->self() && i > j) std::swap(i, j);
+    return h->self() ? i * (2 * n1 - i - 1) / 2 + (j - i - 1) : i * n2 + j;
+  };
+  if (h->pl_tiles) {
+    // tile form (tiles.cuh): mask bits of every unit + the extras, all in sorted positions
+    TileBuffers &B = h->tiles;
+    TileSide &J = B.side[1];
+    TileSide &I = h->self() ? J : B.side[0];
+    unsigned counts[8];
+    CUDA_OK(h, cudaMemcpy(counts, B.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
+    size_t const units = std::min(counts[6], B.cap_units);
+    std::vector<int4> hdr(units);
+    std::vector<int> tj(units * TILE_UNIT * 32);
+    std::vector<unsigned> tm(units * TILE_UNIT * 32);
+    std::vector<int> oi(I.n), oj(J.n);
+    std::vector<unsigned long long> ent((size_t)h->pl_entries);
+    if (units) {
+      CUDA_OK(h, cudaMemcpy(hdr.data(), B.d_unit_hdr, sizeof(int4) * units, cudaMemcpyDeviceToHost));
+      CUDA_OK(h, cudaMemcpy(tj.data(), B.d_tile_j, sizeof(int) * tj.size(), cudaMemcpyDeviceToHost));
+      CUDA_OK(h, cudaMemcpy(tm.data(), B.d_tile_m, sizeof(unsigned) * tm.size(),
+                            cudaMemcpyDeviceToHost));
+    }
+    CUDA_OK(h, cudaMemcpy(oi.data(), I.d_sorted, sizeof(int) * oi.size(), cudaMemcpyDeviceToHost));
+    CUDA_OK(h, cudaMemcpy(oj.data(), J.d_sorted, sizeof(int) * oj.size(), cudaMemcpyDeviceToHost));
+    if (!ent.empty()) {
+      CUDA_OK(h, cudaMemcpy(ent.data(), h->d_pl, sizeof(unsigned long long) * ent.size(),
+                            cudaMemcpyDeviceToHost));
+    }
+    size_t k = 0;
+    for (size_t u = 0; u < units; u++) {
+      int const p0 = hdr[u].x, cnt = hdr[u].y, nt = hdr[u].z;
+      for (int t = 0; t < nt; t++) {
+        size_t const base = (u * TILE_UNIT + (size_t)t) * 32;
+        for (int lane = 0; lane < cnt; lane++) {
+          unsigned m = tm[base + lane];
+          for (int bit = 0; m; bit++, m >>= 1) {
+            if (!(m & 1u)) continue;
+            int const jp = tj[base + ((lane + bit) & 31)];
+            if (jp < 0 || k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent tile list");
+            out[k++] = canonical((unsigned long long)oi[(size_t)p0 + lane],
+                                 (unsigned long long)oj[(size_t)jp]);
+          }
+        }
+      }
+    }
+    for (unsigned long long e : ent) {
+      if (k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent tile list");
+      out[k++] = canonical((unsigned long long)oi[(size_t)(e >> 32)],
+                           (unsigned long long)oj[(size_t)(e & 0xffffffffull)]);
+    }
+    if (k != count) return fail(h, B200CV_BUG_ERROR, "tile list does not add up to its pair count");
+    std::sort(out, out + count);
+    return B200CV_OK;
+  }
   std::vector<unsigned long long> ent(count);
   CUDA_OK(h, cudaMemcpy(ent.data(), h->d_pl, sizeof(unsigned long long) * count,
                         cudaMemcpyDeviceToHost));
@@ -927,9 +1007,7 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
         if (i > j) std::swap(i, j);  // listed by the row that comes first in cell order
       }
     }
-    // canonical index of the reference's dense bool array
-    // (src/colvarcomp_coordnums.cpp:197-238 / :481-520)
-    out[k] = h->self() ? i * (2 * n1 - i - 1) / 2 + (j - i - 1) : i * n2 + j;
+    out[k] = canonical(i, j);
   }
   std::sort(out, out + count);
   return B200CV_OK;
@@ -940,6 +1018,33 @@ int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs)
   if (!h) return B200CV_BUG_ERROR;
   if (kernel_launches) *kernel_launches = h->launches;
   if (exact_pairs) *exact_pairs = h->exact_pairs;
+  return B200CV_OK;
+}
+
+int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entries,
+                          size_t *tile_units, size_t *tiles)
+{
+  if (!h) return B200CV_BUG_ERROR;
+  if (!(h->cfg.tolerance > 0)) return fail(h, B200CV_INPUT_ERROR, "no pair list (tolerance = 0)");
+  if (h->have_calc) CUDA_OK_RC(sync_and_check(h));
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  size_t units = 0, ntiles = 0;
+  if (h->pl_valid && h->pl_tiles) {
+    unsigned counts[8];
+    CUDA_OK(h, cudaMemcpy(counts, h->tiles.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
+    units = std::min(counts[6], h->tiles.cap_units);
+    std::vector<int4> hdr(units);
+    if (units) {
+      CUDA_OK(h, cudaMemcpy(hdr.data(), h->tiles.d_unit_hdr, sizeof(int4) * units,
+                            cudaMemcpyDeviceToHost));
+    }
+    for (auto const &u : hdr) ntiles += (size_t)u.z;
+  }
+  if (form) *form = !h->pl_valid ? -1 : (h->pl_tiles ? 2 : (h->pl_sorted ? 1 : 0));
+  if (pairs) *pairs = (size_t)h->pl_n;
+  if (entries) *entries = (size_t)h->pl_entries;
+  if (tile_units) *tile_units = units;
+  if (tiles) *tiles = ntiles;
   return B200CV_OK;
 }
 

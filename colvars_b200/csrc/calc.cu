@@ -93,6 +93,42 @@ bool rebuild_with_cells(const b200cv_cvc *h, int flags)
          cells_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
 }
 
+// the tile form of the list (tiles.cuh) applies: an open system whose list a previous rebuild
+// has shown to be sparse
+bool tiles_usable(const b200cv_cvc *h)
+{
+  return h->tiles_ready && h->d_pl && h->pl_n > 0 && h->P.bc_type == 0 &&
+         !(h->center1() || h->center2()) && std::getenv("B200CV_NO_TILES") == nullptr &&
+         std::getenv("B200CV_NO_CELLS") == nullptr;
+}
+
+bool rebuild_with_tiles(const b200cv_cvc *h, int flags)
+{
+  return (flags & B200CV_EF_REBUILD_PAIRLIST) && (flags & B200CV_EF_USE_PAIRLIST) &&
+         tiles_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
+}
+
+// units the tile list of the next rebuild may need.  A tile of a homogeneous system is about a
+// quarter full (bounding box + cut-off against the cut-off sphere), i.e. pairs / 1024 units of
+// four tiles, plus one partly filled unit per cluster; a guess that turns out too small costs one
+// redo of the step (post_sync), not a wrong result.
+unsigned tile_units_estimate(const b200cv_cvc *h)
+{
+  unsigned long long const units = h->pl_n / 400ull + (unsigned long long)h->g[0].n / 16ull + 4096ull;
+  return (unsigned)std::min<unsigned long long>(units, 1ull << 28);
+}
+
+int prepare_calc(b200cv_cvc *h, int flags)
+{
+  if (!(flags & B200CV_EF_USE_PAIRLIST)) return B200CV_OK;
+  bool const tiles_next = h->gated ? (tiles_usable(h) && sparse_list(h)) : rebuild_with_tiles(h, flags);
+  if (tiles_next && h->tiles.cap_units == 0) {
+    h->epoch++;
+    CUDA_OK(h, tiles_reserve(h->tiles, tile_units_estimate(h)));
+  }
+  return B200CV_OK;
+}
+
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need)
 {
   if (need <= h->pl_cap && h->d_pl) return B200CV_OK;
@@ -129,6 +165,13 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
   bool const gated = h->gated && use_pl;
 
   CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, 16, stream));
+  // this evaluation builds or walks the tile form of the list
+  bool const tiles_gated = gated && tiles_usable(h) && sparse_list(h) && h->tiles.cap_units > 0;
+  bool const tiles_eval =
+      use_pl && !(h->center1() || h->center2()) &&
+      (tiles_gated || (!gated && ((!rebuild && h->pl_valid && h->pl_tiles) ||
+                                  (rebuild_with_tiles(h, flags) && h->tiles.cap_units > 0))));
+  if (tiles_eval) CUDA_OK(h, cudaMemsetAsync(h->tiles.d_counts, 0, 6 * sizeof(unsigned), stream));
   if (gated) {
     CUDA_OK(h, launch_fetch_gate(h->h_mode_dev, h->gate(), stream));
     h->launches++;
@@ -145,8 +188,13 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     F.pl_count = h->pl_count();
     F.h_counters = h->h_counters_dev;
     F.gate = gated ? h->gate() : nullptr;
+    F.rebuilt = (!gated && use_pl && rebuild && !(h->center1() || h->center2())) ? 1 : 0;
     F.pl_persist = h->pl_count() + 1;
     F.pl_cap = h->pl_cap;
+    F.tile_counts = tiles_eval ? h->tiles.d_counts : nullptr;
+    F.tile_cap = h->tiles.cap_units;
+    F.rare_cap = h->rare_cap;
+    F.overflow = (h->world > 1) ? h->d_reduce + 1 : nullptr;
     return F;
   };
 
@@ -276,7 +324,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     // kernel; records the pair list when `record`.  Returns the number of partial sums.
     auto enqueue_all_pairs = [&](int sweep_flags, bool record, const int *gate,
                                  int &nparts) -> int {
-      if (record) h->pl_sorted = false;  // the sweep and the dense kernel list (i, j) as they are
+      if (record) h->pl_sorted = h->pl_tiles = false;  // the sweep and the dense kernel list (i, j) as they are
       if (general_bc) {
         DenseArgs D{};
         D.x1 = x1; D.y1 = y1; D.z1 = z1; D.x2 = x2; D.y2 = y2; D.z2 = z2;
@@ -376,6 +424,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.flags = cell_flags;
       C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // every kind of cell has a fast form
       h->pl_sorted = sorted_walk_enabled();
+      h->pl_tiles = false;
       C.sorted_entries = h->pl_sorted ? 1 : 0;
       C.gate = gate;
       C.P = h->P;
@@ -384,26 +433,166 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       return B200CV_OK;
     };
 
+    // ---- the list as masked cluster tiles (tiles.cuh): open systems, sparse lists ------------
+    auto tile_planes = [&](ExactArgs &E) {
+      TileSide &J = h->tiles.side[1];
+      TileSide &I = h->self() ? J : h->tiles.side[0];
+      E.x1 = I.d_xs; E.y1 = I.d_ys; E.z1 = I.d_zs;
+      E.x2 = J.d_xs; E.y2 = J.d_ys; E.z2 = J.d_zs;
+      E.g1x = I.d_gs; E.g1y = I.d_gs + I.n; E.g1z = I.d_gs + 2 * (size_t)I.n;
+      E.g2x = J.d_gs; E.g2y = J.d_gs + J.n; E.g2z = J.d_gs + 2 * (size_t)J.n;
+    };
+    // rebuild: sort, tile build (value + gradients + masks), reference-order pairs (those listed
+    // become the extras), gradients back to atom order.  Partial sums: [TILE_BLOCKS | EXACT_BLOCKS]
+    auto enqueue_tiles_build = [&](int build_flags, double *partials, const int *gate) -> int {
+      TileBuffers &B = h->tiles;
+      TileSide &J = B.side[1];
+      TileSide &I = h->self() ? J : B.side[0];
+      CUDA_OK(h, tiles_sort(B, x1, y1, z1, x2, y2, z2, gate, stream));
+      h->launches += h->self() ? 5 : 8;
+      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
+      h->launches++;
+      TileBuildArgs T{};
+      T.xi = I.d_xs; T.yi = I.d_ys; T.zi = I.d_zs; T.gi = I.d_gs; T.ni = I.n;
+      T.clusters = I.d_clusters;
+      T.ncl = I.d_ncl;
+      T.rank = h->rank;
+      T.world = h->world;
+      T.xj = J.d_xs; T.yj = J.d_ys; T.zj = J.d_zs; T.gj = J.d_gs; T.nj = J.n;
+      T.cell_start = J.d_cell_start;
+      T.grid = B.d_grid;
+      T.self = h->self() ? 1 : 0;
+      T.unit_hdr = B.d_unit_hdr;
+      T.tile_j = B.d_tile_j;
+      T.tile_m = B.d_tile_m;
+      T.cap_units = B.cap_units;
+      T.counts = B.d_counts;
+      T.rare = h->d_rare;
+      T.rare_cap = h->rare_cap;
+      T.rare_count = h->rare_count();
+      T.partials = partials;
+      T.want_grad = grad ? 1 : 0;
+      cell_cutoffs(h, T.cut);
+      for (int d = 0; d < 3; d++) T.cut[d] *= (1.0 + 1.0e-9);
+      T.gate = gate;
+      T.P = h->P;
+      CUDA_OK(h, launch_tile_build(T, h->exp_special, h->aniso, stream));
+      h->launches++;
+      h->pl_tiles = true;
+      h->pl_sorted = false;
+      ExactArgs E{};
+      tile_planes(E);
+      E.list = h->d_rare;
+      E.count32 = h->rare_count();
+      E.cap = h->rare_cap;
+      E.partials = partials + TILE_BLOCKS;
+      E.pl = h->d_pl;
+      E.pl_cap = h->pl_cap;
+      E.pl_count = h->pl_count();
+      E.flags = build_flags;
+      E.gate = gate;
+      E.gate_on = 1;
+      if (gate == nullptr) {
+        E.fin_ticket = h->fin_ticket();
+        E.fin = finalize_args(TILE_BLOCKS + EXACT_BLOCKS);
+        finalized = true;
+      }
+      E.P = h->P;
+      CUDA_OK(h, launch_exact(E, stream));
+      h->launches++;
+      if (grad) {
+        CUDA_OK(h, tiles_scatter_add(B, G1.d_grad, G1.stride, G2.d_grad, G2.stride, gate, 1, stream));
+        h->launches++;
+      }
+      return B200CV_OK;
+    };
+    // list step: current coordinates into sorted order, tile walk under the masks, exact-pair
+    // queue + extras in one launch, gradients back.  Partial sums: [TILE_BLOCKS | EXACT_BLOCKS]
+    auto enqueue_tiles_walk = [&](double *partials, const int *gate) -> int {
+      TileBuffers &B = h->tiles;
+      TileSide &J = B.side[1];
+      TileSide &I = h->self() ? J : B.side[0];
+      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
+      h->launches++;
+      TileWalkArgs T{};
+      T.xi = I.d_xs; T.yi = I.d_ys; T.zi = I.d_zs; T.gi = I.d_gs; T.ni = I.n;
+      T.xj = J.d_xs; T.yj = J.d_ys; T.zj = J.d_zs; T.gj = J.d_gs; T.nj = J.n;
+      T.unit_hdr = B.d_unit_hdr;
+      T.tile_j = B.d_tile_j;
+      T.tile_m = B.d_tile_m;
+      T.cap_units = B.cap_units;
+      T.counts = B.d_counts;
+      T.rare = h->d_rare;
+      T.rare_cap = h->rare_cap;
+      T.rare_count = h->rare_count();
+      T.partials = partials;
+      T.want_grad = grad ? 1 : 0;
+      T.gate = gate;
+      T.P = h->P;
+      CUDA_OK(h, launch_tile_walk(T, h->exp_special, h->aniso, stream));
+      h->launches++;
+      ExactArgs E{};
+      tile_planes(E);
+      E.list = h->d_rare;
+      E.count32 = h->rare_count();
+      E.cap = h->rare_cap;
+      E.list2 = h->d_pl;
+      E.count2 = h->pl_count() + 1;  // persistent length of the extras
+      E.cap2 = h->pl_cap;
+      E.partials = partials + TILE_BLOCKS;
+      E.flags = flags & ~B200CV_EF_REBUILD_PAIRLIST;
+      E.fast_exp = (h->exp_special == 3) ? 3 : 0;
+      E.gate = gate;
+      E.gate_on = 0;
+      if (gate == nullptr) {
+        E.fin_ticket = h->fin_ticket();
+        E.fin = finalize_args(TILE_BLOCKS + EXACT_BLOCKS);
+        finalized = true;
+      }
+      E.P = h->P;
+      CUDA_OK(h, launch_exact(E, stream));
+      h->launches++;
+      if (grad) {
+        CUDA_OK(h, tiles_scatter_add(B, G1.d_grad, G1.stride, G2.d_grad, G2.stride, gate, 0, stream));
+        h->launches++;
+      }
+      return B200CV_OK;
+    };
+
     if (gated) {
       // captured evaluation with a pair list: the graph holds the rebuild sweep AND the list
       // walk; the mode word decides on the device which of the two does any work
       int nparts = 0;
       int rc;
-      if (cells_usable(h) && sparse_list(h)) {
-        // sized and found sparse by b200cv_pairlist_reserve before the capture
-        rc = enqueue_cells(flags | B200CV_EF_REBUILD_PAIRLIST, h->gate());
-        nparts = CELL_BLOCKS;
+      if (tiles_gated) {
+        static_assert(2 * (TILE_BLOCKS + EXACT_BLOCKS) <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
+        rc = enqueue_tiles_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate());
+        if (rc) return rc;
+        rc = enqueue_tiles_walk(h->d_partials + TILE_BLOCKS + EXACT_BLOCKS, h->gate());
+        if (rc) return rc;
+        npart = 2 * (TILE_BLOCKS + EXACT_BLOCKS);
       } else {
-        rc = enqueue_all_pairs(flags | B200CV_EF_REBUILD_PAIRLIST, true, h->gate(), nparts);
+        if (cells_usable(h) && sparse_list(h)) {
+          // sized and found sparse by b200cv_pairlist_reserve before the capture
+          rc = enqueue_cells(flags | B200CV_EF_REBUILD_PAIRLIST, h->gate());
+          nparts = CELL_BLOCKS;
+        } else {
+          rc = enqueue_all_pairs(flags | B200CV_EF_REBUILD_PAIRLIST, true, h->gate(), nparts);
+        }
+        if (rc) return rc;
+        rc = enqueue_walk(h->d_partials + nparts, h->gate());
+        if (rc) return rc;
+        npart = nparts + WALK_BLOCKS;
       }
-      if (rc) return rc;
-      rc = enqueue_walk(h->d_partials + nparts, h->gate());
-      if (rc) return rc;
-      npart = nparts + WALK_BLOCKS;
     } else if (walk_list) {
-      int rc = enqueue_walk(h->d_partials, nullptr);
+      int rc = h->pl_tiles ? enqueue_tiles_walk(h->d_partials, nullptr)
+                           : enqueue_walk(h->d_partials, nullptr);
       if (rc) return rc;
-      npart = WALK_BLOCKS;
+      npart = h->pl_tiles ? TILE_BLOCKS + EXACT_BLOCKS : WALK_BLOCKS;
+    } else if (tiles_eval) {
+      int rc = enqueue_tiles_build(flags, h->d_partials, nullptr);
+      if (rc) return rc;
+      npart = TILE_BLOCKS + EXACT_BLOCKS;
     } else if (rebuild_with_cells(h, flags)) {
       int rc = enqueue_cells(flags, nullptr);
       if (rc) return rc;
@@ -436,7 +625,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     h->launches += grad ? 2 : 1;
   }
   if (h->world > 1) {
-    CUDA_OK(h, cudaMemcpyAsync(h->h_value, h->d_value, sizeof(double), cudaMemcpyDeviceToHost,
+    // value + the ranks' overflow count (d_reduce[1], see finalize_body)
+    CUDA_OK(h, cudaMemcpyAsync(h->h_value, h->d_value, 2 * sizeof(double), cudaMemcpyDeviceToHost,
                                stream));
   }
   return B200CV_OK;
@@ -466,9 +656,11 @@ int post_sync(b200cv_cvc *h, bool &redo)
 {
   redo = false;
   unsigned long long const rare_n = h->h_counters[0], pl_n = h->h_counters[1];
+  unsigned long long const units = h->h_counters[3], tile_pairs = h->h_counters[4];
   // gated (captured) evaluations: finalize_kernel reports the mode the finished launch ran in
   bool const rebuild = h->gated ? (h->h_counters[2] == 1)
                                 : (bool)(h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
+  bool const tiles_built = rebuild && h->pl_tiles;
   h->exact_pairs = (size_t)rare_n;
   if (rare_n > h->rare_cap) {
     if (h->async_eval) {
@@ -483,51 +675,76 @@ int post_sync(b200cv_cvc *h, bool &redo)
     redo = true;
   }
   if (rebuild && !(h->center1() || h->center2())) {
-    if (pl_n > h->pl_cap && h->async_eval) {
+    bool const over_pl = pl_n > h->pl_cap;
+    bool const over_tiles = tiles_built && units > h->tiles.cap_units;
+    if ((over_pl || over_tiles) && h->async_eval) {
       return fail(h, B200CV_MEMORY_ERROR,
                   "pair-list overflow in a captured evaluation (" + std::to_string(pl_n) +
-                      " listed pairs, capacity " + std::to_string(h->pl_cap) +
+                      " listed pairs, capacity " + std::to_string(h->pl_cap) + "; " +
+                      std::to_string(units) + " tile units, capacity " +
+                      std::to_string(h->tiles.cap_units) +
                       "): reserve more with b200cv_pairlist_reserve before capturing");
     }
-    if (pl_n > h->pl_cap) {
+    if (over_pl) {
       int rc = ensure_pairlist_capacity(h, pl_n);
       if (rc) return rc;
+    }
+    if (over_tiles) {
+      h->epoch++;
+      CUDA_OK(h, tiles_reserve(h->tiles, (unsigned)std::min<unsigned long long>(
+                                             units + units / 2, 1ull << 30)));
+    }
+    if (over_pl || over_tiles) {
       redo = true;
     } else {
-      h->pl_n = pl_n;
+      h->pl_entries = pl_n;
+      h->pl_n = pl_n + (tiles_built ? tile_pairs : 0ull);
       h->pl_valid = true;
     }
   }
   return B200CV_OK;
 }
 
+// After the stream has drained: commit what the evaluation left behind (list lengths; the
+// device keeps its own copies, written by the final sum) and repair queue overflows by growing
+// the queue and running the evaluation again.  Sharded runs agree on the redo through the
+// overflow word that travels with the all-reduce (d_reduce[1]), so that every rank re-enters
+// the collective together.
 int sync_and_check(b200cv_cvc *h)
 {
-  for (int attempt = 0; attempt < 4; attempt++) {
+  for (int attempt = 0; attempt < 6; attempt++) {
     CUDA_OK(h, cudaStreamSynchronize(h->last_stream));
     bool redo = false;
     int rc = post_sync(h, redo);
-    if (rc) return rc;
-    if (redo && h->world > 1) {
-      // ranks cannot re-run independently: their all-reduces would no longer pair up
-      return fail(h, B200CV_MEMORY_ERROR,
-                  "pair queue overflow in a sharded run; raise the pair-list capacity");
+    if (rc) {
+      h->unchecked = false;  // reported; the caller reserves again or gives up
+      return rc;
+    }
+    if (h->world > 1) {
+      if (h->comm) {
+        redo = redo || (h->h_value[1] > 0.5);
+      } else if (redo) {
+        // b200cv_set_shard without a communicator: the caller reduces, nobody to agree with
+        return fail(h, B200CV_MEMORY_ERROR,
+                    "pair queue overflow in a sharded run without a communicator");
+      }
     }
     if (!redo) {
-      bool const rebuild = !h->gated && (h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
-      if (rebuild && !(h->center1() || h->center2())) {
-        // keep the list length on the device for the list-walk steps (gated evaluations
-        // do that in finalize_kernel)
-        CUDA_OK(h, cudaMemcpyAsync(h->pl_count() + 1, &h->h_counters[1], 8,
-                                   cudaMemcpyHostToDevice, h->last_stream));
-        CUDA_OK(h, cudaStreamSynchronize(h->last_stream));
-      }
+      h->unchecked = false;
       return B200CV_OK;
     }
     rc = reset_gradients(h, h->last_stream);
     if (rc) return rc;
+    rc = prepare_calc(h, h->last_flags);
+    if (rc) return rc;
     rc = enqueue_calc(h, h->last_flags, h->last_stream);
     if (rc) return rc;
+    if (h->fit_after_calc) {
+      // the fit gradients were derived from the incomplete first pass
+      rc = b200cv_calc_fit_gradients(h, h->last_stream);
+      if (rc) return rc;
+      h->fit_after_calc = true;
+    }
   }
   return fail(h, B200CV_BUG_ERROR, "queue capacity did not converge");
 }

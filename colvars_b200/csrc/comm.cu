@@ -16,6 +16,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   std::mutex mu;
   bool load(std::string &err)
@@ -36,8 +38,9 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) {
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather) {
       err = "NCCL library lacks required symbols";
       return false;
     }
@@ -58,6 +61,20 @@ int comm_allreduce(b200cv_cvc *h, cudaStream_t stream)
   if (r != ncclSuccess) {
     return fail(h, B200CV_ERROR,
                 std::string("ncclAllReduce: ") +
+                    (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  }
+  return B200CV_OK;
+}
+
+int comm_allgather(b200cv_cvc *h, double *buf, size_t count_per_rank, cudaStream_t stream)
+{
+  if (!h->comm) return fail(h, B200CV_BUG_ERROR, "all-gather without a communicator");
+  // in place: rank r's contribution already sits at buf + r * count_per_rank
+  ncclResult_t r = g_nccl.AllGather(buf + (size_t)h->rank * count_per_rank, buf, count_per_rank,
+                                    ncclDouble, h->comm, stream);
+  if (r != ncclSuccess) {
+    return fail(h, B200CV_ERROR,
+                std::string("ncclAllGather: ") +
                     (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
   }
   return B200CV_OK;

@@ -29,6 +29,7 @@
 #include "cells.cuh"
 #include "fit.cuh"
 #include "kernels.cuh"
+#include "tiles.cuh"
 
 namespace b200cv {
 
@@ -78,7 +79,8 @@ struct b200cv_cvc {
   double *d_value = nullptr;
   double *h_value = nullptr;                // mapped pinned
   double *h_value_dev = nullptr;            // device alias of h_value
-  unsigned long long *h_counters = nullptr; // mapped pinned [4]: rare, listed, gate mode, -
+  unsigned long long *h_counters = nullptr; // mapped pinned [8]: rare, listed (entries), gate mode,
+                                            // tile units, tile pairs
   unsigned long long *h_counters_dev = nullptr;
   unsigned char *d_counters = nullptr;      // rare_count (u32 @0), pl_count (u64 @8),
                                             // persistent list length (u64 @16), gate (i32 @24),
@@ -95,7 +97,8 @@ struct b200cv_cvc {
   unsigned int rare_cap = 0;
   unsigned long long *d_pl = nullptr;
   unsigned long long pl_cap = 0;
-  unsigned long long pl_n = 0;  // entries of the current list
+  unsigned long long pl_n = 0;  // pairs of the current list (all forms)
+  unsigned long long pl_entries = 0;  // ... of them as packed entries in d_pl (tile form: the extras)
   bool pl_valid = false;        // a rebuild has happened
   // entries of the current list are in cell order (built by the cell kernel with
   // sorted_entries): the walk runs on the cell-ordered copies (cells.cuh, launch_cell_gather)
@@ -106,6 +109,16 @@ struct b200cv_cvc {
   // be sparse
   b200cv::CellBuffers cells;
   bool cells_ready = false;
+  // the sparse list of an open system as masked cluster tiles (tiles.cuh); d_pl then holds the
+  // extras (pairs listed by the reference-order path), entries in sorted positions
+  b200cv::TileBuffers tiles;
+  bool tiles_ready = false;
+  bool pl_tiles = false;   // the current list is in tile form
+  // an evaluation has been enqueued whose queue counters / new list lengths the host has not
+  // looked at yet (sync_and_check): the next call that builds on its result checks first
+  bool unchecked = false;
+  // calc_fit_gradients has been enqueued behind the last evaluation (an overflow redo repeats it)
+  bool fit_after_calc = false;
 
   // sweep work items
   b200cv::SweepItem *d_items = nullptr;
@@ -210,6 +223,11 @@ bool sorted_walk_enabled();
 bool sparse_list(const b200cv_cvc *h);
 bool cells_usable(const b200cv_cvc *h);
 bool rebuild_with_cells(const b200cv_cvc *h, int flags);
+bool tiles_usable(const b200cv_cvc *h);
+bool rebuild_with_tiles(const b200cv_cvc *h, int flags);
+unsigned tile_units_estimate(const b200cv_cvc *h);
+// allocations an evaluation with these flags may need (tile arrays): before any stream capture
+int prepare_calc(b200cv_cvc *h, int flags);
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need);
 int ensure_rare_capacity(b200cv_cvc *h, unsigned long long need);
 // all kernels of one coordnum::calc_value on `stream`
@@ -223,6 +241,8 @@ int sync_and_check(b200cv_cvc *h);
 // ---- comm.cu ----------------------------------------------------------------------------------
 // the one collective of the path: [value | grad1 | grad2] summed over ranks, in place
 int comm_allreduce(b200cv_cvc *h, cudaStream_t stream);
+// buf holds world * count_per_rank doubles; rank r has filled its own block: gather the others
+int comm_allgather(b200cv_cvc *h, double *buf, size_t count_per_rank, cudaStream_t stream);
 void comm_destroy(b200cv_cvc *h);
 
 }  // namespace b200cv

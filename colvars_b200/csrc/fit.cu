@@ -425,22 +425,28 @@ int fit_scatter_force(FitState &F, double force, double *proxy_force, size_t pst
 }
 
 int fit_scatter_force_host(FitState &F, double force, double *h_proxy_force, size_t n_proxy,
-                           cudaStream_t s, std::string &err)
+                           int rank, int world, cudaStream_t s, std::string &err)
 {
   if (!F.active || !F.fit_gradients) return B200CV_OK;
-  F.h_stage.resize(3 * F.fstride);
-  FIT_OK(cudaMemcpyAsync(F.h_stage.data(), F.d_fit_grad, sizeof(double) * 3 * F.fstride,
-                         cudaMemcpyDeviceToHost, s));
+  // this rank's share of the fitting atoms (all of them on a single rank)
+  size_t const j0 = (size_t)F.nfit * (size_t)rank / (size_t)world;
+  size_t const j1 = (size_t)F.nfit * ((size_t)rank + 1) / (size_t)world;
+  size_t const m = j1 - j0;
+  if (m == 0) return B200CV_OK;
+  F.h_stage.resize(3 * m);
+  FIT_OK(cudaMemcpy2DAsync(F.h_stage.data(), sizeof(double) * m, F.d_fit_grad + j0,
+                           sizeof(double) * F.fstride, sizeof(double) * m, 3,
+                           cudaMemcpyDeviceToHost, s));
   FIT_OK(cudaStreamSynchronize(s));
-  for (int j = 0; j < F.nfit; j++) {
-    size_t const p = (size_t)F.h_index[j];
+  for (size_t j = 0; j < m; j++) {
+    size_t const p = (size_t)F.h_index[j0 + j];
     if (p >= n_proxy) {
       err = "proxy index of a fitting atom out of range";
       return B200CV_BUG_ERROR;
     }
     h_proxy_force[3 * p] += force * F.h_stage[j];
-    h_proxy_force[3 * p + 1] += force * F.h_stage[F.fstride + j];
-    h_proxy_force[3 * p + 2] += force * F.h_stage[2 * F.fstride + j];
+    h_proxy_force[3 * p + 1] += force * F.h_stage[m + j];
+    h_proxy_force[3 * p + 2] += force * F.h_stage[2 * m + j];
   }
   return B200CV_OK;
 }

@@ -46,8 +46,10 @@ int fit_calc_gradients(FitState &F, const double *d_grad, size_t stride, int n, 
                        std::string &err);
 int fit_scatter_force(FitState &F, double force, double *proxy_force, size_t pstride, int aos,
                       cudaStream_t s, std::string &err);
+// host-buffer route: forces of this rank's share [nfit rank / world, nfit (rank+1) / world) of the
+// fitting atoms
 int fit_scatter_force_host(FitState &F, double force, double *h_proxy_force, size_t n_proxy,
-                           cudaStream_t s, std::string &err);
+                           int rank, int world, cudaStream_t s, std::string &err);
 int fit_host_inverse_matrix(FitState &F, double Rinv[3][3], std::string &err);
 int fit_get_gradients(FitState &F, double *out_soa, int nfit, std::string &err);
 

@@ -14,6 +14,8 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
   NvtxRange nvtx_range("b200cv::step");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t user = (cudaStream_t)stream;
+  // which graph applies depends on the list the previous step left behind: commit it first
+  if (h->unchecked) CUDA_OK_RC(sync_and_check(h));
   int const flags = calc_flags(h, step_relative, gradients);
   h->gated = false;  // this entry keeps one graph per flag set instead of gating
   bool const fitted = h->g[0].fit.active || h->g[1].fit.active;
@@ -38,13 +40,16 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
     int rc = ensure_partials(h, PARTIALS_TAIL);
     if (rc) return rc;
   }
-  // a rebuild is captured in two forms: all-pairs sweep (first rebuild) and cell list
-  // (the host does not run enqueue_calc on a replay: what it would have noted -- the index
-  // space of the list a rebuild leaves behind -- is noted below), a list walk in two as well:
-  // entries as atom indices or in cell order
-  bool const cells_rebuild = rebuild_with_cells(h, flags);
-  int graph_key = flags | (cells_rebuild ? (1 << 30) : 0);
+  CUDA_OK_RC(prepare_calc(h, flags));
+  // a rebuild is captured in three forms: all-pairs sweep (first rebuild), cell list, cluster
+  // tiles (the host does not run enqueue_calc on a replay: what it would have noted -- the form
+  // of the list a rebuild leaves behind -- is noted below), a list walk in three as well:
+  // entries as atom indices, entries in cell order, tiles
+  bool const tiles_rebuild = rebuild_with_tiles(h, flags) && h->tiles.cap_units > 0;
+  bool const cells_rebuild = !tiles_rebuild && rebuild_with_cells(h, flags);
+  int graph_key = flags | (cells_rebuild ? (1 << 30) : 0) | (tiles_rebuild ? (1 << 28) : 0);
   if (use_pl && !rebuild && h->pl_sorted) graph_key |= (1 << 29);
+  if (use_pl && !rebuild && h->pl_tiles) graph_key |= (1 << 27);
   b200cv_cvc::StepGraph *hit = nullptr;
   for (auto &g : h->step_graphs) {
     if (g.flags == graph_key && g.pos == d_proxy_pos && g.stride == proxy_stride &&
@@ -86,6 +91,7 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
   CUDA_OK(h, cudaGraphLaunch(hit->exec, user));
   if (use_pl && rebuild && !(h->center1() || h->center2())) {
     h->pl_sorted = cells_rebuild && sorted_walk_enabled();
+    h->pl_tiles = tiles_rebuild;
   }
   h->launches = hit->launches;
   h->async_eval = false;
@@ -95,6 +101,8 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
   h->last_flags = flags;
   h->have_calc = true;
   h->data_read = true;
+  h->unchecked = true;
+  h->fit_after_calc = fitted && gradients;
   return B200CV_OK;
 }
 

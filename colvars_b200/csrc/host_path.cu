@@ -67,6 +67,12 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, 
 }
 
 // ---- host-buffer step --------------------------------------------------------------------------
+// Sharded runs (b200cv_comm_init): every rank passes the same proxy array, as the ranks of a
+// replicated-data engine hold it.  Each rank uploads 1/world of it over its own PCIe link and the
+// blocks are exchanged GPU to GPU (ncclAllGather over NVLink); on the way back rank r scatters
+// the forces of its share of every group's atoms -- atoms [n r / world, n (r+1) / world) of a
+// group of n -- so each rank moves 1/world of the gradients and the ranks' force arrays add up
+// to the full force.
 
 int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
                      long long step_relative, int gradients, double *value)
@@ -75,20 +81,36 @@ int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
   if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = h->own_stream;
-  if (h->stage_n < n_proxy) {
+  bool const exchange = h->world > 1 && h->comm != nullptr;
+  size_t const per = exchange ? (n_proxy + (size_t)h->world - 1) / (size_t)h->world : n_proxy;
+  size_t const need = exchange ? per * (size_t)h->world : n_proxy;
+  if (h->stage_n < need) {
     free_dev(h->d_stage_pos);
-    CUDA_OK(h, cudaMalloc(&h->d_stage_pos, sizeof(double) * 3 * n_proxy));
-    h->stage_n = n_proxy;
+    CUDA_OK(h, cudaMalloc(&h->d_stage_pos, sizeof(double) * 3 * need));
+    h->stage_n = need;
   }
-  // the CPU proxy's AoS rvector array (src/colvarproxy.h:275) goes up in one copy; the
-  // gather by atoms_index runs on the device
-  CUDA_OK(h, cudaMemcpyAsync(h->d_stage_pos, h_proxy_pos, sizeof(double) * 3 * n_proxy,
-                             cudaMemcpyHostToDevice, s));
+  // the CPU proxy's AoS rvector array (src/colvarproxy.h:275) goes up as it is; the gather by
+  // atoms_index runs on the device
+  if (exchange) {
+    size_t const a0 = std::min(per * (size_t)h->rank, n_proxy);
+    size_t const a1 = std::min(a0 + per, n_proxy);
+    if (a1 > a0) {
+      CUDA_OK(h, cudaMemcpyAsync(h->d_stage_pos + 3 * a0, h_proxy_pos + 3 * a0,
+                                 sizeof(double) * 3 * (a1 - a0), cudaMemcpyHostToDevice, s));
+    }
+    CUDA_OK_RC(comm_allgather(h, h->d_stage_pos, 3 * per, s));
+  } else {
+    CUDA_OK(h, cudaMemcpyAsync(h->d_stage_pos, h_proxy_pos, sizeof(double) * 3 * n_proxy,
+                               cudaMemcpyHostToDevice, s));
+  }
   int rc = reset_gradients(h, s);
   if (rc) return rc;
   int const ng = h->self() ? 1 : 2;
   for (int k = 0; k < ng; k++) {
     Group &G = h->g[k];
+    if (G.max_index >= 0 && (size_t)G.max_index >= n_proxy) {
+      return fail(h, B200CV_BUG_ERROR, "proxy index out of range");
+    }
     CUDA_OK(h, launch_gather(h->d_stage_pos, n_proxy, 1, G.d_index, G.n, G.d_pos, G.stride, s));
     std::string err;
     rc = fit_read_and_apply(G.fit, h->d_stage_pos, n_proxy, 1, G.d_pos, G.stride, G.n, s, err);
@@ -110,23 +132,44 @@ int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, 
   if (!h || !h_proxy_force) return B200CV_BUG_ERROR;
   if (!h->have_calc) return fail(h, B200CV_BUG_ERROR, "apply_force before calc_value");
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  if (h->unchecked) CUDA_OK_RC(sync_and_check(h));
   cudaStream_t s = h->last_stream;
-  // one D2H copy of [grad1 | grad2]; the scatter into the AoS force array is the same
-  // host loop as atom_group::apply_colvar_force (src/colvaratoms.cpp:1637-1704)
-  if (h->h_stage_count < h->reduce_count) {
+  int const ng = h->self() ? 1 : 2;
+  // this rank's share of each group (all of it on a single rank)
+  // (b200cv_set_shard without a communicator leaves the reduction to the caller: every rank then
+  // holds partial gradients of all atoms and scatters all of them)
+  bool const shares = h->world > 1 && h->comm != nullptr;
+  size_t const srank = shares ? (size_t)h->rank : 0, sworld = shares ? (size_t)h->world : 1;
+  size_t b0[2] = {0, 0}, b1[2] = {0, 0}, off[2] = {0, 0}, total = 0;
+  for (int k = 0; k < ng; k++) {
+    size_t const n = (size_t)h->g[k].n;
+    b0[k] = n * srank / sworld;
+    b1[k] = n * (srank + 1) / sworld;
+    off[k] = total;
+    total += 3 * (b1[k] - b0[k]);
+  }
+  if (h->h_stage_count < total) {
     if (h->h_stage_grad) cudaFreeHost(h->h_stage_grad);
     h->h_stage_grad = nullptr;
-    CUDA_OK(h, cudaHostAlloc(&h->h_stage_grad, sizeof(double) * h->reduce_count,
+    CUDA_OK(h, cudaHostAlloc(&h->h_stage_grad, sizeof(double) * std::max<size_t>(total, 1),
                              cudaHostAllocDefault));
-    h->h_stage_count = h->reduce_count;
+    h->h_stage_count = total;
   }
-  CUDA_OK(h, cudaMemcpyAsync(h->h_stage_grad, h->d_reduce, sizeof(double) * h->reduce_count,
-                             cudaMemcpyDeviceToHost, s));
-  CUDA_OK(h, cudaStreamSynchronize(s));
-  int const ng = h->self() ? 1 : 2;
+  // one strided D2H copy per group (three plane segments); the scatter into the AoS force array
+  // is the same host loop as atom_group::apply_colvar_force (src/colvaratoms.cpp:1637-1704)
   for (int k = 0; k < ng; k++) {
     Group &G = h->g[k];
-    const double *g = h->h_stage_grad + (G.d_grad - h->d_reduce);
+    size_t const m = b1[k] - b0[k];
+    if (m == 0) continue;
+    CUDA_OK(h, cudaMemcpy2DAsync(h->h_stage_grad + off[k], sizeof(double) * m, G.d_grad + b0[k],
+                                 sizeof(double) * G.stride, sizeof(double) * m, 3,
+                                 cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_OK(h, cudaStreamSynchronize(s));
+  for (int k = 0; k < ng; k++) {
+    Group &G = h->g[k];
+    size_t const m = b1[k] - b0[k];
+    const double *g = h->h_stage_grad + off[k];
     double Rinv[3][3];
     bool const rot = G.fit.rotate;
     if (rot) {
@@ -137,15 +180,14 @@ int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, 
     if (G.max_index >= 0 && (size_t)G.max_index >= n_proxy) {
       return fail(h, B200CV_BUG_ERROR, "proxy index out of range");
     }
-    const int *idx = G.h_index.data();
-    size_t const stride = G.stride;
-    int const n = G.n;
+    const int *idx = G.h_index.data() + b0[k];
     // distinct atoms of one group: the rows are independent, large groups are split over the
     // host threads (the reference's loop is sequential, src/colvaratoms.cpp:1637-1704)
-#pragma omp parallel for schedule(static) if (n > 16384)
-    for (int i = 0; i < n; i++) {
+#pragma omp parallel for schedule(static) if (m > 16384)
+    for (long long ii = 0; ii < (long long)m; ii++) {
+      size_t const i = (size_t)ii;
       size_t const p = (size_t)idx[i];
-      double gx = g[i], gy = g[stride + i], gz = g[2 * stride + i];
+      double gx = g[i], gy = g[m + i], gz = g[2 * m + i];
       if (rot) {
         double const tx = Rinv[0][0] * gx + Rinv[0][1] * gy + Rinv[0][2] * gz;
         double const ty = Rinv[1][0] * gx + Rinv[1][1] * gy + Rinv[1][2] * gz;
@@ -157,7 +199,7 @@ int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, 
       h_proxy_force[3 * p + 2] += force * gz;
     }
     std::string err;
-    int rc = fit_scatter_force_host(G.fit, force, h_proxy_force, n_proxy, s, err);
+    int rc = fit_scatter_force_host(G.fit, force, h_proxy_force, n_proxy, (int)srank, (int)sworld, s, err);
     if (rc) return fail(h, rc, err);
   }
   return B200CV_OK;

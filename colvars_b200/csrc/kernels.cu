@@ -51,12 +51,32 @@ __device__ __forceinline__ void finalize_body(FinalizeArgs const &A, double *red
           A.rare_count ? (unsigned long long)*(const volatile unsigned int *)A.rare_count : 0ull;
       A.h_counters[1] = A.pl_count ? *(const volatile unsigned long long *)A.pl_count : 0ull;
     }
+    bool rebuilt = A.rebuilt != 0;
     if (A.gate) {
       int const mode = *A.gate;
       if (A.h_counters) A.h_counters[2] = (unsigned long long)mode;
-      if (mode == 1 && A.pl_persist) {
-        unsigned long long const n = *A.pl_count;
+      rebuilt = mode == 1;
+    }
+    if (A.tile_counts && A.h_counters) {
+      A.h_counters[3] = (unsigned long long)*(const volatile unsigned *)A.tile_counts;
+      A.h_counters[4] = *(const volatile unsigned long long *)(A.tile_counts + 4);
+    }
+    if (A.overflow) {
+      bool over = A.rare_count && *(const volatile unsigned int *)A.rare_count > A.rare_cap;
+      if (rebuilt) {
+        over = over || (A.pl_count && *(const volatile unsigned long long *)A.pl_count > A.pl_cap);
+        over = over || (A.tile_counts && *(const volatile unsigned *)A.tile_counts > A.tile_cap);
+      }
+      *A.overflow = over ? 1.0 : 0.0;
+    }
+    if (rebuilt) {
+      if (A.pl_persist) {
+        unsigned long long const n = *(const volatile unsigned long long *)A.pl_count;
         *A.pl_persist = n < A.pl_cap ? n : A.pl_cap;
+      }
+      if (A.tile_counts) {
+        unsigned const u = *(const volatile unsigned *)A.tile_counts;
+        A.tile_counts[6] = u < A.tile_cap ? u : A.tile_cap;
       }
     }
     // mapped pinned copies: the host reads them after synchronising with the stream, and
@@ -85,8 +105,14 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
     }
     __syncthreads();
   }
-  unsigned long long n = A.count32 ? (unsigned long long)*A.count32 : *A.count64;
-  if (n > A.cap) n = A.cap;
+  unsigned long long n1 = A.count32 ? (unsigned long long)*A.count32 : *A.count64;
+  if (n1 > A.cap) n1 = A.cap;
+  unsigned long long n = n1;
+  if (A.list2 != nullptr) {
+    unsigned long long n2 = *A.count2;
+    if (n2 > A.cap2) n2 = A.cap2;
+    n += n2;
+  }
   bool const grad = A.flags & EF_GRADIENTS;
   bool const rebuild = (A.flags & EF_REBUILD_PAIRLIST) && A.pl;
   double fsum = 0.0;
@@ -103,7 +129,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
     double Gx = 0.0, Gy = 0.0, Gz = 0.0, F = 0.0;
     unsigned long long ent = 0ull;
     if (valid) {
-      ent = A.list[e];
+      ent = e < n1 ? A.list[e] : A.list2[e - n1];
       i = (int)(ent >> 32);
       j = (int)(ent & 0xffffffffu);
       double const x1 = A.x1[i], y1 = A.y1[i], z1 = A.z1[i];

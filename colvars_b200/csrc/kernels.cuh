@@ -43,11 +43,21 @@ struct FinalizeArgs {
   double *h_value;  // mapped pinned
   const unsigned int *rare_count;
   const unsigned long long *pl_count;
-  unsigned long long *h_counters;  // mapped pinned [4]: rare_count, pl_count, gate mode, unused
-  // gated evaluations: after a rebuild (*gate == 1) the list length is kept on the device
+  // mapped pinned [8]: rare_count, pl_count, gate mode, tile units, tile pairs
+  unsigned long long *h_counters;
+  // after a rebuild -- `rebuilt` != 0, or *gate == 1 in a gated (captured) evaluation -- the
+  // lengths of the new list are kept on the device for the list steps that follow (clamped to
+  // the capacities; the host sees the unclamped counts and redoes the step on overflow)
   const int *gate;
+  int rebuilt;
   unsigned long long *pl_persist;
   unsigned long long pl_cap;
+  unsigned *tile_counts;  // TileBuffers::d_counts or null
+  unsigned tile_cap;
+  // sharded runs: 1.0 when a queue of this rank overflowed, else 0.0, into the word that the
+  // all-reduce sums next to the value (null: single rank)
+  unsigned int rare_cap;
+  double *overflow;
 };
 // Pairs queued by the sweep (or every listed pair on non-rebuild steps, or every pair for
 // the general-PBC fallback) evaluated in the reference's operation order.
@@ -60,6 +70,11 @@ struct ExactArgs {
   const unsigned int *count32;         // number of entries (device), or NULL
   const unsigned long long *count64;   // ... 64-bit variant (pair list), or NULL
   unsigned long long cap;              // entries beyond cap were never written
+  // a second list evaluated behind the first in the same launch (tile walk: exact-pair queue +
+  // the extras of the tile list), or NULL
+  const unsigned long long *list2;
+  const unsigned long long *count2;
+  unsigned long long cap2;
   double *partials;                    // one per CTA
   unsigned long long *pl;              // pair list to append to on rebuild (or NULL)
   unsigned long long pl_cap;
@@ -79,8 +94,9 @@ constexpr int EXACT_THREADS = 128;
 // the pair-list walk is a latency-bound gather (6 coordinate loads per entry): it wants every
 // warp slot the register file allows (58 registers -> 8 CTAs per SM)
 constexpr int WALK_BLOCKS = 1184;
-// partial sums behind the sweep items: [rare queue | walk] or [cell kernel (592) | walk]
-constexpr int PARTIALS_TAIL = 2 * WALK_BLOCKS;
+// partial sums behind the sweep items: [rare queue | walk], [cell kernel (592) | walk] or
+// [tile build | its exact queue | tile walk | its exact lists]
+constexpr int PARTIALS_TAIL = 4096;
 int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks = EXACT_BLOCKS);
 
 // Dense fallback for boundary conditions the tile sweep does not specialise (mixed /

@@ -130,7 +130,13 @@ int b200cv_set_boundaries(b200cv_cvc *h, int periodic_x, int periodic_y, int per
  * d_proxy_pos / d_proxy_force: device double[3 * proxy_stride], SoA planes x|y|z with
  * stride = number of proxy atoms (src/colvaratoms_gpu.cpp:210-214,
  * src/cuda/colvaratoms_kernel.cu:47-52).  All work is enqueued on `stream`
- * (proxy->get_default_stream()); nothing synchronises except b200cv_value(). */
+ * (proxy->get_default_stream()); b200cv_value() is where the host normally waits: it returns
+ * the scalar, commits what a pair-list rebuild left behind and repairs a queue overflow (grow,
+ * run the evaluation again).  A caller that skips it loses nothing: the list lengths of a
+ * rebuild are kept on the device by the evaluation itself, and the next b200cv_calc_value /
+ * b200cv_step / b200cv_apply_force on the handle first does the same check (one extra
+ * synchronisation in that case), so stale list lengths or gradients of an overflowed evaluation
+ * are never used. */
 int b200cv_read_data(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
                      void *stream);
 int b200cv_calc_value(b200cv_cvc *h, long long step_relative, int gradients, void *stream);
@@ -195,7 +201,12 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1_soa, const double *h_po
 /* ---- host-buffer step (CPU proxy arrays; host<->device copies included) ---------------
  * h_proxy_pos: AoS rvector array double[3*n_proxy] (src/colvarproxy.h:275).
  * b200cv_calc_host = read_data + calc_value (+ fit gradients) and returns the value;
- * b200cv_apply_force_host adds force * gradients into h_proxy_force (AoS). */
+ * b200cv_apply_force_host adds force * gradients into h_proxy_force (AoS).
+ * Sharded runs (after b200cv_comm_init): every rank passes the same position array (a
+ * replicated-data engine); each rank uploads 1/world of it and the blocks are exchanged GPU to
+ * GPU (ncclAllGather).  b200cv_apply_force_host on rank r adds the forces of atoms
+ * [n r / world, n (r+1) / world) of every group of n atoms (and of the fitting atoms), so each
+ * rank moves 1/world of the gradients and the ranks' force arrays SUM to the full force. */
 int b200cv_calc_host(b200cv_cvc *h, const double *h_proxy_pos, size_t n_proxy,
                      long long step_relative, int gradients, double *value);
 int b200cv_apply_force_host(b200cv_cvc *h, double force, double *h_proxy_force, size_t n_proxy);
@@ -214,6 +225,12 @@ int b200cv_get_tolerance_l2_max(const b200cv_cvc *h, double *l2_max);
  * (ip = i*N2 + j, or the row-major upper triangle for selfCoordNum; sorted ascending). */
 int b200cv_pairlist_count(b200cv_cvc *h, size_t *count);
 int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *h_indices, size_t capacity);
+/* How the current list is kept: form 0 = packed (i, j) entries as the all-pairs sweep compacts
+ * them, 1 = entries in cell order (cell-list rebuild, periodic cells), 2 = masked 32 x 32
+ * cluster tiles + a few entries (open systems, sparse lists), -1 = no rebuild yet; listed pairs,
+ * of them as packed entries, tile units and tiles (pairs / (1024 tiles) is the tile fill). */
+int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entries,
+                          size_t *tile_units, size_t *tiles);
 /* Counters of the last calc_value: kernels launched, pairs sent to the exact
  * (reference-order) path. */
 int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs);
@@ -226,7 +243,8 @@ unsigned long long b200cv_kernel_launches(void);
 int b200cv_comm_unique_id(unsigned char id[128]);
 /* Join the communicator; afterwards calc_value evaluates only this rank's rows of
  * group1 (cyclic tiles for selfCoordNum) and all-reduces [value | grad1 | grad2] with
- * ncclAllReduce(ncclDouble, ncclSum) on the compute stream. */
+ * ncclAllReduce(ncclDouble, ncclSum) on the compute stream.  A queue overflow on any rank
+ * travels with that all-reduce, so all ranks grow and repeat the evaluation together. */
 int b200cv_comm_init(b200cv_cvc *h, const unsigned char id[128], int rank, int world);
 /* Shard without a communicator (the caller reduces): for tests and external plumbing. */
 int b200cv_set_shard(b200cv_cvc *h, int rank, int world);

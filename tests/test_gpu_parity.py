@@ -659,11 +659,17 @@ def test_duplicate_atoms_in_a_group_are_rejected():
                     np.array([5, 6], dtype=np.int32))
 
 
-def test_captured_pairlist_overflow_is_an_error_not_a_truncation():
-    """A captured graph holds the list's address, so the list cannot grow: when a rebuild finds
-    more pairs than were reserved, the step's value must come back as an error."""
+@pytest.mark.parametrize("form", ["entries", "tiles"])
+def test_captured_pairlist_overflow_is_an_error_not_a_truncation(form, monkeypatch):
+    """A captured graph holds the list's address, so the list cannot grow under it: when a
+    rebuild finds more pairs than were reserved, the step's value must come back as an error --
+    and reserving again on the new positions plus a re-capture must recover.  The tile form of
+    the list stores 32 x 32 masks per tile, so the same compression only fills its tiles: it has
+    to come out right without any error."""
     import torch
     cb = _cb()
+    if form == "entries":
+        monkeypatch.setenv("B200CV_NO_TILES", "1")
     rng = np.random.default_rng(9)
     n = 6000
     pos = rng.random((n, 3)) * 60.0
@@ -672,12 +678,17 @@ def test_captured_pairlist_overflow_is_an_error_not_a_truncation():
     p1 = torch.tensor(np.ascontiguousarray(pos.T), device="cuda")
     g1 = torch.zeros_like(p1)
     side = torch.cuda.Stream()
-    cv.pairlist_reserve(p1, None, headroom=1.0, stream=side)
-    side.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        cv.eval_async(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST, stream=side)
-        cv.accumulate_gradients(g1, None, stream=side)
+
+    def capture():
+        cv.pairlist_reserve(p1, None, headroom=1.0, stream=side)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            cv.eval_async(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST, stream=side)
+            cv.accumulate_gradients(g1, None, stream=side)
+        return graph
+
+    graph = capture()
     graph.replay()
     torch.cuda.synchronize()
     v0 = cv.value()  # fits: same positions as the reservation
@@ -686,14 +697,26 @@ def test_captured_pairlist_overflow_is_an_error_not_a_truncation():
     # allocated with at least 2^20 entries, so check that the new count really exceeds it
     p1.mul_(1.0 / 3.0)
     cv.pairlist_set_rebuild(True)
+    g1.zero_()
     graph.replay()
     torch.cuda.synchronize()
     dense = cb.CoordNum("selfCoordNum", i1, cutoff=4.0, tolerance=0.01, pairlist_freq=2)
-    dense.eval(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST | cb.EF_REBUILD_PAIRLIST,
-               torch.zeros_like(p1), None)
+    gd = torch.zeros_like(p1)
+    dense.eval(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST | cb.EF_REBUILD_PAIRLIST, gd, None)
+    vd = dense.value()
     assert len(dense.pairlist()) > (1 << 20)
-    with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
-        cv.value()
+    if form == "entries":
+        with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
+            cv.value()
+        # recover: size the list on the positions of now, capture again
+        graph = capture()
+        cv.pairlist_set_rebuild(True)
+        g1.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+    close_val(cv.value(), vd, 1e-13)
+    close_arr(g1.cpu().numpy(), gd.cpu().numpy(), 1e-13)
+    assert np.array_equal(cv.pairlist(), dense.pairlist())
 
 
 def test_handles_are_independent_across_host_threads():
@@ -739,14 +762,18 @@ def test_handles_are_independent_across_host_threads():
     assert not errors, errors
 
 
+@pytest.mark.parametrize("form", ["tiles", "cells"])
 @pytest.mark.parametrize("kind,aniso", [("selfCoordNum", False), ("coordNum", False),
-                                        ("coordNum", True)])
-def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso):
+                                        ("coordNum", True), ("selfCoordNum", True)])
+def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso, form, monkeypatch):
     """Once a rebuild has shown the list to be sparse (< 2 % of the pairs), later rebuilds only
-    visit pairs in neighbouring cells (csrc/cells.cu); everything else is exactly zero in the
-    reference as well (l2 > tolerance_l2_max returns before anything is evaluated), so value,
-    gradients and list must not change."""
+    visit pairs in neighbouring cells; everything else is exactly zero in the reference as well
+    (l2 > tolerance_l2_max returns before anything is evaluated), so value, gradients and list
+    must not change.  Two forms of the sparse list in an open system: masked cluster tiles
+    (csrc/tiles.cu, the default) and packed entries in cell order (csrc/cells.cu)."""
     cb = _cb()
+    if form == "cells":
+        monkeypatch.setenv("B200CV_NO_TILES", "1")
     rng = np.random.default_rng(77)
     n1, n2 = (3000, 0) if kind == "selfCoordNum" else (700, 5000)
     L = 70.0  # ~0.01 atoms / A^3: a few listed pairs per atom
