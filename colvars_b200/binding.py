@@ -67,10 +67,10 @@ SYMBOLS = [
     "b200cv_set_group", "b200cv_set_fitting", "b200cv_set_boundaries", "b200cv_read_data",
     "b200cv_calc_value", "b200cv_step", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
     "b200cv_eval", "b200cv_eval_async", "b200cv_accumulate_gradients",
-    "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
+    "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_async_set_skip", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
-    "b200cv_pairlist_export", "b200cv_pairlist_stats", "b200cv_last_stats", "b200cv_kernel_launches", "b200cv_comm_unique_id",
+    "b200cv_pairlist_export", "b200cv_pairlist_stats", "b200cv_last_stats", "b200cv_kernel_launches", "b200cv_current_device", "b200cv_comm_unique_id",
     "b200cv_comm_init", "b200cv_set_shard", "b200cv_plan_items", "b200cv_fp64_peak", "b200cv_selftest_rcp",
 ]
 
@@ -107,6 +107,7 @@ def load():
     L.b200cv_accumulate_gradients.argtypes = [H, vp, vp, vp]
     L.b200cv_pairlist_reserve.argtypes = [H, vp, vp, C.c_double, vp]
     L.b200cv_pairlist_set_rebuild.argtypes = [H, C.c_int]
+    L.b200cv_async_set_skip.argtypes = [H, C.c_int]
     L.b200cv_eval_host.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
     L.b200cv_calc_host.argtypes = [H, vp, sz, ll, C.c_int, _dp]
     L.b200cv_apply_force_host.argtypes = [H, C.c_double, vp, sz]
@@ -121,6 +122,7 @@ def load():
     L.b200cv_pairlist_stats.argtypes = [H, _ip, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz),
                                         C.POINTER(sz)]
     L.b200cv_last_stats.argtypes = [H, _ip, C.POINTER(sz)]
+    L.b200cv_current_device.argtypes = [_ip]
     L.b200cv_kernel_launches.argtypes = []
     L.b200cv_kernel_launches.restype = C.c_ulonglong
     L.b200cv_comm_unique_id.argtypes = [C.c_char_p]
@@ -309,6 +311,9 @@ class CoordNum:
 
     def pairlist_set_rebuild(self, rebuild):
         self._check(self._L.b200cv_pairlist_set_rebuild(self._h, int(bool(rebuild))))
+
+    def async_set_skip(self, skip):
+        self._check(self._L.b200cv_async_set_skip(self._h, int(bool(skip))))
 
     def eval_host(self, pos1, pos2=None, flags=EF_GRADIENTS, grad1=None, grad2=None):
         """pos*/grad*: numpy SoA arrays (3, n) float64 in host memory; returns the value."""

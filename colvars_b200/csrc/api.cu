@@ -310,9 +310,10 @@ int b200cv_create(const b200cv_config *cfg, b200cv_cvc **out)
   CREATE_OK(cudaHostGetDevicePointer(&h->h_counters_dev, h->h_counters, 0));
   for (int k = 0; k < 8; k++) h->h_counters[k] = 0;
   for (int k = 0; k < 4; k++) h->h_value[k] = 0.0;
-  CREATE_OK(cudaHostAlloc(&h->h_mode, sizeof(int), cudaHostAllocMapped));
+  CREATE_OK(cudaHostAlloc(&h->h_mode, 2 * sizeof(int), cudaHostAllocMapped));
   CREATE_OK(cudaHostGetDevicePointer(&h->h_mode_dev, h->h_mode, 0));
-  *h->h_mode = 1;
+  h->h_mode[0] = 1;
+  h->h_mode[1] = 0;
   CREATE_OK(cudaMalloc(&h->d_counters, 32));
   CREATE_OK(cudaMemset(h->d_counters, 0, 32));
   CREATE_OK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -348,6 +349,7 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_items);
   cells_free(h->cells);
   tiles_free(h->tiles);
+  rows_free(h->rows);
   free_dev(h->d_stage_pos);
   if (h->h_value) cudaFreeHost(h->h_value);
   if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -681,7 +683,7 @@ static int eval_device(b200cv_cvc *h, const double *d_pos1, const double *d_pos2
   h->have_calc = true;
   h->data_read = true;
   h->async_eval = !sync;
-  h->gated = !sync && (flags & B200CV_EF_USE_PAIRLIST);
+  h->gated = !sync;  // every captured evaluation carries the mode word (rebuild / walk / skip)
   h->fit_after_calc = false;
   h->unchecked = true;
   if (sync) CUDA_OK_RC(prepare_calc(h, flags));
@@ -739,6 +741,13 @@ int b200cv_pairlist_set_rebuild(b200cv_cvc *h, int rebuild)
   return B200CV_OK;
 }
 
+int b200cv_async_set_skip(b200cv_cvc *h, int skip)
+{
+  if (!h) return B200CV_BUG_ERROR;
+  h->h_mode[1] = skip ? 1 : 0;  // mapped pinned: read by fetch_gate_kernel of the next launch
+  return B200CV_OK;
+}
+
 int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
                             double headroom, void *stream)
 {
@@ -771,10 +780,24 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
     h->pl_cap = want;
   }
   if (tiles_usable(h) && sparse_list(h)) {
-    unsigned const need = (unsigned)std::min(4.0e9, std::ceil(headroom * (double)tile_units_estimate(h)));
-    if (need > h->tiles.cap_units) {
-      h->epoch++;
-      CUDA_OK(h, tiles_reserve(h->tiles, need));
+    if (rows_preferred()) {
+      // two entries per listed pair, one chunk per atom and per ROW_BUF entries
+      double const atoms = (double)h->g[0].n + (h->self() ? 0.0 : (double)h->g[1].n);
+      double const ent = headroom * 2.0 * (double)h->pl_n + 65536.0;
+      double const chk = atoms + headroom * ent / ROW_BUF + 4096.0;
+      if ((unsigned)std::min(4.0e9, ent) > h->rows.cap_idx ||
+          (unsigned)std::min(4.0e9, chk) > h->rows.cap_chunks) {
+        h->epoch++;
+        CUDA_OK(h, rows_reserve(h->rows, (unsigned)std::min(4.0e9, ent),
+                                (unsigned)std::min(4.0e9, chk)));
+      }
+    } else {
+      unsigned const need =
+          (unsigned)std::min(4.0e9, std::ceil(headroom * (double)tile_units_estimate(h)));
+      if (need > h->tiles.cap_units) {
+        h->epoch++;
+        CUDA_OK(h, tiles_reserve(h->tiles, need));
+      }
     }
   }
   h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1);
@@ -937,6 +960,65 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
     if (h->self() && i > j) std::swap(i, j);
     return h->self() ? i * (2 * n1 - i - 1) / 2 + (j - i - 1) : i * n2 + j;
   };
+  if (h->pl_rows) {
+    // row form (rows.cuh): the canonical side of every row chunk + the extras (atom indices)
+    TileBuffers &B = h->tiles;
+    TileSide &J = B.side[1];
+    TileSide &I = h->self() ? J : B.side[0];
+    unsigned counts[8];
+    CUDA_OK(h, cudaMemcpy(counts, B.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
+    // valid slots: this rank's rows of each group, then the overflow chunks
+    std::vector<int4> all((size_t)h->rows.cap_chunks), chunks;
+    CUDA_OK(h, cudaMemcpy(all.data(), h->rows.d_chunks, sizeof(int4) * all.size(),
+                          cudaMemcpyDeviceToHost));
+    {
+      size_t const slots = row_slots(h);
+      int const ns[2] = {I.n, h->self() ? 0 : J.n};
+      size_t base = 0;
+      for (int d = 0; d < 2; d++) {
+        size_t const r0 = (size_t)ns[d] * (size_t)h->rank / (size_t)h->world;
+        size_t const r1 = (size_t)ns[d] * ((size_t)h->rank + 1) / (size_t)h->world;
+        for (size_t r = r0; r < r1; r++) chunks.push_back(all[base + r]);
+        base += (size_t)ns[d];
+      }
+      size_t const extra = std::min<size_t>(counts[6], all.size() > slots ? all.size() - slots : 0);
+      for (size_t x = 0; x < extra; x++) chunks.push_back(all[slots + x]);
+    }
+    std::vector<int> oi(I.n), oj(J.n);
+    std::vector<unsigned long long> ent((size_t)h->pl_entries);
+    CUDA_OK(h, cudaMemcpy(oi.data(), I.d_sorted, sizeof(int) * oi.size(), cudaMemcpyDeviceToHost));
+    CUDA_OK(h, cudaMemcpy(oj.data(), J.d_sorted, sizeof(int) * oj.size(), cudaMemcpyDeviceToHost));
+    if (!ent.empty()) {
+      CUDA_OK(h, cudaMemcpy(ent.data(), h->d_pl, sizeof(unsigned long long) * ent.size(),
+                            cudaMemcpyDeviceToHost));
+    }
+    size_t k = 0, used = 0;
+    for (auto const &c : chunks) used = std::max(used, (size_t)c.y + (size_t)std::max(c.z, 0));
+    used = std::min(used, (size_t)h->rows.cap_idx);
+    std::vector<int> idx(used);
+    if (used) {
+      CUDA_OK(h, cudaMemcpy(idx.data(), h->rows.d_idx, sizeof(int) * used, cudaMemcpyDeviceToHost));
+    }
+    for (auto const &c : chunks) {
+      int const p = c.x, start = c.y, len = c.z, dir = c.w;
+      bool const self = h->self();
+      if (!self && dir != 0) continue;  // the rows of group2 repeat the pairs of group1's rows
+      if (len <= 0 || (size_t)start + (size_t)len > used) continue;
+      for (int e = start; e < start + len; e++) {
+        int const q = idx[(size_t)e];
+        if (self && q <= p) continue;  // listed from the other atom's row
+        if (k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent row list");
+        out[k++] = canonical((unsigned long long)oi[(size_t)p], (unsigned long long)oj[(size_t)q]);
+      }
+    }
+    for (unsigned long long e : ent) {
+      if (k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent row list");
+      out[k++] = canonical(e >> 32, e & 0xffffffffull);
+    }
+    if (k != count) return fail(h, B200CV_BUG_ERROR, "row list does not add up to its pair count");
+    std::sort(out, out + count);
+    return B200CV_OK;
+  }
   if (h->pl_tiles) {
     // tile form (tiles.cuh): mask bits of every unit + the extras, all in sorted positions
     TileBuffers &B = h->tiles;
@@ -1040,7 +1122,12 @@ int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entri
     }
     for (auto const &u : hdr) ntiles += (size_t)u.z;
   }
-  if (form) *form = !h->pl_valid ? -1 : (h->pl_tiles ? 2 : (h->pl_sorted ? 1 : 0));
+  if (h->pl_valid && h->pl_rows) {
+    unsigned counts[8];
+    CUDA_OK(h, cudaMemcpy(counts, h->tiles.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
+    units = (size_t)row_slots(h) / (size_t)h->world + counts[6];
+  }
+  if (form) *form = !h->pl_valid ? -1 : (h->pl_rows ? 3 : (h->pl_tiles ? 2 : (h->pl_sorted ? 1 : 0)));
   if (pairs) *pairs = (size_t)h->pl_n;
   if (entries) *entries = (size_t)h->pl_entries;
   if (tile_units) *tile_units = units;
@@ -1049,6 +1136,14 @@ int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entri
 }
 
 unsigned long long b200cv_kernel_launches(void) { return launches_so_far(); }
+
+int b200cv_current_device(int *device)
+{
+  if (!device) return B200CV_BUG_ERROR;
+  cudaError_t const e = cudaGetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, B200CV_ERROR, cudaGetErrorString(e));
+  return B200CV_OK;
+}
 
 #if defined(B200CV_TRACE)
 // debug builds only: {start, tiles begin, tiles end, end (ns), smid} per CTA of the last sweep

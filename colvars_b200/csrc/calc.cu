@@ -118,11 +118,44 @@ unsigned tile_units_estimate(const b200cv_cvc *h)
   return (unsigned)std::min<unsigned long long>(units, 1ull << 28);
 }
 
+// chunk slots taken by the rows themselves (one per atom of both groups); overflow chunks follow
+unsigned row_slots(const b200cv_cvc *h)
+{
+  return (unsigned)h->g[0].n + (h->self() ? 0u : (unsigned)h->g[1].n);
+}
+
+// which sparse form a rebuild produces: neighbour rows (rows.cuh) unless B200CV_LIST_FORM=tiles
+bool rows_preferred()
+{
+  const char *f = std::getenv("B200CV_LIST_FORM");
+  return !(f && std::strcmp(f, "tiles") == 0);
+}
+
+// entries / chunks the rows of the next rebuild may need: two entries per listed pair (one per
+// direction), one chunk per atom plus one per ROW_BUF entries; a guess that turns out too small
+// costs one redo of the step
+static void row_estimate(const b200cv_cvc *h, unsigned &entries, unsigned &chunks)
+{
+  unsigned long long const atoms = (unsigned long long)h->g[0].n + (h->self() ? 0ull : (unsigned long long)h->g[1].n);
+  unsigned long long const e = 2ull * h->pl_n + h->pl_n / 2ull + 65536ull;
+  unsigned long long const c = atoms + e / (unsigned long long)ROW_BUF + 4096ull;
+  entries = (unsigned)std::min<unsigned long long>(e, 0xfffffff0ull);
+  chunks = (unsigned)std::min<unsigned long long>(c, 0xfffffff0ull);
+}
+
 int prepare_calc(b200cv_cvc *h, int flags)
 {
   if (!(flags & B200CV_EF_USE_PAIRLIST)) return B200CV_OK;
-  bool const tiles_next = h->gated ? (tiles_usable(h) && sparse_list(h)) : rebuild_with_tiles(h, flags);
-  if (tiles_next && h->tiles.cap_units == 0) {
+  bool const sparse_next = h->gated ? (tiles_usable(h) && sparse_list(h)) : rebuild_with_tiles(h, flags);
+  if (!sparse_next) return B200CV_OK;
+  if (rows_preferred()) {
+    if (h->rows.cap_idx == 0) {
+      unsigned entries, chunks;
+      row_estimate(h, entries, chunks);
+      h->epoch++;
+      CUDA_OK(h, rows_reserve(h->rows, entries, chunks));
+    }
+  } else if (h->tiles.cap_units == 0) {
     h->epoch++;
     CUDA_OK(h, tiles_reserve(h->tiles, tile_units_estimate(h)));
   }
@@ -163,17 +196,24 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
   h->launches = 0;
   int npart = 0;
   bool const gated = h->gated && use_pl;
+  // captured evaluation without a pair list: one form only, but the host may still have to skip
+  // a launch (mode 2, b200cv_async_set_skip); its kernels run in mode 0
+  bool const skip_gated = h->gated && !use_pl;
 
   CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, 16, stream));
   // this evaluation builds or walks the tile form of the list
-  bool const tiles_gated = gated && tiles_usable(h) && sparse_list(h) && h->tiles.cap_units > 0;
+  bool const build_rows = rows_preferred();
+  bool const sparse_ready = build_rows ? h->rows.cap_idx > 0 : h->tiles.cap_units > 0;
+  bool const tiles_gated = gated && tiles_usable(h) && sparse_list(h) && sparse_ready;
   bool const tiles_eval =
       use_pl && !(h->center1() || h->center2()) &&
-      (tiles_gated || (!gated && ((!rebuild && h->pl_valid && h->pl_tiles) ||
-                                  (rebuild_with_tiles(h, flags) && h->tiles.cap_units > 0))));
+      (tiles_gated || (!gated && ((!rebuild && h->pl_valid && (h->pl_tiles || h->pl_rows)) ||
+                                  (rebuild_with_tiles(h, flags) && sparse_ready))));
+  // the form this evaluation works on: the one being built, or the one the current list has
+  bool const rows_eval = tiles_eval && ((tiles_gated || rebuild) ? build_rows : h->pl_rows);
   if (tiles_eval) CUDA_OK(h, cudaMemsetAsync(h->tiles.d_counts, 0, 6 * sizeof(unsigned), stream));
-  if (gated) {
-    CUDA_OK(h, launch_fetch_gate(h->h_mode_dev, h->gate(), stream));
+  if (gated || skip_gated) {
+    CUDA_OK(h, launch_fetch_gate(h->h_mode_dev, h->gate(), gated ? 1 : 0, stream));
     h->launches++;
   }
   // the final sum: a launch of its own, or the last CTA of the exact kernel (`finalized`)
@@ -187,12 +227,14 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     F.rare_count = h->rare_count();
     F.pl_count = h->pl_count();
     F.h_counters = h->h_counters_dev;
-    F.gate = gated ? h->gate() : nullptr;
+    F.gate = (gated || skip_gated) ? h->gate() : nullptr;
     F.rebuilt = (!gated && use_pl && rebuild && !(h->center1() || h->center2())) ? 1 : 0;
     F.pl_persist = h->pl_count() + 1;
     F.pl_cap = h->pl_cap;
     F.tile_counts = tiles_eval ? h->tiles.d_counts : nullptr;
-    F.tile_cap = h->tiles.cap_units;
+    F.tile_cap = rows_eval ? (h->rows.cap_chunks > row_slots(h) ? h->rows.cap_chunks - row_slots(h) : 0u)
+                           : h->tiles.cap_units;
+    F.tile_cap2 = rows_eval ? h->rows.cap_idx : 0xffffffffu;
     F.rare_cap = h->rare_cap;
     F.overflow = (h->world > 1) ? h->d_reduce + 1 : nullptr;
     return F;
@@ -207,7 +249,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     A.flags = flags;
     A.partials = h->d_partials;
     A.pairlist = use_pl ? h->d_pl_center : nullptr;
-    A.gate = gated ? h->gate() : nullptr;
+    A.gate = (gated || skip_gated) ? h->gate() : nullptr;
     CUDA_OK(h, cudaMemsetAsync(G1.com_grad(), 0, 3 * sizeof(double), stream));
     CUDA_OK(h, cudaMemsetAsync(G2.com_grad(), 0, 3 * sizeof(double), stream));
     if (h->center1() && h->center2()) {
@@ -323,8 +365,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     // every pair: tile sweep (+ exact-pair queue) or, for mixed / triclinic cells, the dense
     // kernel; records the pair list when `record`.  Returns the number of partial sums.
     auto enqueue_all_pairs = [&](int sweep_flags, bool record, const int *gate,
-                                 int &nparts) -> int {
-      if (record) h->pl_sorted = h->pl_tiles = false;  // the sweep and the dense kernel list (i, j) as they are
+                                 int &nparts, int gate_on = 1) -> int {
+      if (record) h->pl_sorted = h->pl_tiles = h->pl_rows = false;  // the sweep and the dense kernel list (i, j) as they are
       if (general_bc) {
         DenseArgs D{};
         D.x1 = x1; D.y1 = y1; D.z1 = z1; D.x2 = x2; D.y2 = y2; D.z2 = z2;
@@ -340,7 +382,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
         D.pl_count = h->pl_count();
         D.flags = sweep_flags;
         D.gate = gate;
-        D.gate_on = 1;
+        D.gate_on = gate_on;
         D.P = h->P;
         CUDA_OK(h, launch_dense(D, stream));
         h->launches++;
@@ -361,7 +403,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       S.i_end = G1.n;
       S.want_grad = grad ? 1 : 0;
       S.gate = gate;
-      S.gate_on = 1;
+      S.gate_on = gate_on;
       S.P = h->P;
       int const pbc = h->P.bc_type == 2 ? BC_ORTHO : (general_cell ? BC_GENERAL : BC_NONE);
       CUDA_OK(h, launch_sweep(S, h->nitems, h->exp_special, h->aniso, pbc, use_pl, stream));
@@ -380,7 +422,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.pl_count = h->pl_count();
       E.flags = sweep_flags;
       E.gate = gate;
-      E.gate_on = 1;
+      E.gate_on = gate_on;
       nparts = h->nitems + EXACT_BLOCKS;
       if (gate == nullptr) {
         E.fin_ticket = h->fin_ticket();
@@ -424,7 +466,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.flags = cell_flags;
       C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // every kind of cell has a fast form
       h->pl_sorted = sorted_walk_enabled();
-      h->pl_tiles = false;
+      h->pl_tiles = h->pl_rows = false;
       C.sorted_entries = h->pl_sorted ? 1 : 0;
       C.gate = gate;
       C.P = h->P;
@@ -479,7 +521,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       CUDA_OK(h, launch_tile_build(T, h->exp_special, h->aniso, stream));
       h->launches++;
       h->pl_tiles = true;
-      h->pl_sorted = false;
+      h->pl_sorted = h->pl_rows = false;
       ExactArgs E{};
       tile_planes(E);
       E.list = h->d_rare;
@@ -559,12 +601,139 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       return B200CV_OK;
     };
 
+    // ---- the list as neighbour rows (rows.cuh): open systems, sparse lists --------------------
+    auto row_sides = [&](RowSideView &s1, RowSideView &s2) {
+      TileSide &J = h->tiles.side[1];
+      TileSide &I = h->self() ? J : h->tiles.side[0];
+      s1 = RowSideView{I.d_xs, I.d_ys, I.d_zs, I.d_sorted, I.d_cell_start, I.n, G1.d_grad, G1.stride};
+      s2 = RowSideView{J.d_xs, J.d_ys, J.d_zs, J.d_sorted, J.d_cell_start, J.n, G2.d_grad, G2.stride};
+    };
+    // exact-pair queue (and, on list steps, the extras) on the groups' own arrays: the rows queue
+    // atom indices.  Partial sums of the exact kernel at `partials`.
+    auto enqueue_row_exact = [&](int exact_flags, bool walk, double *partials, int nparts,
+                                 const int *gate, int gate_on) -> int {
+      ExactArgs E{};
+      E.x1 = x1; E.y1 = y1; E.z1 = z1; E.x2 = x2; E.y2 = y2; E.z2 = z2;
+      E.g1x = g1x; E.g1y = g1y; E.g1z = g1z; E.g2x = g2x; E.g2y = g2y; E.g2z = g2z;
+      E.list = h->d_rare;
+      E.count32 = h->rare_count();
+      E.cap = h->rare_cap;
+      if (walk) {
+        E.list2 = h->d_pl;
+        E.count2 = h->pl_count() + 1;  // persistent length of the extras
+        E.cap2 = h->pl_cap;
+        E.fast_exp = (h->exp_special == 3) ? 3 : 0;
+      } else {
+        E.pl = h->d_pl;
+        E.pl_cap = h->pl_cap;
+        E.pl_count = h->pl_count();
+      }
+      E.partials = partials;
+      E.flags = exact_flags;
+      E.gate = gate;
+      E.gate_on = gate_on;
+      if (gate == nullptr) {
+        E.fin_ticket = h->fin_ticket();
+        E.fin = finalize_args(nparts);
+        finalized = true;
+      }
+      E.P = h->P;
+      CUDA_OK(h, launch_exact(E, stream));
+      h->launches++;
+      return B200CV_OK;
+    };
+    // rebuild.  Partial sums: [ROW_BLOCKS (| ROW_BLOCKS for the rows of group2) | EXACT_BLOCKS]
+    auto enqueue_rows_build = [&](int build_flags, double *partials, const int *gate,
+                                  int &nparts) -> int {
+      TileBuffers &B = h->tiles;
+      CUDA_OK(h, tiles_sort(B, x1, y1, z1, x2, y2, z2, gate, stream));
+      h->launches += h->self() ? 5 : 8;
+      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
+      h->launches++;
+      RowSideView s1, s2;
+      row_sides(s1, s2);
+      int const ndir = h->self() ? 1 : 2;
+      for (int dir = 0; dir < ndir; dir++) {
+        RowBuildArgs T{};
+        T.own = dir == 0 ? s1 : s2;
+        T.nbr = (h->self() || dir == 1) ? s1 : s2;
+        T.grid = B.d_grid;
+        T.self = h->self() ? 1 : 0;
+        T.canonical = dir == 0 ? 1 : 0;
+        T.own_is_group1 = dir == 0 ? 1 : 0;
+        T.dir = dir;
+        T.row_begin = (int)((long long)T.own.n * h->rank / h->world);
+        T.row_end = (int)((long long)T.own.n * (h->rank + 1) / h->world);
+        T.idx = h->rows.d_idx;
+        T.cap_idx = h->rows.cap_idx;
+        T.chunks = h->rows.d_chunks;
+        T.cap_chunks = h->rows.cap_chunks;
+        T.chunk_base = dir == 0 ? 0u : (unsigned)s1.n;
+        T.chunk_extra = row_slots(h);
+        T.counts = B.d_counts;
+        T.rare = h->d_rare;
+        T.rare_cap = h->rare_cap;
+        T.rare_count = h->rare_count();
+        T.partials = partials + dir * ROW_BLOCKS;
+        T.want_grad = grad ? 1 : 0;
+        cell_cutoffs(h, T.cut);
+        for (int d = 0; d < 3; d++) T.cut[d] *= (1.0 + 1.0e-9);
+        T.gate = gate;
+        T.P = h->P;
+        CUDA_OK(h, launch_row_build(T, h->exp_special, h->aniso, stream));
+        h->launches++;
+      }
+      h->pl_rows = true;
+      h->pl_tiles = h->pl_sorted = false;
+      nparts = ndir * ROW_BLOCKS + EXACT_BLOCKS;
+      return enqueue_row_exact(build_flags, false, partials + ndir * ROW_BLOCKS, nparts, gate, 1);
+    };
+    // list step.  Partial sums: [ROW_BLOCKS | EXACT_BLOCKS]
+    auto enqueue_rows_walk = [&](double *partials, const int *gate) -> int {
+      TileBuffers &B = h->tiles;
+      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
+      h->launches++;
+      RowWalkArgs T{};
+      row_sides(T.side[0], T.side[1]);
+      T.self = h->self() ? 1 : 0;
+      T.idx = h->rows.d_idx;
+      T.chunks = h->rows.d_chunks;
+      T.cap_chunks = h->rows.cap_chunks;
+      for (int d = 0; d < 2; d++) {
+        int const n = T.side[d].n;
+        T.row_begin[d] = (int)((long long)n * h->rank / h->world);
+        T.row_end[d] = (int)((long long)n * (h->rank + 1) / h->world);
+      }
+      T.chunk_base1 = (unsigned)T.side[0].n;
+      T.chunk_extra = row_slots(h);
+      T.counts = B.d_counts;
+      T.rare = h->d_rare;
+      T.rare_cap = h->rare_cap;
+      T.rare_count = h->rare_count();
+      T.partials = partials;
+      T.want_grad = grad ? 1 : 0;
+      T.gate = gate;
+      T.P = h->P;
+      CUDA_OK(h, launch_row_walk(T, h->exp_special, h->aniso, stream));
+      h->launches++;
+      return enqueue_row_exact(flags & ~B200CV_EF_REBUILD_PAIRLIST, true, partials + ROW_BLOCKS,
+                               ROW_BLOCKS + EXACT_BLOCKS, gate, 0);
+    };
+
     if (gated) {
       // captured evaluation with a pair list: the graph holds the rebuild sweep AND the list
       // walk; the mode word decides on the device which of the two does any work
       int nparts = 0;
       int rc;
-      if (tiles_gated) {
+      if (tiles_gated && rows_eval) {
+        static_assert(3 * ROW_BLOCKS + 2 * EXACT_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
+        int nb = 0;
+        rc = enqueue_rows_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate(), nb);
+        if (rc) return rc;
+        rc = enqueue_rows_walk(h->d_partials + nb, h->gate());
+        if (rc) return rc;
+        npart = nb + ROW_BLOCKS + EXACT_BLOCKS;
+      } else if (tiles_gated) {
         static_assert(2 * (TILE_BLOCKS + EXACT_BLOCKS) <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
         rc = enqueue_tiles_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate());
         if (rc) return rc;
@@ -585,10 +754,15 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
         npart = nparts + WALK_BLOCKS;
       }
     } else if (walk_list) {
-      int rc = h->pl_tiles ? enqueue_tiles_walk(h->d_partials, nullptr)
-                           : enqueue_walk(h->d_partials, nullptr);
+      int rc = h->pl_rows ? enqueue_rows_walk(h->d_partials, nullptr)
+                          : (h->pl_tiles ? enqueue_tiles_walk(h->d_partials, nullptr)
+                                         : enqueue_walk(h->d_partials, nullptr));
       if (rc) return rc;
-      npart = h->pl_tiles ? TILE_BLOCKS + EXACT_BLOCKS : WALK_BLOCKS;
+      npart = h->pl_rows ? ROW_BLOCKS + EXACT_BLOCKS
+                         : (h->pl_tiles ? TILE_BLOCKS + EXACT_BLOCKS : WALK_BLOCKS);
+    } else if (tiles_eval && rows_eval) {
+      int rc = enqueue_rows_build(flags, h->d_partials, nullptr, npart);
+      if (rc) return rc;
     } else if (tiles_eval) {
       int rc = enqueue_tiles_build(flags, h->d_partials, nullptr);
       if (rc) return rc;
@@ -598,7 +772,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       if (rc) return rc;
       npart = CELL_BLOCKS;
     } else {
-      int rc = enqueue_all_pairs(flags, rebuild, nullptr, npart);
+      int rc = enqueue_all_pairs(flags, rebuild, skip_gated ? h->gate() : nullptr, npart, 0);
       if (rc) return rc;
     }
   }
@@ -660,7 +834,8 @@ int post_sync(b200cv_cvc *h, bool &redo)
   // gated (captured) evaluations: finalize_kernel reports the mode the finished launch ran in
   bool const rebuild = h->gated ? (h->h_counters[2] == 1)
                                 : (bool)(h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
-  bool const tiles_built = rebuild && h->pl_tiles;
+  bool const tiles_built = rebuild && (h->pl_tiles || h->pl_rows);
+  unsigned long long const row_entries = h->h_counters[5];
   h->exact_pairs = (size_t)rare_n;
   if (rare_n > h->rare_cap) {
     if (h->async_eval) {
@@ -676,7 +851,10 @@ int post_sync(b200cv_cvc *h, bool &redo)
   }
   if (rebuild && !(h->center1() || h->center2())) {
     bool const over_pl = pl_n > h->pl_cap;
-    bool const over_tiles = tiles_built && units > h->tiles.cap_units;
+    bool const over_tiles =
+        tiles_built && (h->pl_rows ? (units + row_slots(h) > h->rows.cap_chunks ||
+                                      row_entries > h->rows.cap_idx)
+                                   : units > h->tiles.cap_units);
     if ((over_pl || over_tiles) && h->async_eval) {
       return fail(h, B200CV_MEMORY_ERROR,
                   "pair-list overflow in a captured evaluation (" + std::to_string(pl_n) +
@@ -691,8 +869,15 @@ int post_sync(b200cv_cvc *h, bool &redo)
     }
     if (over_tiles) {
       h->epoch++;
-      CUDA_OK(h, tiles_reserve(h->tiles, (unsigned)std::min<unsigned long long>(
-                                             units + units / 2, 1ull << 30)));
+      if (h->pl_rows) {
+        CUDA_OK(h, rows_reserve(h->rows,
+                                (unsigned)std::min<unsigned long long>(row_entries + row_entries / 4 + 1024, 0xfffffff0ull),
+                                (unsigned)std::min<unsigned long long>(
+                                    row_slots(h) + units + units / 4 + 1024, 0xfffffff0ull)));
+      } else {
+        CUDA_OK(h, tiles_reserve(h->tiles, (unsigned)std::min<unsigned long long>(
+                                               units + units / 2, 1ull << 30)));
+      }
     }
     if (over_pl || over_tiles) {
       redo = true;

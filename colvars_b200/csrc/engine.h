@@ -30,6 +30,7 @@
 #include "fit.cuh"
 #include "kernels.cuh"
 #include "tiles.cuh"
+#include "rows.cuh"
 
 namespace b200cv {
 
@@ -114,6 +115,10 @@ struct b200cv_cvc {
   b200cv::TileBuffers tiles;
   bool tiles_ready = false;
   bool pl_tiles = false;   // the current list is in tile form
+  // ... or as neighbour rows (rows.cuh, the default sparse form): both directions of every pair,
+  // d_pl again holds the extras (atom indices here)
+  b200cv::RowList rows;
+  bool pl_rows = false;
   // an evaluation has been enqueued whose queue counters / new list lengths the host has not
   // looked at yet (sync_and_check): the next call that builds on its result checks first
   bool unchecked = false;
@@ -226,6 +231,8 @@ bool rebuild_with_cells(const b200cv_cvc *h, int flags);
 bool tiles_usable(const b200cv_cvc *h);
 bool rebuild_with_tiles(const b200cv_cvc *h, int flags);
 unsigned tile_units_estimate(const b200cv_cvc *h);
+bool rows_preferred();
+unsigned row_slots(const b200cv_cvc *h);
 // allocations an evaluation with these flags may need (tile arrays): before any stream capture
 int prepare_calc(b200cv_cvc *h, int flags);
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need);

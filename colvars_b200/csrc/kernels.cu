@@ -60,12 +60,14 @@ __device__ __forceinline__ void finalize_body(FinalizeArgs const &A, double *red
     if (A.tile_counts && A.h_counters) {
       A.h_counters[3] = (unsigned long long)*(const volatile unsigned *)A.tile_counts;
       A.h_counters[4] = *(const volatile unsigned long long *)(A.tile_counts + 4);
+      A.h_counters[5] = (unsigned long long)*(const volatile unsigned *)(A.tile_counts + 3);
     }
     if (A.overflow) {
       bool over = A.rare_count && *(const volatile unsigned int *)A.rare_count > A.rare_cap;
       if (rebuilt) {
         over = over || (A.pl_count && *(const volatile unsigned long long *)A.pl_count > A.pl_cap);
-        over = over || (A.tile_counts && *(const volatile unsigned *)A.tile_counts > A.tile_cap);
+        over = over || (A.tile_counts && (*(const volatile unsigned *)A.tile_counts > A.tile_cap ||
+                                          *(const volatile unsigned *)(A.tile_counts + 3) > A.tile_cap2));
       }
       *A.overflow = over ? 1.0 : 0.0;
     }
@@ -284,6 +286,10 @@ __global__ void __launch_bounds__(EXACT_THREADS) center_kernel(const __grid_cons
   __shared__ double red[EXACT_THREADS / 32];
   bool const grad = A.flags & EF_GRADIENTS;
   bool const use_pl = A.flags & EF_USE_PAIRLIST;
+  if (A.gate != nullptr && *A.gate == 2) {  // skipped launch of a captured evaluation
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
+    return;
+  }
   bool const rebuild = A.gate ? (*A.gate == 1) : (bool)(A.flags & EF_REBUILD_PAIRLIST);
   double const cx = A.center[0], cy = A.center[1], cz = A.center[2];
   double fsum = 0.0, sgx = 0.0, sgy = 0.0, sgz = 0.0;
@@ -367,11 +373,16 @@ int launch_finalize(const FinalizeArgs &args, cudaStream_t stream)
   return (int)cudaGetLastError();
 }
 
-__global__ void fetch_gate_kernel(const int *h_mode_dev, int *d_gate) { *d_gate = *h_mode_dev; }
-
-int launch_fetch_gate(const int *h_mode_dev, int *d_gate, cudaStream_t stream)
+// mode word of a captured evaluation: h_mode[0] = 1 rebuild / 0 walk (or plain evaluation),
+// h_mode[1] != 0: skip this launch altogether (mode 2: no kernel of the evaluation does any work)
+__global__ void fetch_gate_kernel(const int *h_mode_dev, int *d_gate, int with_list)
 {
-  fetch_gate_kernel<<<1, 1, 0, stream>>>(h_mode_dev, d_gate);
+  *d_gate = h_mode_dev[1] != 0 ? 2 : (with_list ? h_mode_dev[0] : 0);
+}
+
+int launch_fetch_gate(const int *h_mode_dev, int *d_gate, int with_list, cudaStream_t stream)
+{
+  fetch_gate_kernel<<<1, 1, 0, stream>>>(h_mode_dev, d_gate, with_list);
   note_launch();
   return (int)cudaGetLastError();
 }

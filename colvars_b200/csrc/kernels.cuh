@@ -53,7 +53,8 @@ struct FinalizeArgs {
   unsigned long long *pl_persist;
   unsigned long long pl_cap;
   unsigned *tile_counts;  // TileBuffers::d_counts or null
-  unsigned tile_cap;
+  unsigned tile_cap;      // capacity in units (tiles) or chunks (rows)
+  unsigned tile_cap2;     // rows: capacity in entries (counts[3]); tiles: unused (all ones)
   // sharded runs: 1.0 when a queue of this rank overflowed, else 0.0, into the word that the
   // all-reduce sums next to the value (null: single rank)
   unsigned int rare_cap;
@@ -96,7 +97,7 @@ constexpr int EXACT_THREADS = 128;
 constexpr int WALK_BLOCKS = 1184;
 // partial sums behind the sweep items: [rare queue | walk], [cell kernel (592) | walk] or
 // [tile build | its exact queue | tile walk | its exact lists]
-constexpr int PARTIALS_TAIL = 4096;
+constexpr int PARTIALS_TAIL = 6144;
 int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks = EXACT_BLOCKS);
 
 // Dense fallback for boundary conditions the tile sweep does not specialise (mixed /
@@ -140,8 +141,10 @@ int launch_center(const CenterArgs &args, cudaStream_t stream);
 
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
 
-// copies the host-written mode word (mapped pinned) into device memory once per evaluation
-int launch_fetch_gate(const int *h_mode_dev, int *d_gate, cudaStream_t stream);
+// copies the host-written mode word (mapped pinned) into device memory once per evaluation:
+// 2 when the host asked to skip the launch, else rebuild (1) / walk (0) for pair-list
+// evaluations (with_list) and 0 for the others
+int launch_fetch_gate(const int *h_mode_dev, int *d_gate, int with_list, cudaStream_t stream);
 
 // distanceInv epilogue (src/colvarcomp_distances.cpp:442-455): *d_value holds sum_ij d^-n
 // (already reduced over ranks); x = (sum / npairs)^(-1/n) replaces it and every gradient entry

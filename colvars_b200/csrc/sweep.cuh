@@ -452,11 +452,9 @@ __global__ void __launch_bounds__(W * 32, MINB) sweep_kernel(const __grid_consta
     }
   }
 
-  if constexpr (PL) {
-    if (A.gate != nullptr && *A.gate != A.gate_on) {
-      if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
-      return;
-    }
+  if (A.gate != nullptr && *A.gate != A.gate_on) {
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
+    return;
   }
 #if defined(B200CV_TRACE)
   unsigned long long const trace_t0 = trace_now();

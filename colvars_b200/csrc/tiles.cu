@@ -85,14 +85,6 @@ tile_grid_kernel(const double *__restrict__ x, const double *__restrict__ y,
   }
 }
 
-// cell index along one axis, clamped to the grid: monotonic in p, so "every atom with
-// coordinate >= a sits in a cell >= cell(a)" holds for atoms inside and outside the grid alike
-__device__ __forceinline__ int tile_cell(double p, double origin, double inv_cell, int dim)
-{
-  double const c = floor((p - origin) * inv_cell);
-  return (int)fmin(fmax(c, 0.0), (double)(dim - 1));
-}
-
 __global__ void tile_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                 const double *__restrict__ z, int n,
                                 const TileGrid *__restrict__ grid, int *key, int *val,

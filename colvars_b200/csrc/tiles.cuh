@@ -57,6 +57,14 @@ struct TileGrid {
   int nrows;  // dim[1] * dim[2]: rows of cells along x
 };
 
+// cell index along one axis, clamped to the grid: monotonic in p, so "every atom with
+// coordinate >= a sits in a cell >= cell(a)" holds for atoms inside and outside the grid alike
+__device__ __forceinline__ int tile_cell(double p, double origin, double inv_cell, int dim)
+{
+  double const c = floor((p - origin) * inv_cell);
+  return (int)fmin(fmax(c, 0.0), (double)(dim - 1));
+}
+
 // one sorted group
 struct TileSide {
   int n = 0;

@@ -3,7 +3,11 @@
 #include "coordnum_b200.h"
 
 #include <cctype>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <thread>
 #include <vector>
 
 #include "colvaratoms.h"
@@ -37,6 +41,81 @@ struct component_registry : public colvar {
     global_cvc_map["hBond"] = []() -> colvar::cvc * { return new hbond_b200(); };
   }
 };
+
+// One process per GPU: the engine -- or the launcher, torchrun style --
+// tells every process its place through the environment.  B200CV_RANK / B200CV_WORLD (else
+// RANK / WORLD_SIZE), B200CV_DEVICE (else LOCAL_RANK when sharded, else the device current on
+// the calling thread, i.e. the one the proxy's stream lives on, src/colvarproxy_gpu.h:25),
+// B200CV_NCCL_ID_FILE: a path unique to the run through which rank 0 hands the NCCL id of every
+// component to the other ranks (plain files: the host has no MPI of its own).
+struct shard_env {
+  int rank = 0, world = 1, device = 0;
+  std::string id_file;
+};
+
+int env_int(char const *a, char const *b, int def)
+{
+  char const *v = std::getenv(a);
+  if (!v && b) v = std::getenv(b);
+  return v ? std::atoi(v) : def;
+}
+
+shard_env read_shard_env()
+{
+  shard_env e;
+  if (char const *f = std::getenv("B200CV_NCCL_ID_FILE")) e.id_file = f;
+  if (!e.id_file.empty()) {
+    e.world = env_int("B200CV_WORLD", "WORLD_SIZE", 1);
+    e.rank = env_int("B200CV_RANK", "RANK", 0);
+  }
+  int current = 0;
+  if (b200cv_current_device(&current) != B200CV_OK) current = 0;
+  e.device = env_int("B200CV_DEVICE", e.world > 1 ? "LOCAL_RANK" : nullptr, current);
+  return e;
+}
+
+// components are created in the same order on every rank: the serial number names the id file
+int g_component_serial = 0;
+
+int join_shards(b200cv_cvc *h, shard_env const &e, std::string &err)
+{
+  std::string const path = e.id_file + "." + std::to_string(g_component_serial++);
+  unsigned char id[128];
+  if (e.rank == 0) {
+    if (b200cv_comm_unique_id(id) != B200CV_OK) {
+      err = b200cv_last_error(nullptr);
+      return COLVARS_ERROR;
+    }
+    std::string const tmp = path + ".tmp";
+    {
+      std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+      f.write(reinterpret_cast<char const *>(id), sizeof(id));
+    }
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) {
+      err = "cannot write " + path;
+      return COLVARS_FILE_ERROR;
+    }
+  } else {
+    bool ok = false;
+    for (int attempt = 0; attempt < 1200 && !ok; attempt++) {  // up to two minutes
+      std::ifstream f(path, std::ios::binary);
+      if (f && f.read(reinterpret_cast<char *>(id), sizeof(id)) && f.gcount() == sizeof(id)) {
+        ok = true;
+      } else {
+        std::this_thread::sleep_for(std::chrono::milliseconds(100));
+      }
+    }
+    if (!ok) {
+      err = "timed out waiting for " + path + " (rank 0 writes it)";
+      return COLVARS_FILE_ERROR;
+    }
+  }
+  if (b200cv_comm_init(h, id, e.rank, e.world) != B200CV_OK) {
+    err = b200cv_last_error(h);
+    return COLVARS_ERROR;
+  }
+  return COLVARS_OK;
+}
 
 int set_engine_group(b200cv_cvc *h, int which, cvm::atom_group *g)
 {
@@ -177,8 +256,12 @@ int coordnum_b200::init(std::string const &conf)
   return error_code | create_engine(cfg);
 }
 
-int coordnum_b200::create_engine(b200cv_config const &cfg)
+int coordnum_b200::create_engine(b200cv_config const &cfg_in)
 {
+  // the device of the proxy's context; one rank of a sharded run when the environment says so
+  shard_env const env = read_shard_env();
+  b200cv_config cfg = cfg_in;
+  cfg.device = env.device;
   int rc = b200cv_create(&cfg, &engine);
   if (rc != B200CV_OK) {
     return cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
@@ -186,6 +269,15 @@ int coordnum_b200::create_engine(b200cv_config const &cfg)
   rc = set_engine_group(engine, 1, group1);
   if (rc == B200CV_OK && group2) rc = set_engine_group(engine, 2, group2);
   if (rc != B200CV_OK) return b200_error(rc);
+  if (env.world > 1) {
+    // group1 rows over the ranks, one ncclAllReduce of [value | grad1 | grad2] per evaluation:
+    // every rank ends up with the full value and gradients, the host above notices nothing
+    std::string err;
+    int const jrc = join_shards(engine, env, err);
+    if (jrc != COLVARS_OK) return cvmodule->error("Error: " + err + "\n", jrc);
+    cvmodule->log("b200cv: component \"" + name + "\" sharded, rank " + cvm::to_str(env.rank) +
+                  " of " + cvm::to_str(env.world) + " on device " + cvm::to_str(env.device) + "\n");
+  }
 #if defined(COLVARS_CUDA)
   if (has_gpu_implementation()) {
     // positions and gradients stay on the device (as colvar::rmsd does,
@@ -281,7 +373,7 @@ int hbond_b200::init(std::string const &conf)
   cfg.cutoff3[2] = r0_vec.z;
   cfg.exp_numer = en;
   cfg.exp_denom = ed;
-  cfg.device = 0;
+  cfg.device = read_shard_env().device;  // one pair: never sharded
   int rc = b200cv_create(&cfg, &engine);
   if (rc != B200CV_OK) {
     return error_code | cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);

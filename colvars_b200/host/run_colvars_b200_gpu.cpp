@@ -6,6 +6,7 @@
 // memory, one stream.  Same command line and output files as the reference's runners.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -191,6 +192,15 @@ int main(int argc, char **argv)
   if (config.empty() || traj.empty()) {
     std::cerr << "usage: run_colvars_b200_gpu -c test.in -t trajectory.xyz [-o prefix [--force]]\n";
     return 2;
+  }
+  // one process per GPU: the device of this rank (torchrun-style LOCAL_RANK, or B200CV_DEVICE);
+  // the components pick it up from the context (coordnum_b200.cpp, read_shard_env)
+  if (char const *dev = std::getenv("B200CV_DEVICE") ? std::getenv("B200CV_DEVICE")
+                                                     : std::getenv("LOCAL_RANK")) {
+    if (cudaSetDevice(std::atoi(dev)) != cudaSuccess) {
+      std::cerr << "cannot select CUDA device " << dev << "\n";
+      return 2;
+    }
   }
   device_proxy *proxy = new device_proxy();
   colvarmodule *cvmodule = proxy->cvmodule;

@@ -183,6 +183,14 @@ int b200cv_eval_async(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
 int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d_pos2,
                             double headroom, void *stream);
 int b200cv_pairlist_set_rebuild(b200cv_cvc *h, int rebuild);
+/* Captured evaluations freeze what they were enqueued with: the periodic cell and the
+ * addresses of the queues.  skip != 0 makes the NEXT launch of a captured b200cv_eval_async do
+ * nothing (every kernel of it returns at once) -- for the step on which the caller has found
+ * the frozen state out of date (the cell changed: cvc::read_data copies it every step,
+ * src/colvarcomp.cpp:457-465) and evaluates with b200cv_eval instead, before it captures again.
+ * May be called from a host node of the same graph (cudaLaunchHostFunc), i.e. after the engine
+ * has delivered this step's cell and before the kernels read the word. */
+int b200cv_async_set_skip(b200cv_cvc *h, int skip);
 
 /* d_grad1 / d_grad2 (d_atoms_grad layout) += the gradients of the last evaluation, with
  * atomics (groups may be shared between components).  Only enqueues work: this is the node
@@ -237,6 +245,11 @@ int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs);
 /* Kernels this library has launched in this process so far (all handles, every stream).
  * bench.py reports the difference over its timed region as "gpu_launches". */
 unsigned long long b200cv_kernel_launches(void);
+
+/* The CUDA device current on the calling thread: the one the engine's proxy works on (its
+ * stream, src/colvarproxy_gpu.h:25, belongs to that device).  The `colvar::cvc` shim creates its
+ * components there. */
+int b200cv_current_device(int *device);
 
 /* ---- multi-GPU (one process per GPU; group1 rows sharded, group2 replicated) ---------- */
 /* NCCL unique id (128 bytes) created on rank 0 and handed to every rank by the caller. */

@@ -127,3 +127,49 @@ def test_periodic_cell_through_the_reference_host(case, tmp_path):
         assert np.allclose(out[tag][0], out["ref"][0], rtol=1e-11, atol=1e-13), tag
         for k in range(5):
             assert np.allclose(out[tag][1][k], out["ref"][1][k], rtol=1e-9, atol=1e-13), (tag, k)
+
+
+@pytest.mark.parametrize("route", ["cpu-proxy", "smp-gpu"])
+@pytest.mark.parametrize("case", R.CASES + R.PAIR_CASES)
+def test_sharded_components_through_the_reference_host(case, route, tmp_path):
+    """Two processes, one per GPU, each running the whole unmodified host on the same
+    trajectory; the environment (B200CV_NCCL_ID_FILE, RANK, WORLD_SIZE, LOCAL_RANK) makes every
+    coordination-number component shard its group1 rows over the two ranks and all-reduce
+    [value | gradients] (coordnum_b200.cpp, join_shards).  Both ranks have to reproduce the
+    reference's golden files; nothing else in the host knows about the sharding."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    runner = RUNNER_GPU if route == "smp-gpu" else RUNNER
+    if not runner.exists():
+        pytest.fail(f"{runner} missing: build it with __graft_entry__.build()")
+    import os
+    procs = []
+    for rank in range(2):
+        wd = tmp_path / f"rank{rank}"
+        wd.mkdir()
+        for f in ("trajectory.xyz", "index.ndx"):
+            shutil.copy(R.GOLDEN / f, wd / f)
+        d = wd / f"{case}_harmonic-fixed"
+        d.mkdir()
+        shutil.copy(R.GOLDEN / f"{case}_harmonic-fixed" / "test.in", d / "test.in")
+        env = dict(os.environ, B200CV_NCCL_ID_FILE=str(tmp_path / "nccl_id"), RANK=str(rank),
+                   WORLD_SIZE="2", LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen(
+            [str(runner), "-c", f"{d.name}/test.in", "-t", "trajectory.xyz", "-o",
+             f"{d.name}/test_out", "--force"], cwd=wd, env=env, stdout=subprocess.PIPE,
+            stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    gold = R.GOLDEN / f"{case}_harmonic-fixed" / "AutoDiff"
+    gtraj = np.loadtxt(gold / "test_out.colvars.traj", comments="#")
+    for rank in range(2):
+        assert procs[rank].returncode == 0, outs[rank][-3000:]
+        d = tmp_path / f"rank{rank}" / f"{case}_harmonic-fixed"
+        traj = np.loadtxt(d / "test_out.colvars.traj", comments="#")
+        assert traj.shape == gtraj.shape and _close(traj, gtraj), (rank, traj, gtraj)
+        for k in range(5):
+            f = np.loadtxt(d / f"test_out_forces_{k}.dat")
+            g = np.loadtxt(gold / f"test_out_forces_{k}.dat")
+            assert f.shape == g.shape and _close(f, g), (rank, k)
+        if case != "hbond":
+            assert "sharded, rank %d of 2" % rank in outs[rank], outs[rank][-1500:]

@@ -659,7 +659,7 @@ def test_duplicate_atoms_in_a_group_are_rejected():
                     np.array([5, 6], dtype=np.int32))
 
 
-@pytest.mark.parametrize("form", ["entries", "tiles"])
+@pytest.mark.parametrize("form", ["entries", "tiles", "rows"])
 def test_captured_pairlist_overflow_is_an_error_not_a_truncation(form, monkeypatch):
     """A captured graph holds the list's address, so the list cannot grow under it: when a
     rebuild finds more pairs than were reserved, the step's value must come back as an error --
@@ -670,6 +670,8 @@ def test_captured_pairlist_overflow_is_an_error_not_a_truncation(form, monkeypat
     cb = _cb()
     if form == "entries":
         monkeypatch.setenv("B200CV_NO_TILES", "1")
+    elif form == "tiles":
+        monkeypatch.setenv("B200CV_LIST_FORM", "tiles")
     rng = np.random.default_rng(9)
     n = 6000
     pos = rng.random((n, 3)) * 60.0
@@ -705,7 +707,8 @@ def test_captured_pairlist_overflow_is_an_error_not_a_truncation(form, monkeypat
     dense.eval(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST | cb.EF_REBUILD_PAIRLIST, gd, None)
     vd = dense.value()
     assert len(dense.pairlist()) > (1 << 20)
-    if form == "entries":
+    if form != "tiles":
+        # rows keep two entries per pair: 27x the pairs do not fit either
         with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
             cv.value()
         # recover: size the list on the positions of now, capture again
@@ -762,18 +765,21 @@ def test_handles_are_independent_across_host_threads():
     assert not errors, errors
 
 
-@pytest.mark.parametrize("form", ["tiles", "cells"])
+@pytest.mark.parametrize("form", ["rows", "tiles", "cells"])
 @pytest.mark.parametrize("kind,aniso", [("selfCoordNum", False), ("coordNum", False),
                                         ("coordNum", True), ("selfCoordNum", True)])
 def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso, form, monkeypatch):
     """Once a rebuild has shown the list to be sparse (< 2 % of the pairs), later rebuilds only
     visit pairs in neighbouring cells; everything else is exactly zero in the reference as well
     (l2 > tolerance_l2_max returns before anything is evaluated), so value, gradients and list
-    must not change.  Two forms of the sparse list in an open system: masked cluster tiles
-    (csrc/tiles.cu, the default) and packed entries in cell order (csrc/cells.cu)."""
+    must not change.  Three forms of the sparse list in an open system: neighbour rows
+    (csrc/rows.cu, the default), masked cluster tiles (csrc/tiles.cu) and packed entries in cell
+    order (csrc/cells.cu)."""
     cb = _cb()
     if form == "cells":
         monkeypatch.setenv("B200CV_NO_TILES", "1")
+    elif form == "tiles":
+        monkeypatch.setenv("B200CV_LIST_FORM", "tiles")
     rng = np.random.default_rng(77)
     n1, n2 = (3000, 0) if kind == "selfCoordNum" else (700, 5000)
     L = 70.0  # ~0.01 atoms / A^3: a few listed pairs per atom
