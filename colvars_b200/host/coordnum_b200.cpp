@@ -19,6 +19,18 @@ namespace {
 // read access to the cell the base class copied into cvc::boundary_conditions
 // (src/colvarcomp.cpp:461); the fields are protected in the reference
 struct boundaries_view : public cvm::system_boundary_conditions {
+  void numbers(double out[12]) const
+  {
+    out[0] = periodic_x;
+    out[1] = periodic_y;
+    out[2] = periodic_z;
+    cvm::rvector const v[3] = {unit_cell_x, unit_cell_y, unit_cell_z};
+    for (int a = 0; a < 3; a++) {
+      out[3 + 3 * a] = v[a].x;
+      out[4 + 3 * a] = v[a].y;
+      out[5 + 3 * a] = v[a].z;
+    }
+  }
   void push(b200cv_cvc *h) const
   {
     double const A[3] = {unit_cell_x.x, unit_cell_x.y, unit_cell_x.z};
@@ -500,6 +512,8 @@ int coordnum_b200::add_calc_value_node(
     boundary_conditions.reset();
   }
   static_cast<boundaries_view const &>(boundary_conditions).push(engine);
+  static_cast<boundaries_view const &>(boundary_conditions).numbers(frozen_cell);
+  if (char const *f = std::getenv("B200CV_SHIM_FAKE_OVERFLOW_STEP")) fake_overflow_step = std::atoi(f);
   auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
   const double *p2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_pos : nullptr;
   int flags = is_enabled(f_cvc_gradient) ? B200CV_EF_GRADIENTS : B200CV_EF_NULL;
@@ -516,17 +530,108 @@ int coordnum_b200::add_calc_value_node(
   // gradients stay in the engine's buffers until add_calc_gradients_node hands them over:
   // debug_gradients_gpu relaunches this graph many times (src/colvarcomp.cpp:986-996)
   int const rc = capture_into(graph, capture_stream, [&]() {
+    // host node first: is the frozen cell still the proxy's cell?
+    if (cudaLaunchHostFunc(capture_stream, &coordnum_b200::cell_check, this) != cudaSuccess) {
+      return (int)B200CV_ERROR;
+    }
     return b200cv_eval_async(engine, b1.d_atoms_pos, p2, flags, nullptr, nullptr, capture_stream);
   });
   if (rc != COLVARS_OK) return b200_error(COLVARS_ERROR);
   return COLVARS_OK;
 }
 
+void coordnum_b200::current_cell(double out[12])
+{
+  if (is_enabled(f_cvc_pbc_minimum_image)) {
+    cvm::system_boundary_conditions const now = cvmodule->proxy->get_system_boundaries();
+    static_cast<boundaries_view const &>(now).numbers(out);
+  } else {
+    for (int k = 0; k < 12; k++) out[k] = 0.0;
+  }
+}
+
+// runs as a node of the calc_value graph (no CUDA calls in here): one word in mapped pinned
+// memory tells the kernels behind it whether to run
+void CUDART_CB coordnum_b200::cell_check(void *self)
+{
+  coordnum_b200 *c = static_cast<coordnum_b200 *>(self);
+  double now[12];
+  c->current_cell(now);
+  bool differs = false;
+  for (int k = 0; k < 12; k++) differs = differs || (now[k] != c->frozen_cell[k]);
+  int const skip = (differs || c->dynamic_cell) ? 1 : 0;
+  b200cv_async_set_skip(c->engine, skip);
+  c->launch_skipped.store(skip);
+}
+
+// this step outside the graph: the proxy's cell of now, synchronous (queues may grow)
+int coordnum_b200::evaluate_now()
+{
+  if (is_enabled(f_cvc_pbc_minimum_image)) {
+    boundary_conditions = cvmodule->proxy->get_system_boundaries();
+  } else {
+    boundary_conditions.reset();
+  }
+  static_cast<boundaries_view const &>(boundary_conditions).push(engine);
+  int flags = is_enabled(f_cvc_gradient) ? B200CV_EF_GRADIENTS : B200CV_EF_NULL;
+  if (tolerance > 0 && function_type() != "groupCoord") {
+    flags |= B200CV_EF_USE_PAIRLIST;
+    if (cvmodule->step_relative() % pairlist_freq == 0) flags |= B200CV_EF_REBUILD_PAIRLIST;
+  }
+  auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
+  const double *p2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_pos : nullptr;
+  // gradients stay in the engine's buffers: the calc_gradients graph hands them over as usual
+  int rc = b200cv_eval(engine, b1.d_atoms_pos, p2, flags, nullptr, nullptr,
+                       cvmodule->proxy->get_default_stream());
+  if (rc == B200CV_OK) rc = b200cv_value(engine, &x.real_value);
+  if (rc != B200CV_OK) return b200_error(rc);
+  return COLVARS_OK;
+}
+
 int coordnum_b200::calc_value_after_gpu()
 {
   // the scheduler has synchronised the stream; the scalar sits in mapped pinned memory
-  int const rc = b200cv_value(engine, &x.real_value);
-  if (rc != B200CV_OK) return b200_error(rc);
+  bool const skipped = launch_skipped.load() != 0;
+  bool rebuild_graphs = false;
+  if (!skipped) {
+    int rc = b200cv_value(engine, &x.real_value);
+    if (rc == B200CV_OK && fake_overflow_step >= 0 &&
+        cvmodule->step_relative() == (cvm::step_number)fake_overflow_step) {
+      rc = B200CV_MEMORY_ERROR;
+      fake_overflow_step = -1;
+    }
+    if (rc == B200CV_MEMORY_ERROR) {
+      // a queue of the captured evaluation overflowed (it cannot grow under the graph that
+      // holds its address): do this step directly -- that path grows the queues -- and have
+      // the graphs built again on the new buffers
+      cvmodule->log("b200cv: " + name + ": " + std::string(b200cv_last_error(engine)) +
+                    " -- evaluating this step directly and rebuilding the graphs\n");
+      int const erc = evaluate_now();
+      if (erc != COLVARS_OK) return erc;
+      rebuild_graphs = true;
+    } else if (rc != B200CV_OK) {
+      return b200_error(rc);
+    }
+  } else {
+    int const erc = evaluate_now();
+    if (erc != COLVARS_OK) return erc;
+    if (!dynamic_cell) {
+      long long const step = (long long)cvmodule->step_relative();
+      if (step - last_cell_change <= 1) {
+        dynamic_cell = true;  // two steps in a row: a barostat; stop re-capturing
+        cvmodule->log("b200cv: " + name + ": the periodic cell changes every step; evaluating "
+                      "outside the captured graph from now on\n");
+      } else {
+        rebuild_graphs = true;  // capture again with the new cell
+      }
+      last_cell_change = step;
+    }
+  }
+  if (rebuild_graphs && cvmodule->gpu_calc) {
+    // colvarmodule_gpu_calc::init (src/colvar_gpu_calc.cpp:724-735): every graph is built again
+    // on its next use, add_calc_value_node included
+    cvmodule->gpu_calc->init();
+  }
   if (tolerance > 0) {
     // compute_coordnum's rebuild test (src/colvarcomp_coordnums.cpp:255) for the NEXT launch
     b200cv_pairlist_set_rebuild(engine, (cvmodule->step_relative() + 1) % pairlist_freq == 0);

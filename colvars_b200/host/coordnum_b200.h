@@ -10,6 +10,7 @@
 #ifndef COORDNUM_B200_H
 #define COORDNUM_B200_H
 
+#include <atomic>
 #include <string>
 
 #include "colvarmodule.h"
@@ -65,6 +66,22 @@ protected:
   b200cv_cvc *engine = nullptr;
 #if defined(COLVARS_CUDA)
   cudaStream_t capture_stream = nullptr;
+  // A captured evaluation freezes the periodic cell (and the addresses of the engine's queues).
+  // cvc::read_data copies the cell from the proxy every step (src/colvarcomp.cpp:457-465), so
+  // the graph carries a host node in front of the kernels (cell_check, run by the graph itself,
+  // i.e. after wait_for_extra_info_ready has delivered this step's lattice,
+  // src/colvar_gpu_calc.cpp:753-757) that compares the proxy's cell with the frozen one and,
+  // if they differ, makes the kernels of this launch do nothing; calc_value_after_gpu then
+  // evaluates the step directly (evaluate_now) and asks the scheduler to build its graphs again
+  // -- or, when the cell changes step after step (a barostat), keeps evaluating directly.
+  double frozen_cell[12] = {0};     // periodic flags + unit cell the captured graph was built with
+  std::atomic<int> launch_skipped{0};
+  bool dynamic_cell = false;        // the cell changes every step: the graph's nodes stay switched off
+  long long last_cell_change = -10;
+  int fake_overflow_step = -1;      // B200CV_SHIM_FAKE_OVERFLOW_STEP: exercise the recovery path
+  void current_cell(double out[12]);
+  static void CUDART_CB cell_check(void *self);
+  int evaluate_now();
 #endif
 };
 

@@ -31,7 +31,7 @@ int main(int argc, char **argv)
 {
   std::string config, traj, prefix;
   bool forces = false, reference_components = false;
-  double cell[3] = {0, 0, 0};
+  double cell[3] = {0, 0, 0}, drift = 0.0;
   for (int a = 1; a < argc; a++) {
     std::string const s = argv[a];
     if ((s == "-c" || s == "--configuration_file") && a + 1 < argc) config = argv[++a];
@@ -44,6 +44,9 @@ int main(int argc, char **argv)
     else if (s == "--cell" && a + 3 < argc) {
       for (int d = 0; d < 3; d++) cell[d] = std::stod(argv[++a]);
     }
+    // ... that grows by this fraction every frame (a barostat: cvc::read_data has to pick the
+    // cell up each step, src/colvarcomp.cpp:457-465)
+    else if (s == "--cell-drift" && a + 1 < argc) drift = std::stod(argv[++a]);
   }
   if (config.empty() || traj.empty()) {
     std::cerr << "usage: run_colvars_b200 -c test.in -t trajectory.xyz [-o prefix [--force]]\n";
@@ -67,7 +70,11 @@ int main(int argc, char **argv)
   ifs.close();
   for (int ai = 0; ai < natoms; ai++) proxy->init_atom(ai + 1);
   int io_err = 0;
-  while (!io_err) {
+  for (int frame = 0; !io_err; frame++) {
+    if (cell[0] > 0 && drift != 0.0) {
+      double const f = 1.0 + drift * frame;
+      proxy->set_cell(f * cell[0], f * cell[1], f * cell[2]);
+    }
     io_err = proxy->read_frame_xyz(traj.c_str(), forces && !prefix.empty());
   }
   proxy->post_run();

@@ -60,6 +60,25 @@ public:
     boundaries_.set_boundaries(true, true, true, cvm::rvector(ax, 0, 0), cvm::rvector(0, by, 0),
                                cvm::rvector(0, 0, cz));
   }
+  // the lattice of the coming step the way NAMD's CudaGlobalMaster delivers it: not before
+  // calc(), but when the scheduler asks for the "extra info" between the atom groups' read_data
+  // graph and the components' calc_value graph (src/colvar_gpu_calc.cpp:753-757,
+  // namd/cudaglobalmaster/colvarproxy_cudaglobalmaster.C:731-763)
+  void set_cell_late(double ax, double by, double cz)
+  {
+    late_cell[0] = ax;
+    late_cell[1] = by;
+    late_cell[2] = cz;
+    late_pending = true;
+  }
+  int wait_for_extra_info_ready() override
+  {
+    if (late_pending) {
+      set_cell(late_cell[0], late_cell[1], late_cell[2]);
+      late_pending = false;
+    }
+    return COLVARS_OK;
+  }
   void request_total_force(bool yesno) override { total_force_requested = yesno; }
   bool total_forces_enabled() const override { return total_force_requested; }
   bool total_forces_same_step() const override { return total_force_requested; }
@@ -166,6 +185,8 @@ private:
   cudaStream_t stream = nullptr;
   double *d_pos = nullptr, *d_force = nullptr, *d_total = nullptr;
   bool changed = true;
+  double late_cell[3] = {0, 0, 0};
+  bool late_pending = false;
 };
 
 }  // namespace
@@ -178,7 +199,8 @@ int main(int argc, char **argv)
 {
   std::string config, traj, prefix;
   bool forces = false;
-  double cell[3] = {0, 0, 0};
+  double cell[3] = {0, 0, 0}, drift = 0.0;
+  bool late_lattice = false;
   for (int a = 1; a < argc; a++) {
     std::string const s = argv[a];
     if ((s == "-c" || s == "--configuration_file") && a + 1 < argc) config = argv[++a];
@@ -188,6 +210,10 @@ int main(int argc, char **argv)
     else if (s == "--cell" && a + 3 < argc) {
       for (int d = 0; d < 3; d++) cell[d] = std::stod(argv[++a]);
     }
+    // the cell grows by this fraction every frame; --late-lattice delivers each frame's cell
+    // through wait_for_extra_info_ready() instead of before calc()
+    else if (s == "--cell-drift" && a + 1 < argc) drift = std::stod(argv[++a]);
+    else if (s == "--late-lattice") late_lattice = true;
   }
   if (config.empty() || traj.empty()) {
     std::cerr << "usage: run_colvars_b200_gpu -c test.in -t trajectory.xyz [-o prefix [--force]]\n";
@@ -217,7 +243,14 @@ int main(int argc, char **argv)
   ifs.close();
   for (int ai = 0; ai < natoms; ai++) proxy->init_atom(ai + 1);
   int io_err = 0;
-  while (!io_err) io_err = proxy->step_xyz(traj.c_str(), forces && !prefix.empty());
+  for (int frame = 0; !io_err; frame++) {
+    if (cell[0] > 0 && drift != 0.0) {
+      double const f = 1.0 + drift * frame;
+      if (late_lattice && frame > 0) proxy->set_cell_late(f * cell[0], f * cell[1], f * cell[2]);
+      else proxy->set_cell(f * cell[0], f * cell[1], f * cell[2]);
+    }
+    io_err = proxy->step_xyz(traj.c_str(), forces && !prefix.empty());
+  }
   proxy->post_run();
   bool gpu_route = false;
   for (colvar *cv : *cvmodule->variables()) {

@@ -173,3 +173,79 @@ def test_sharded_components_through_the_reference_host(case, route, tmp_path):
             assert f.shape == g.shape and _close(f, g), (rank, k)
         if case != "hbond":
             assert "sharded, rank %d of 2" % rank in outs[rank], outs[rank][-1500:]
+
+
+@pytest.mark.parametrize("late", [False, True])
+@pytest.mark.parametrize("case", ["coordnum", "selfcoordnum-pairlist", "coordnum-aniso"])
+def test_cell_that_changes_every_step_on_the_graph_route(case, late, tmp_path):
+    """cvc::read_data copies the periodic cell from the proxy every step
+    (src/colvarcomp.cpp:457-465); a captured graph freezes the one it was built with.  Here the
+    cell grows by 1 % per frame (a barostat).  The graph carries a host node that notices the
+    change and switches the captured kernels off for that launch; the component then evaluates
+    the step directly with the proxy's cell of now.  late: the new cell arrives only through
+    wait_for_extra_info_ready(), between the read_data and the calc_value graphs, the way
+    NAMD's CudaGlobalMaster delivers its lattice.  Reference: the unmodified components on the
+    CPU with the same cells."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    for f in ("trajectory.xyz", "index.ndx"):
+        shutil.copy(R.GOLDEN / f, tmp_path / f)
+    d = tmp_path / "case"
+    d.mkdir()
+    shutil.copy(R.GOLDEN / f"{case}_harmonic-fixed" / "test.in", d / "test.in")
+    cell = ["--cell", "3.1", "2.7", "2.9", "--cell-drift", "0.01"]
+    runs = {"ref": [str(RUNNER), "--reference-components"] + cell,
+            "gpu": [str(RUNNER_GPU)] + cell + (["--late-lattice"] if late else [])}
+    out = {}
+    for tag, cmd in runs.items():
+        r = subprocess.run(cmd + ["-c", "case/test.in", "-t", "trajectory.xyz", "-o",
+                                  f"case/{tag}", "--force"], cwd=tmp_path,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, tag + r.stdout[-2000:] + r.stderr[-2000:]
+        out[tag] = (np.loadtxt(d / f"{tag}.colvars.traj", comments="#"),
+                    [np.loadtxt(d / f"{tag}_forces_{k}.dat") for k in range(5)], r.stdout)
+    assert "the periodic cell changes every step" in out["gpu"][2]
+    # the drift matters: frame 4 is not what the fixed cell gives
+    fixed = subprocess.run([str(RUNNER), "--reference-components", "--cell", "3.1", "2.7", "2.9",
+                            "-c", "case/test.in", "-t", "trajectory.xyz", "-o", "case/fixed"],
+                           cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert fixed.returncode == 0
+    ftraj = np.loadtxt(d / "fixed.colvars.traj", comments="#")
+    assert abs(ftraj[4, 1] - out["ref"][0][4, 1]) > 1e-6
+    assert np.allclose(out["gpu"][0], out["ref"][0], rtol=1e-11, atol=1e-13)
+    for k in range(5):
+        assert np.allclose(out["gpu"][1][k], out["ref"][1][k], rtol=1e-9, atol=1e-13), k
+
+
+@pytest.mark.parametrize("case", ["coordnum-pairlist", "selfcoordnum-pairlist", "coordnum"])
+def test_overflow_of_a_captured_evaluation_recovers_on_the_graph_route(case, tmp_path):
+    """A queue of a captured evaluation cannot grow under the graph that holds its address;
+    the C ABI reports the overflow (tests/test_gpu_parity.py::test_captured_pairlist_overflow...).
+    The component recovers from it: it evaluates that step outside the graph -- where queues
+    grow -- and has colvarmodule_gpu_calc build its graphs again.  The da-ala system is too
+    small to overflow anything, so the overflow of step 2 is injected
+    (B200CV_SHIM_FAKE_OVERFLOW_STEP); everything downstream of the report is the real path."""
+    import os
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    for f in ("trajectory.xyz", "index.ndx"):
+        shutil.copy(R.GOLDEN / f, tmp_path / f)
+    d = tmp_path / f"{case}_harmonic-fixed"
+    d.mkdir()
+    shutil.copy(R.GOLDEN / f"{case}_harmonic-fixed" / "test.in", d / "test.in")
+    r = subprocess.run([str(RUNNER_GPU), "-c", f"{d.name}/test.in", "-t", "trajectory.xyz", "-o",
+                        f"{d.name}/test_out", "--force"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300,
+                       env=dict(os.environ, B200CV_SHIM_FAKE_OVERFLOW_STEP="2"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "evaluating this step directly and rebuilding the graphs" in r.stdout
+    gold = R.GOLDEN / f"{case}_harmonic-fixed" / "AutoDiff"
+    traj = np.loadtxt(d / "test_out.colvars.traj", comments="#")
+    gtraj = np.loadtxt(gold / "test_out.colvars.traj", comments="#")
+    assert traj.shape == gtraj.shape and _close(traj, gtraj), (traj, gtraj)
+    for k in range(5):
+        f = np.loadtxt(d / f"test_out_forces_{k}.dat")
+        g = np.loadtxt(gold / f"test_out_forces_{k}.dat")
+        assert f.shape == g.shape and _close(f, g), k
