@@ -376,10 +376,9 @@ def quick_workload(cb, torch, key, device, fp64_tflops, steps=10, warmup=3):
         out["pairlist"] = {"rebuild_ms": float(np.mean(reb)), "list_ms": float(np.mean(lst)),
                            "listed_pairs": int(st["pairs"]),
                            "form": {0: "entries", 1: "entries in cell order",
-                                    2: "masked cluster tiles"}.get(st["form"], "none"),
-                           "tiles": int(st["tiles"]),
-                           "tile_fill": (st["pairs"] - st["entries"]) / (1024.0 * st["tiles"])
-                           if st["tiles"] else None}
+                                    2: "neighbour rows"}.get(st["form"], "none"),
+                           "row_entries": int(st["row_entries"]),
+                           "extras": int(st["entries"])}
         kern = float(np.mean(reb))
     else:
         kern = float(np.mean([m for _, m in kms]))

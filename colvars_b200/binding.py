@@ -378,12 +378,12 @@ class CoordNum:
         return out[:n.value]
 
     def pairlist_stats(self):
-        """dict(form, pairs, entries, tile_units, tiles); see b200cv_pairlist_stats."""
+        """dict(form, pairs, entries, row_entries, row_chunks); see b200cv_pairlist_stats."""
         form = C.c_int()
         v = [C.c_size_t() for _ in range(4)]
         self._check(self._L.b200cv_pairlist_stats(self._h, C.byref(form), *[C.byref(x) for x in v]))
         return dict(form=form.value, pairs=v[0].value, entries=v[1].value,
-                    tile_units=v[2].value, tiles=v[3].value)
+                    row_entries=v[2].value, row_chunks=v[3].value)
 
     def last_stats(self):
         k = C.c_int()

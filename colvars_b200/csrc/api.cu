@@ -143,6 +143,7 @@ void reset_boundaries(PairParams &P)
   std::memset(P.tri_n, 0, sizeof(P.tri_n));
   std::memset(P.tri_shift, 0, sizeof(P.tri_shift));
   P.tri_margin = 0.0;
+  P.tri_search = 1;
 }
 
 // tables of the tile sweep's image search in mixed / triclinic cells (general_image,
@@ -348,7 +349,7 @@ int b200cv_destroy(b200cv_cvc *h)
   free_dev(h->d_pl_center);
   free_dev(h->d_items);
   cells_free(h->cells);
-  tiles_free(h->tiles);
+  cellsort_free(h->sort);
   rows_free(h->rows);
   free_dev(h->d_stage_pos);
   if (h->h_value) cudaFreeHost(h->h_value);
@@ -429,7 +430,7 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
     if (rc) return rc;
     if (h->cfg.tolerance > 0) {
       if (h->center1() || h->center2()) {
-        int const m = h->center1() ? h->g[1].n : h->g[0].n;
+        int const m = (h->center1() && h->center2()) ? 1 : (h->center1() ? h->g[1].n : h->g[0].n);
         CUDA_OK(h, cudaMalloc(&h->d_pl_center, std::max(m, 1)));
         CUDA_OK(h, cudaMemset(h->d_pl_center, 1, std::max(m, 1)));  // list starts all-true
       } else {
@@ -437,8 +438,8 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
         unsigned long long const pairs = h->self() ? n1 * (n1 - 1) / 2 : n1 * n2;
         CUDA_OK(h, cells_setup(h->cells, (int)n2));
         h->cells_ready = true;
-        CUDA_OK(h, tiles_setup(h->tiles, h->self() ? 0 : (int)n1, (int)n2));
-        h->tiles_ready = true;
+        CUDA_OK(h, cellsort_setup(h->sort, h->self() ? 0 : (int)n1, (int)n2));
+        h->sort_ready = true;
         rc = ensure_pairlist_capacity(h, std::min<unsigned long long>(pairs, 64ull * (n1 + n2)));
         if (rc) return rc;
       }
@@ -511,16 +512,24 @@ int b200cv_set_boundaries(b200cv_cvc *h, int px, int py, int pz, const double A[
   }
   if (P.bc_type == 2) {
     // the tile sweep's orthogonal path reads only the diagonal; the reference also adds the
-    // (<= 1e-5) off-diagonal terms it tolerates -- route those cells to the general path
+    // (<= 1e-5) off-diagonal terms it tolerates, without searching the neighbouring images --
+    // route those cells to the general path with the search switched off
     bool exact_diag = true;
     for (int d = 0; d < 3; d++) {
       for (int k = 0; k < 3; k++) {
         if (k != d && P.cell[d][k] != 0.0) exact_diag = false;
       }
     }
-    if (!exact_diag) P.bc_type = 3;
+    if (!exact_diag) {
+      P.bc_type = 3;
+      P.tri_search = 0;
+    }
   }
   if (P.bc_type == 1 || P.bc_type == 3) fill_general_cell_tables(P);
+  if (!P.tri_search) {
+    // no image search: no direction can ever win in general_image
+    for (int k = 0; k < 13; k++) P.tri_n[k] = 1.0e300;
+  }
   return B200CV_OK;
 }
 
@@ -779,25 +788,15 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
     CUDA_OK(h, cudaMalloc(&h->d_pl, sizeof(unsigned long long) * want));
     h->pl_cap = want;
   }
-  if (tiles_usable(h) && sparse_list(h)) {
-    if (rows_preferred()) {
-      // two entries per listed pair, one chunk per atom and per ROW_BUF entries
-      double const atoms = (double)h->g[0].n + (h->self() ? 0.0 : (double)h->g[1].n);
-      double const ent = headroom * 2.0 * (double)h->pl_n + 65536.0;
-      double const chk = atoms + headroom * ent / ROW_BUF + 4096.0;
-      if ((unsigned)std::min(4.0e9, ent) > h->rows.cap_idx ||
-          (unsigned)std::min(4.0e9, chk) > h->rows.cap_chunks) {
-        h->epoch++;
-        CUDA_OK(h, rows_reserve(h->rows, (unsigned)std::min(4.0e9, ent),
-                                (unsigned)std::min(4.0e9, chk)));
-      }
-    } else {
-      unsigned const need =
-          (unsigned)std::min(4.0e9, std::ceil(headroom * (double)tile_units_estimate(h)));
-      if (need > h->tiles.cap_units) {
-        h->epoch++;
-        CUDA_OK(h, tiles_reserve(h->tiles, need));
-      }
+  if (rows_usable(h) && sparse_list(h)) {
+    // the row form: two entries per listed pair, one chunk per atom and per ROW_BUF entries
+    double const ent = headroom * 2.0 * (double)h->pl_n + 65536.0;
+    double const chk = (double)row_slots(h) + headroom * ent / ROW_BUF + 4096.0;
+    if ((unsigned)std::min(4.0e9, ent) > h->rows.cap_idx ||
+        (unsigned)std::min(4.0e9, chk) > h->rows.cap_chunks) {
+      h->epoch++;
+      CUDA_OK(h, rows_reserve(h->rows, (unsigned)std::min(4.0e9, ent),
+                              (unsigned)std::min(4.0e9, chk)));
     }
   }
   h->pl_valid = false;  // the first captured launch rebuilds (mode word starts at 1);
@@ -914,7 +913,7 @@ int b200cv_pairlist_count(b200cv_cvc *h, size_t *count)
   }
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
   if (h->center1() || h->center2()) {
-    int const m = h->center1() ? h->g[1].n : h->g[0].n;
+    int const m = (h->center1() && h->center2()) ? 1 : (h->center1() ? h->g[1].n : h->g[0].n);
     std::vector<unsigned char> f(m);
     CUDA_OK(h, cudaMemcpy(f.data(), h->d_pl_center, m, cudaMemcpyDeviceToHost));
     size_t c = 0;
@@ -941,7 +940,7 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
   if (capacity < count) return fail(h, B200CV_MEMORY_ERROR, "pair-list export buffer too small");
   unsigned long long const n1 = h->g[0].n, n2 = h->self() ? n1 : h->g[1].n;
   if (h->center1() || h->center2()) {
-    int const m = h->center1() ? h->g[1].n : h->g[0].n;
+    int const m = (h->center1() && h->center2()) ? 1 : (h->center1() ? h->g[1].n : h->g[0].n);
     std::vector<unsigned char> f(m);
     CUDA_OK(h, cudaMemcpy(f.data(), h->d_pl_center, m, cudaMemcpyDeviceToHost));
     size_t k = 0;
@@ -962,9 +961,9 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
   };
   if (h->pl_rows) {
     // row form (rows.cuh): the canonical side of every row chunk + the extras (atom indices)
-    TileBuffers &B = h->tiles;
-    TileSide &J = B.side[1];
-    TileSide &I = h->self() ? J : B.side[0];
+    CellSort &B = h->sort;
+    SortedGroup &J = B.side[1];
+    SortedGroup &I = h->self() ? J : B.side[0];
     unsigned counts[8];
     CUDA_OK(h, cudaMemcpy(counts, B.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
     // valid slots: this rank's rows of each group, then the overflow chunks
@@ -1019,57 +1018,6 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
     std::sort(out, out + count);
     return B200CV_OK;
   }
-  if (h->pl_tiles) {
-    // tile form (tiles.cuh): mask bits of every unit + the extras, all in sorted positions
-    TileBuffers &B = h->tiles;
-    TileSide &J = B.side[1];
-    TileSide &I = h->self() ? J : B.side[0];
-    unsigned counts[8];
-    CUDA_OK(h, cudaMemcpy(counts, B.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
-    size_t const units = std::min(counts[6], B.cap_units);
-    std::vector<int4> hdr(units);
-    std::vector<int> tj(units * TILE_UNIT * 32);
-    std::vector<unsigned> tm(units * TILE_UNIT * 32);
-    std::vector<int> oi(I.n), oj(J.n);
-    std::vector<unsigned long long> ent((size_t)h->pl_entries);
-    if (units) {
-      CUDA_OK(h, cudaMemcpy(hdr.data(), B.d_unit_hdr, sizeof(int4) * units, cudaMemcpyDeviceToHost));
-      CUDA_OK(h, cudaMemcpy(tj.data(), B.d_tile_j, sizeof(int) * tj.size(), cudaMemcpyDeviceToHost));
-      CUDA_OK(h, cudaMemcpy(tm.data(), B.d_tile_m, sizeof(unsigned) * tm.size(),
-                            cudaMemcpyDeviceToHost));
-    }
-    CUDA_OK(h, cudaMemcpy(oi.data(), I.d_sorted, sizeof(int) * oi.size(), cudaMemcpyDeviceToHost));
-    CUDA_OK(h, cudaMemcpy(oj.data(), J.d_sorted, sizeof(int) * oj.size(), cudaMemcpyDeviceToHost));
-    if (!ent.empty()) {
-      CUDA_OK(h, cudaMemcpy(ent.data(), h->d_pl, sizeof(unsigned long long) * ent.size(),
-                            cudaMemcpyDeviceToHost));
-    }
-    size_t k = 0;
-    for (size_t u = 0; u < units; u++) {
-      int const p0 = hdr[u].x, cnt = hdr[u].y, nt = hdr[u].z;
-      for (int t = 0; t < nt; t++) {
-        size_t const base = (u * TILE_UNIT + (size_t)t) * 32;
-        for (int lane = 0; lane < cnt; lane++) {
-          unsigned m = tm[base + lane];
-          for (int bit = 0; m; bit++, m >>= 1) {
-            if (!(m & 1u)) continue;
-            int const jp = tj[base + ((lane + bit) & 31)];
-            if (jp < 0 || k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent tile list");
-            out[k++] = canonical((unsigned long long)oi[(size_t)p0 + lane],
-                                 (unsigned long long)oj[(size_t)jp]);
-          }
-        }
-      }
-    }
-    for (unsigned long long e : ent) {
-      if (k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent tile list");
-      out[k++] = canonical((unsigned long long)oi[(size_t)(e >> 32)],
-                           (unsigned long long)oj[(size_t)(e & 0xffffffffull)]);
-    }
-    if (k != count) return fail(h, B200CV_BUG_ERROR, "tile list does not add up to its pair count");
-    std::sort(out, out + count);
-    return B200CV_OK;
-  }
   std::vector<unsigned long long> ent(count);
   CUDA_OK(h, cudaMemcpy(ent.data(), h->d_pl, sizeof(unsigned long long) * count,
                         cudaMemcpyDeviceToHost));
@@ -1104,34 +1052,25 @@ int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs)
 }
 
 int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entries,
-                          size_t *tile_units, size_t *tiles)
+                          size_t *row_entries, size_t *row_chunks)
 {
   if (!h) return B200CV_BUG_ERROR;
   if (!(h->cfg.tolerance > 0)) return fail(h, B200CV_INPUT_ERROR, "no pair list (tolerance = 0)");
   if (h->have_calc) CUDA_OK_RC(sync_and_check(h));
   CUDA_OK(h, cudaSetDevice(h->cfg.device));
-  size_t units = 0, ntiles = 0;
-  if (h->pl_valid && h->pl_tiles) {
-    unsigned counts[8];
-    CUDA_OK(h, cudaMemcpy(counts, h->tiles.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
-    units = std::min(counts[6], h->tiles.cap_units);
-    std::vector<int4> hdr(units);
-    if (units) {
-      CUDA_OK(h, cudaMemcpy(hdr.data(), h->tiles.d_unit_hdr, sizeof(int4) * units,
-                            cudaMemcpyDeviceToHost));
-    }
-    for (auto const &u : hdr) ntiles += (size_t)u.z;
-  }
+  size_t chunks = 0, rentries = 0;
   if (h->pl_valid && h->pl_rows) {
     unsigned counts[8];
-    CUDA_OK(h, cudaMemcpy(counts, h->tiles.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
-    units = (size_t)row_slots(h) / (size_t)h->world + counts[6];
+    CUDA_OK(h, cudaMemcpy(counts, h->sort.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
+    chunks = (size_t)row_slots(h) / (size_t)h->world + counts[6];
+    // both directions of every pair that is kept in rows
+    rentries = 2 * (size_t)(h->pl_n - h->pl_entries);
   }
-  if (form) *form = !h->pl_valid ? -1 : (h->pl_rows ? 3 : (h->pl_tiles ? 2 : (h->pl_sorted ? 1 : 0)));
+  if (form) *form = !h->pl_valid ? -1 : (h->pl_rows ? 2 : (h->pl_sorted ? 1 : 0));
   if (pairs) *pairs = (size_t)h->pl_n;
   if (entries) *entries = (size_t)h->pl_entries;
-  if (tile_units) *tile_units = units;
-  if (tiles) *tiles = ntiles;
+  if (row_entries) *row_entries = rentries;
+  if (row_chunks) *row_chunks = chunks;
   return B200CV_OK;
 }
 

@@ -93,42 +93,25 @@ bool rebuild_with_cells(const b200cv_cvc *h, int flags)
          cells_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
 }
 
-// the tile form of the list (tiles.cuh) applies: an open system whose list a previous rebuild
-// has shown to be sparse
-bool tiles_usable(const b200cv_cvc *h)
+// the row form of the list (rows.cuh) applies: an open system whose list a previous rebuild
+// has shown to be sparse (B200CV_NO_ROWS=1 keeps the cell-ordered entries of cells.cuh there)
+bool rows_usable(const b200cv_cvc *h)
 {
-  return h->tiles_ready && h->d_pl && h->pl_n > 0 && h->P.bc_type == 0 &&
-         !(h->center1() || h->center2()) && std::getenv("B200CV_NO_TILES") == nullptr &&
+  return h->sort_ready && h->d_pl && h->pl_n > 0 && h->P.bc_type == 0 &&
+         !(h->center1() || h->center2()) && std::getenv("B200CV_NO_ROWS") == nullptr &&
          std::getenv("B200CV_NO_CELLS") == nullptr;
 }
 
-bool rebuild_with_tiles(const b200cv_cvc *h, int flags)
+bool rebuild_with_rows(const b200cv_cvc *h, int flags)
 {
   return (flags & B200CV_EF_REBUILD_PAIRLIST) && (flags & B200CV_EF_USE_PAIRLIST) &&
-         tiles_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
-}
-
-// units the tile list of the next rebuild may need.  A tile of a homogeneous system is about a
-// quarter full (bounding box + cut-off against the cut-off sphere), i.e. pairs / 1024 units of
-// four tiles, plus one partly filled unit per cluster; a guess that turns out too small costs one
-// redo of the step (post_sync), not a wrong result.
-unsigned tile_units_estimate(const b200cv_cvc *h)
-{
-  unsigned long long const units = h->pl_n / 400ull + (unsigned long long)h->g[0].n / 16ull + 4096ull;
-  return (unsigned)std::min<unsigned long long>(units, 1ull << 28);
+         rows_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
 }
 
 // chunk slots taken by the rows themselves (one per atom of both groups); overflow chunks follow
 unsigned row_slots(const b200cv_cvc *h)
 {
   return (unsigned)h->g[0].n + (h->self() ? 0u : (unsigned)h->g[1].n);
-}
-
-// which sparse form a rebuild produces: neighbour rows (rows.cuh) unless B200CV_LIST_FORM=tiles
-bool rows_preferred()
-{
-  const char *f = std::getenv("B200CV_LIST_FORM");
-  return !(f && std::strcmp(f, "tiles") == 0);
 }
 
 // entries / chunks the rows of the next rebuild may need: two entries per listed pair (one per
@@ -146,18 +129,12 @@ static void row_estimate(const b200cv_cvc *h, unsigned &entries, unsigned &chunk
 int prepare_calc(b200cv_cvc *h, int flags)
 {
   if (!(flags & B200CV_EF_USE_PAIRLIST)) return B200CV_OK;
-  bool const sparse_next = h->gated ? (tiles_usable(h) && sparse_list(h)) : rebuild_with_tiles(h, flags);
-  if (!sparse_next) return B200CV_OK;
-  if (rows_preferred()) {
-    if (h->rows.cap_idx == 0) {
-      unsigned entries, chunks;
-      row_estimate(h, entries, chunks);
-      h->epoch++;
-      CUDA_OK(h, rows_reserve(h->rows, entries, chunks));
-    }
-  } else if (h->tiles.cap_units == 0) {
+  bool const rows_next = h->gated ? (rows_usable(h) && sparse_list(h)) : rebuild_with_rows(h, flags);
+  if (rows_next && h->rows.cap_idx == 0) {
+    unsigned entries, chunks;
+    row_estimate(h, entries, chunks);
     h->epoch++;
-    CUDA_OK(h, tiles_reserve(h->tiles, tile_units_estimate(h)));
+    CUDA_OK(h, rows_reserve(h->rows, entries, chunks));
   }
   return B200CV_OK;
 }
@@ -201,17 +178,13 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
   bool const skip_gated = h->gated && !use_pl;
 
   CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, 16, stream));
-  // this evaluation builds or walks the tile form of the list
-  bool const build_rows = rows_preferred();
-  bool const sparse_ready = build_rows ? h->rows.cap_idx > 0 : h->tiles.cap_units > 0;
-  bool const tiles_gated = gated && tiles_usable(h) && sparse_list(h) && sparse_ready;
-  bool const tiles_eval =
+  // this evaluation builds or walks the row form of the list (rows.cuh)
+  bool const rows_gated = gated && rows_usable(h) && sparse_list(h) && h->rows.cap_idx > 0;
+  bool const rows_eval =
       use_pl && !(h->center1() || h->center2()) &&
-      (tiles_gated || (!gated && ((!rebuild && h->pl_valid && (h->pl_tiles || h->pl_rows)) ||
-                                  (rebuild_with_tiles(h, flags) && sparse_ready))));
-  // the form this evaluation works on: the one being built, or the one the current list has
-  bool const rows_eval = tiles_eval && ((tiles_gated || rebuild) ? build_rows : h->pl_rows);
-  if (tiles_eval) CUDA_OK(h, cudaMemsetAsync(h->tiles.d_counts, 0, 6 * sizeof(unsigned), stream));
+      (rows_gated || (!gated && ((!rebuild && h->pl_valid && h->pl_rows) ||
+                                 (rebuild_with_rows(h, flags) && h->rows.cap_idx > 0))));
+  if (rows_eval) CUDA_OK(h, cudaMemsetAsync(h->sort.d_counts, 0, 6 * sizeof(unsigned), stream));
   if (gated || skip_gated) {
     CUDA_OK(h, launch_fetch_gate(h->h_mode_dev, h->gate(), gated ? 1 : 0, stream));
     h->launches++;
@@ -231,10 +204,9 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     F.rebuilt = (!gated && use_pl && rebuild && !(h->center1() || h->center2())) ? 1 : 0;
     F.pl_persist = h->pl_count() + 1;
     F.pl_cap = h->pl_cap;
-    F.tile_counts = tiles_eval ? h->tiles.d_counts : nullptr;
-    F.tile_cap = rows_eval ? (h->rows.cap_chunks > row_slots(h) ? h->rows.cap_chunks - row_slots(h) : 0u)
-                           : h->tiles.cap_units;
-    F.tile_cap2 = rows_eval ? h->rows.cap_idx : 0xffffffffu;
+    F.row_counts = rows_eval ? h->sort.d_counts : nullptr;
+    F.row_cap_chunks = h->rows.cap_chunks > row_slots(h) ? h->rows.cap_chunks - row_slots(h) : 0u;
+    F.row_cap_idx = h->rows.cap_idx;
     F.rare_cap = h->rare_cap;
     F.overflow = (h->world > 1) ? h->d_reduce + 1 : nullptr;
     return F;
@@ -366,7 +338,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     // kernel; records the pair list when `record`.  Returns the number of partial sums.
     auto enqueue_all_pairs = [&](int sweep_flags, bool record, const int *gate,
                                  int &nparts, int gate_on = 1) -> int {
-      if (record) h->pl_sorted = h->pl_tiles = h->pl_rows = false;  // the sweep and the dense kernel list (i, j) as they are
+      if (record) h->pl_sorted = h->pl_rows = false;  // the sweep and the dense kernel list (i, j) as they are
       if (general_bc) {
         DenseArgs D{};
         D.x1 = x1; D.y1 = y1; D.z1 = z1; D.x2 = x2; D.y2 = y2; D.z2 = z2;
@@ -466,7 +438,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       C.flags = cell_flags;
       C.fast_exp = (h->exp_special == 3) ? 3 : 0;  // every kind of cell has a fast form
       h->pl_sorted = sorted_walk_enabled();
-      h->pl_tiles = h->pl_rows = false;
+      h->pl_rows = false;
       C.sorted_entries = h->pl_sorted ? 1 : 0;
       C.gate = gate;
       C.P = h->P;
@@ -475,136 +447,10 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       return B200CV_OK;
     };
 
-    // ---- the list as masked cluster tiles (tiles.cuh): open systems, sparse lists ------------
-    auto tile_planes = [&](ExactArgs &E) {
-      TileSide &J = h->tiles.side[1];
-      TileSide &I = h->self() ? J : h->tiles.side[0];
-      E.x1 = I.d_xs; E.y1 = I.d_ys; E.z1 = I.d_zs;
-      E.x2 = J.d_xs; E.y2 = J.d_ys; E.z2 = J.d_zs;
-      E.g1x = I.d_gs; E.g1y = I.d_gs + I.n; E.g1z = I.d_gs + 2 * (size_t)I.n;
-      E.g2x = J.d_gs; E.g2y = J.d_gs + J.n; E.g2z = J.d_gs + 2 * (size_t)J.n;
-    };
-    // rebuild: sort, tile build (value + gradients + masks), reference-order pairs (those listed
-    // become the extras), gradients back to atom order.  Partial sums: [TILE_BLOCKS | EXACT_BLOCKS]
-    auto enqueue_tiles_build = [&](int build_flags, double *partials, const int *gate) -> int {
-      TileBuffers &B = h->tiles;
-      TileSide &J = B.side[1];
-      TileSide &I = h->self() ? J : B.side[0];
-      CUDA_OK(h, tiles_sort(B, x1, y1, z1, x2, y2, z2, gate, stream));
-      h->launches += h->self() ? 5 : 8;
-      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
-      h->launches++;
-      TileBuildArgs T{};
-      T.xi = I.d_xs; T.yi = I.d_ys; T.zi = I.d_zs; T.gi = I.d_gs; T.ni = I.n;
-      T.clusters = I.d_clusters;
-      T.ncl = I.d_ncl;
-      T.rank = h->rank;
-      T.world = h->world;
-      T.xj = J.d_xs; T.yj = J.d_ys; T.zj = J.d_zs; T.gj = J.d_gs; T.nj = J.n;
-      T.cell_start = J.d_cell_start;
-      T.grid = B.d_grid;
-      T.self = h->self() ? 1 : 0;
-      T.unit_hdr = B.d_unit_hdr;
-      T.tile_j = B.d_tile_j;
-      T.tile_m = B.d_tile_m;
-      T.cap_units = B.cap_units;
-      T.counts = B.d_counts;
-      T.rare = h->d_rare;
-      T.rare_cap = h->rare_cap;
-      T.rare_count = h->rare_count();
-      T.partials = partials;
-      T.want_grad = grad ? 1 : 0;
-      cell_cutoffs(h, T.cut);
-      for (int d = 0; d < 3; d++) T.cut[d] *= (1.0 + 1.0e-9);
-      T.gate = gate;
-      T.P = h->P;
-      CUDA_OK(h, launch_tile_build(T, h->exp_special, h->aniso, stream));
-      h->launches++;
-      h->pl_tiles = true;
-      h->pl_sorted = h->pl_rows = false;
-      ExactArgs E{};
-      tile_planes(E);
-      E.list = h->d_rare;
-      E.count32 = h->rare_count();
-      E.cap = h->rare_cap;
-      E.partials = partials + TILE_BLOCKS;
-      E.pl = h->d_pl;
-      E.pl_cap = h->pl_cap;
-      E.pl_count = h->pl_count();
-      E.flags = build_flags;
-      E.gate = gate;
-      E.gate_on = 1;
-      if (gate == nullptr) {
-        E.fin_ticket = h->fin_ticket();
-        E.fin = finalize_args(TILE_BLOCKS + EXACT_BLOCKS);
-        finalized = true;
-      }
-      E.P = h->P;
-      CUDA_OK(h, launch_exact(E, stream));
-      h->launches++;
-      if (grad) {
-        CUDA_OK(h, tiles_scatter_add(B, G1.d_grad, G1.stride, G2.d_grad, G2.stride, gate, 1, stream));
-        h->launches++;
-      }
-      return B200CV_OK;
-    };
-    // list step: current coordinates into sorted order, tile walk under the masks, exact-pair
-    // queue + extras in one launch, gradients back.  Partial sums: [TILE_BLOCKS | EXACT_BLOCKS]
-    auto enqueue_tiles_walk = [&](double *partials, const int *gate) -> int {
-      TileBuffers &B = h->tiles;
-      TileSide &J = B.side[1];
-      TileSide &I = h->self() ? J : B.side[0];
-      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
-      h->launches++;
-      TileWalkArgs T{};
-      T.xi = I.d_xs; T.yi = I.d_ys; T.zi = I.d_zs; T.gi = I.d_gs; T.ni = I.n;
-      T.xj = J.d_xs; T.yj = J.d_ys; T.zj = J.d_zs; T.gj = J.d_gs; T.nj = J.n;
-      T.unit_hdr = B.d_unit_hdr;
-      T.tile_j = B.d_tile_j;
-      T.tile_m = B.d_tile_m;
-      T.cap_units = B.cap_units;
-      T.counts = B.d_counts;
-      T.rare = h->d_rare;
-      T.rare_cap = h->rare_cap;
-      T.rare_count = h->rare_count();
-      T.partials = partials;
-      T.want_grad = grad ? 1 : 0;
-      T.gate = gate;
-      T.P = h->P;
-      CUDA_OK(h, launch_tile_walk(T, h->exp_special, h->aniso, stream));
-      h->launches++;
-      ExactArgs E{};
-      tile_planes(E);
-      E.list = h->d_rare;
-      E.count32 = h->rare_count();
-      E.cap = h->rare_cap;
-      E.list2 = h->d_pl;
-      E.count2 = h->pl_count() + 1;  // persistent length of the extras
-      E.cap2 = h->pl_cap;
-      E.partials = partials + TILE_BLOCKS;
-      E.flags = flags & ~B200CV_EF_REBUILD_PAIRLIST;
-      E.fast_exp = (h->exp_special == 3) ? 3 : 0;
-      E.gate = gate;
-      E.gate_on = 0;
-      if (gate == nullptr) {
-        E.fin_ticket = h->fin_ticket();
-        E.fin = finalize_args(TILE_BLOCKS + EXACT_BLOCKS);
-        finalized = true;
-      }
-      E.P = h->P;
-      CUDA_OK(h, launch_exact(E, stream));
-      h->launches++;
-      if (grad) {
-        CUDA_OK(h, tiles_scatter_add(B, G1.d_grad, G1.stride, G2.d_grad, G2.stride, gate, 0, stream));
-        h->launches++;
-      }
-      return B200CV_OK;
-    };
-
     // ---- the list as neighbour rows (rows.cuh): open systems, sparse lists --------------------
     auto row_sides = [&](RowSideView &s1, RowSideView &s2) {
-      TileSide &J = h->tiles.side[1];
-      TileSide &I = h->self() ? J : h->tiles.side[0];
+      SortedGroup &J = h->sort.side[1];
+      SortedGroup &I = h->self() ? J : h->sort.side[0];
       s1 = RowSideView{I.d_xs, I.d_ys, I.d_zs, I.d_sorted, I.d_cell_start, I.n, G1.d_grad, G1.stride};
       s2 = RowSideView{J.d_xs, J.d_ys, J.d_zs, J.d_sorted, J.d_cell_start, J.n, G2.d_grad, G2.stride};
     };
@@ -645,10 +491,10 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     // rebuild.  Partial sums: [ROW_BLOCKS (| ROW_BLOCKS for the rows of group2) | EXACT_BLOCKS]
     auto enqueue_rows_build = [&](int build_flags, double *partials, const int *gate,
                                   int &nparts) -> int {
-      TileBuffers &B = h->tiles;
-      CUDA_OK(h, tiles_sort(B, x1, y1, z1, x2, y2, z2, gate, stream));
+      CellSort &B = h->sort;
+      CUDA_OK(h, cellsort_build(B, x1, y1, z1, x2, y2, z2, gate, stream));
       h->launches += h->self() ? 5 : 8;
-      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
+      CUDA_OK(h, cellsort_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
       h->launches++;
       RowSideView s1, s2;
       row_sides(s1, s2);
@@ -684,14 +530,14 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
         h->launches++;
       }
       h->pl_rows = true;
-      h->pl_tiles = h->pl_sorted = false;
+      h->pl_sorted = false;
       nparts = ndir * ROW_BLOCKS + EXACT_BLOCKS;
       return enqueue_row_exact(build_flags, false, partials + ndir * ROW_BLOCKS, nparts, gate, 1);
     };
     // list step.  Partial sums: [ROW_BLOCKS | EXACT_BLOCKS]
     auto enqueue_rows_walk = [&](double *partials, const int *gate) -> int {
-      TileBuffers &B = h->tiles;
-      CUDA_OK(h, tiles_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
+      CellSort &B = h->sort;
+      CUDA_OK(h, cellsort_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
       h->launches++;
       RowWalkArgs T{};
       row_sides(T.side[0], T.side[1]);
@@ -725,7 +571,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       // walk; the mode word decides on the device which of the two does any work
       int nparts = 0;
       int rc;
-      if (tiles_gated && rows_eval) {
+      if (rows_gated) {
         static_assert(3 * ROW_BLOCKS + 2 * EXACT_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
         int nb = 0;
         rc = enqueue_rows_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate(), nb);
@@ -733,13 +579,6 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
         rc = enqueue_rows_walk(h->d_partials + nb, h->gate());
         if (rc) return rc;
         npart = nb + ROW_BLOCKS + EXACT_BLOCKS;
-      } else if (tiles_gated) {
-        static_assert(2 * (TILE_BLOCKS + EXACT_BLOCKS) <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
-        rc = enqueue_tiles_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate());
-        if (rc) return rc;
-        rc = enqueue_tiles_walk(h->d_partials + TILE_BLOCKS + EXACT_BLOCKS, h->gate());
-        if (rc) return rc;
-        npart = 2 * (TILE_BLOCKS + EXACT_BLOCKS);
       } else {
         if (cells_usable(h) && sparse_list(h)) {
           // sized and found sparse by b200cv_pairlist_reserve before the capture
@@ -755,18 +594,12 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       }
     } else if (walk_list) {
       int rc = h->pl_rows ? enqueue_rows_walk(h->d_partials, nullptr)
-                          : (h->pl_tiles ? enqueue_tiles_walk(h->d_partials, nullptr)
-                                         : enqueue_walk(h->d_partials, nullptr));
+                          : enqueue_walk(h->d_partials, nullptr);
       if (rc) return rc;
-      npart = h->pl_rows ? ROW_BLOCKS + EXACT_BLOCKS
-                         : (h->pl_tiles ? TILE_BLOCKS + EXACT_BLOCKS : WALK_BLOCKS);
-    } else if (tiles_eval && rows_eval) {
+      npart = h->pl_rows ? ROW_BLOCKS + EXACT_BLOCKS : WALK_BLOCKS;
+    } else if (rows_eval) {
       int rc = enqueue_rows_build(flags, h->d_partials, nullptr, npart);
       if (rc) return rc;
-    } else if (tiles_eval) {
-      int rc = enqueue_tiles_build(flags, h->d_partials, nullptr);
-      if (rc) return rc;
-      npart = TILE_BLOCKS + EXACT_BLOCKS;
     } else if (rebuild_with_cells(h, flags)) {
       int rc = enqueue_cells(flags, nullptr);
       if (rc) return rc;
@@ -830,11 +663,13 @@ int post_sync(b200cv_cvc *h, bool &redo)
 {
   redo = false;
   unsigned long long const rare_n = h->h_counters[0], pl_n = h->h_counters[1];
-  unsigned long long const units = h->h_counters[3], tile_pairs = h->h_counters[4];
+  unsigned long long const units = h->h_counters[3];
+  // listed pairs kept in rows: selfCoordNum counts both directions of a pair
+  unsigned long long const row_pairs = h->h_counters[4] / (h->self() ? 2ull : 1ull);
   // gated (captured) evaluations: finalize_kernel reports the mode the finished launch ran in
   bool const rebuild = h->gated ? (h->h_counters[2] == 1)
                                 : (bool)(h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
-  bool const tiles_built = rebuild && (h->pl_tiles || h->pl_rows);
+  bool const rows_built = rebuild && h->pl_rows;
   unsigned long long const row_entries = h->h_counters[5];
   h->exact_pairs = (size_t)rare_n;
   if (rare_n > h->rare_cap) {
@@ -851,39 +686,32 @@ int post_sync(b200cv_cvc *h, bool &redo)
   }
   if (rebuild && !(h->center1() || h->center2())) {
     bool const over_pl = pl_n > h->pl_cap;
-    bool const over_tiles =
-        tiles_built && (h->pl_rows ? (units + row_slots(h) > h->rows.cap_chunks ||
-                                      row_entries > h->rows.cap_idx)
-                                   : units > h->tiles.cap_units);
-    if ((over_pl || over_tiles) && h->async_eval) {
+    bool const over_rows = rows_built && (units + row_slots(h) > h->rows.cap_chunks ||
+                                          row_entries > h->rows.cap_idx);
+    if ((over_pl || over_rows) && h->async_eval) {
       return fail(h, B200CV_MEMORY_ERROR,
                   "pair-list overflow in a captured evaluation (" + std::to_string(pl_n) +
                       " listed pairs, capacity " + std::to_string(h->pl_cap) + "; " +
-                      std::to_string(units) + " tile units, capacity " +
-                      std::to_string(h->tiles.cap_units) +
+                      std::to_string(row_entries) + " row entries, capacity " +
+                      std::to_string(h->rows.cap_idx) +
                       "): reserve more with b200cv_pairlist_reserve before capturing");
     }
     if (over_pl) {
       int rc = ensure_pairlist_capacity(h, pl_n);
       if (rc) return rc;
     }
-    if (over_tiles) {
+    if (over_rows) {
       h->epoch++;
-      if (h->pl_rows) {
-        CUDA_OK(h, rows_reserve(h->rows,
-                                (unsigned)std::min<unsigned long long>(row_entries + row_entries / 4 + 1024, 0xfffffff0ull),
-                                (unsigned)std::min<unsigned long long>(
-                                    row_slots(h) + units + units / 4 + 1024, 0xfffffff0ull)));
-      } else {
-        CUDA_OK(h, tiles_reserve(h->tiles, (unsigned)std::min<unsigned long long>(
-                                               units + units / 2, 1ull << 30)));
-      }
+      CUDA_OK(h, rows_reserve(h->rows,
+                              (unsigned)std::min<unsigned long long>(row_entries + row_entries / 4 + 1024, 0xfffffff0ull),
+                              (unsigned)std::min<unsigned long long>(
+                                  row_slots(h) + units + units / 4 + 1024, 0xfffffff0ull)));
     }
-    if (over_pl || over_tiles) {
+    if (over_pl || over_rows) {
       redo = true;
     } else {
       h->pl_entries = pl_n;
-      h->pl_n = pl_n + (tiles_built ? tile_pairs : 0ull);
+      h->pl_n = pl_n + (rows_built ? row_pairs : 0ull);
       h->pl_valid = true;
     }
   }

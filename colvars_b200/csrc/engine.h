@@ -29,7 +29,6 @@
 #include "cells.cuh"
 #include "fit.cuh"
 #include "kernels.cuh"
-#include "tiles.cuh"
 #include "rows.cuh"
 
 namespace b200cv {
@@ -81,7 +80,7 @@ struct b200cv_cvc {
   double *h_value = nullptr;                // mapped pinned
   double *h_value_dev = nullptr;            // device alias of h_value
   unsigned long long *h_counters = nullptr; // mapped pinned [8]: rare, listed (entries), gate mode,
-                                            // tile units, tile pairs
+                                            // overflow chunks / listed pairs / entries of the rows
   unsigned long long *h_counters_dev = nullptr;
   unsigned char *d_counters = nullptr;      // rare_count (u32 @0), pl_count (u64 @8),
                                             // persistent list length (u64 @16), gate (i32 @24),
@@ -110,15 +109,13 @@ struct b200cv_cvc {
   // be sparse
   b200cv::CellBuffers cells;
   bool cells_ready = false;
-  // the sparse list of an open system as masked cluster tiles (tiles.cuh); d_pl then holds the
-  // extras (pairs listed by the reference-order path), entries in sorted positions
-  b200cv::TileBuffers tiles;
-  bool tiles_ready = false;
-  bool pl_tiles = false;   // the current list is in tile form
-  // ... or as neighbour rows (rows.cuh, the default sparse form): both directions of every pair,
-  // d_pl again holds the extras (atom indices here)
+  // the sparse list of an open system as neighbour rows (rows.cuh): both groups sorted along a
+  // cell grid (cellsort.cuh), every atom keeps the sorted positions of all its listed partners;
+  // d_pl then holds the extras (pairs listed by the reference-order path), atom indices
+  b200cv::CellSort sort;
+  bool sort_ready = false;
   b200cv::RowList rows;
-  bool pl_rows = false;
+  bool pl_rows = false;    // the current list is in row form
   // an evaluation has been enqueued whose queue counters / new list lengths the host has not
   // looked at yet (sync_and_check): the next call that builds on its result checks first
   bool unchecked = false;
@@ -228,12 +225,10 @@ bool sorted_walk_enabled();
 bool sparse_list(const b200cv_cvc *h);
 bool cells_usable(const b200cv_cvc *h);
 bool rebuild_with_cells(const b200cv_cvc *h, int flags);
-bool tiles_usable(const b200cv_cvc *h);
-bool rebuild_with_tiles(const b200cv_cvc *h, int flags);
-unsigned tile_units_estimate(const b200cv_cvc *h);
-bool rows_preferred();
+bool rows_usable(const b200cv_cvc *h);
+bool rebuild_with_rows(const b200cv_cvc *h, int flags);
 unsigned row_slots(const b200cv_cvc *h);
-// allocations an evaluation with these flags may need (tile arrays): before any stream capture
+// allocations an evaluation with these flags may need (the row list): before any stream capture
 int prepare_calc(b200cv_cvc *h, int flags);
 int ensure_pairlist_capacity(b200cv_cvc *h, unsigned long long need);
 int ensure_rare_capacity(b200cv_cvc *h, unsigned long long need);

@@ -41,19 +41,15 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
     if (rc) return rc;
   }
   CUDA_OK_RC(prepare_calc(h, flags));
-  // a rebuild is captured in three forms: all-pairs sweep (first rebuild), cell list, cluster
-  // tiles (the host does not run enqueue_calc on a replay: what it would have noted -- the form
+  // a rebuild is captured in three forms: all-pairs sweep (first rebuild), cell list, neighbour
+  // rows (the host does not run enqueue_calc on a replay: what it would have noted -- the form
   // of the list a rebuild leaves behind -- is noted below), a list walk in three as well:
-  // entries as atom indices, entries in cell order, tiles
-  bool const rows_form = rows_preferred();
-  bool const tiles_rebuild = rebuild_with_tiles(h, flags) &&
-                             (rows_form ? h->rows.cap_idx > 0 : h->tiles.cap_units > 0);
-  bool const cells_rebuild = !tiles_rebuild && rebuild_with_cells(h, flags);
-  int graph_key = flags | (cells_rebuild ? (1 << 30) : 0) | (tiles_rebuild ? (1 << 28) : 0);
+  // entries as atom indices, entries in cell order, rows
+  bool const rows_rebuild = rebuild_with_rows(h, flags) && h->rows.cap_idx > 0;
+  bool const cells_rebuild = !rows_rebuild && rebuild_with_cells(h, flags);
+  int graph_key = flags | (cells_rebuild ? (1 << 30) : 0) | (rows_rebuild ? (1 << 28) : 0);
   if (use_pl && !rebuild && h->pl_sorted) graph_key |= (1 << 29);
-  if (use_pl && !rebuild && h->pl_tiles) graph_key |= (1 << 27);
-  if (use_pl && !rebuild && h->pl_rows) graph_key |= (1 << 26);
-  if (tiles_rebuild && rows_form) graph_key |= (1 << 25);
+  if (use_pl && !rebuild && h->pl_rows) graph_key |= (1 << 27);
   b200cv_cvc::StepGraph *hit = nullptr;
   for (auto &g : h->step_graphs) {
     if (g.flags == graph_key && g.pos == d_proxy_pos && g.stride == proxy_stride &&
@@ -95,8 +91,7 @@ int b200cv_step(b200cv_cvc *h, const double *d_proxy_pos, size_t proxy_stride,
   CUDA_OK(h, cudaGraphLaunch(hit->exec, user));
   if (use_pl && rebuild && !(h->center1() || h->center2())) {
     h->pl_sorted = cells_rebuild && sorted_walk_enabled();
-    h->pl_tiles = tiles_rebuild && !rows_form;
-    h->pl_rows = tiles_rebuild && rows_form;
+    h->pl_rows = rows_rebuild;
   }
   h->launches = hit->launches;
   h->async_eval = false;

@@ -57,17 +57,17 @@ __device__ __forceinline__ void finalize_body(FinalizeArgs const &A, double *red
       if (A.h_counters) A.h_counters[2] = (unsigned long long)mode;
       rebuilt = mode == 1;
     }
-    if (A.tile_counts && A.h_counters) {
-      A.h_counters[3] = (unsigned long long)*(const volatile unsigned *)A.tile_counts;
-      A.h_counters[4] = *(const volatile unsigned long long *)(A.tile_counts + 4);
-      A.h_counters[5] = (unsigned long long)*(const volatile unsigned *)(A.tile_counts + 3);
+    if (A.row_counts && A.h_counters) {
+      A.h_counters[3] = (unsigned long long)*(const volatile unsigned *)A.row_counts;
+      A.h_counters[4] = *(const volatile unsigned long long *)(A.row_counts + 4);
+      A.h_counters[5] = (unsigned long long)*(const volatile unsigned *)(A.row_counts + 3);
     }
     if (A.overflow) {
       bool over = A.rare_count && *(const volatile unsigned int *)A.rare_count > A.rare_cap;
       if (rebuilt) {
         over = over || (A.pl_count && *(const volatile unsigned long long *)A.pl_count > A.pl_cap);
-        over = over || (A.tile_counts && (*(const volatile unsigned *)A.tile_counts > A.tile_cap ||
-                                          *(const volatile unsigned *)(A.tile_counts + 3) > A.tile_cap2));
+        over = over || (A.row_counts && (*(const volatile unsigned *)A.row_counts > A.row_cap_chunks ||
+                                         *(const volatile unsigned *)(A.row_counts + 3) > A.row_cap_idx));
       }
       *A.overflow = over ? 1.0 : 0.0;
     }
@@ -76,9 +76,9 @@ __device__ __forceinline__ void finalize_body(FinalizeArgs const &A, double *red
         unsigned long long const n = *(const volatile unsigned long long *)A.pl_count;
         *A.pl_persist = n < A.pl_cap ? n : A.pl_cap;
       }
-      if (A.tile_counts) {
-        unsigned const u = *(const volatile unsigned *)A.tile_counts;
-        A.tile_counts[6] = u < A.tile_cap ? u : A.tile_cap;
+      if (A.row_counts) {
+        unsigned const u = *(const volatile unsigned *)A.row_counts;
+        A.row_counts[6] = u < A.row_cap_chunks ? u : A.row_cap_chunks;
       }
     }
     // mapped pinned copies: the host reads them after synchronising with the stream, and
@@ -294,11 +294,16 @@ __global__ void __launch_bounds__(EXACT_THREADS) center_kernel(const __grid_cons
   double const cx = A.center[0], cy = A.center[1], cz = A.center[2];
   double fsum = 0.0, sgx = 0.0, sgy = 0.0, sgz = 0.0;
   if (A.n == 0) {
-    // both sides are centres: one pair (groupCoord)
+    // both sides are centres: one pair (groupCoord; coordNum with both groups centre-only, which
+    // may carry a one-entry pair list: src/colvarcomp_coordnums.cpp:219-232)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      double Gx, Gy, Gz;
-      double const F = pair_exact(A.P, cx, cy, cz, A.center2[0], A.center2[1], A.center2[2],
-                                  A.flags, Gx, Gy, Gz);
+      bool const within = !use_pl || rebuild || A.pairlist[0];
+      double Gx = 0.0, Gy = 0.0, Gz = 0.0, F = 0.0;
+      if (within) {
+        F = pair_exact(A.P, cx, cy, cz, A.center2[0], A.center2[1], A.center2[2], A.flags, Gx,
+                       Gy, Gz);
+      }
+      if (use_pl && rebuild) A.pairlist[0] = F > 0.0 ? 1 : 0;
       fsum = F;
       if (grad && F > 0.0) {
         A.center_grad[0] += -Gx;

@@ -43,7 +43,8 @@ struct FinalizeArgs {
   double *h_value;  // mapped pinned
   const unsigned int *rare_count;
   const unsigned long long *pl_count;
-  // mapped pinned [8]: rare_count, pl_count, gate mode, tile units, tile pairs
+  // mapped pinned [8]: rare_count, pl_count, gate mode, overflow chunks of the rows, listed
+  // pairs in rows, row entries
   unsigned long long *h_counters;
   // after a rebuild -- `rebuilt` != 0, or *gate == 1 in a gated (captured) evaluation -- the
   // lengths of the new list are kept on the device for the list steps that follow (clamped to
@@ -52,9 +53,9 @@ struct FinalizeArgs {
   int rebuilt;
   unsigned long long *pl_persist;
   unsigned long long pl_cap;
-  unsigned *tile_counts;  // TileBuffers::d_counts or null
-  unsigned tile_cap;      // capacity in units (tiles) or chunks (rows)
-  unsigned tile_cap2;     // rows: capacity in entries (counts[3]); tiles: unused (all ones)
+  unsigned *row_counts;     // CellSort::d_counts (counters of the row list, rows.cuh) or null
+  unsigned row_cap_chunks;  // capacity in overflow chunks (counts[0])
+  unsigned row_cap_idx;     // capacity in entries (counts[3])
   // sharded runs: 1.0 when a queue of this rank overflowed, else 0.0, into the word that the
   // all-reduce sums next to the value (null: single rank)
   unsigned int rare_cap;
@@ -96,7 +97,7 @@ constexpr int EXACT_THREADS = 128;
 // warp slot the register file allows (58 registers -> 8 CTAs per SM)
 constexpr int WALK_BLOCKS = 1184;
 // partial sums behind the sweep items: [rare queue | walk], [cell kernel (592) | walk] or
-// [tile build | its exact queue | tile walk | its exact lists]
+// [row build (| rows of group2) | its exact queue | row walk | its exact lists]
 constexpr int PARTIALS_TAIL = 6144;
 int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks = EXACT_BLOCKS);
 

@@ -54,6 +54,10 @@ struct PairParams {
   double tri_n[13];          // |s_k|^2 of the 13 directions TRI_DIRS (1e300: not periodic)
   double tri_shift[13][3];   // s_k = ix a + iy b + iz c in the reference's operation order
   double tri_margin;         // image decisions closer than this go to the exact-pair queue
+  // 0: an orthogonal cell whose vectors carry off-diagonal terms below the reference's tolerance
+  // (1e-5; src/colvars_system.h:120-140 keeps type "orthogonal" for it): the reference rounds the
+  // fractional coordinates with the full vectors but does not search the neighbouring images
+  int tri_search;
 };
 
 // the 13 lattice directions of get_triclinic_shift (src/colvars_system.h:194-219) up to sign:
@@ -284,7 +288,7 @@ __device__ inline void position_distance_exact(PairParams const &P, double x1, d
                                __dmul_rn(zs, P.cell[2][1])));
   dz = __dsub_rn(dz, __dadd_rn(__dadd_rn(__dmul_rn(xs, P.cell[0][2]), __dmul_rn(ys, P.cell[1][2])),
                                __dmul_rn(zs, P.cell[2][2])));
-  if (P.bc_type != 2) {
+  if (P.bc_type != 2 && P.tri_search) {
     // get_triclinic_shift: search the neighbouring images for a shorter vector
     double min_d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     double rx = 0.0, ry = 0.0, rz = 0.0;

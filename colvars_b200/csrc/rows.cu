@@ -10,33 +10,91 @@ namespace b200cv {
 namespace {
 
 constexpr int WARPS = ROW_THREADS / 32;
+#ifndef B200CV_ROW_U
+#define B200CV_ROW_U 2
+#endif
+#ifndef B200CV_ROW_MINB
+#define B200CV_ROW_MINB 8  // CTAs per SM the walk's register allocation targets
+#endif
 
-// One pair of a row, branch-free: d = x_partner - x_own.  `valid` lanes that are not next to a
-// decision threshold get the sweep's fast form (F = 0 exactly beyond tolerance_l2_max); every
-// other lane evaluates l2 = 2^100 and contributes nothing.
+// decision thresholds of the pair function as integers (high words of l2), kept in registers
+struct RowConsts {
+  int thr_lo;       // window around tolerance_l2_max and the root of f0 = tolerance ...
+  unsigned thr_w;   // ... [thr_lo, thr_lo + thr_w]
+  int l2max_hi;     // high word of tolerance_l2_max
+};
+
+// One pair of a row, branch-free: d = x_partner - x_own, vm = all ones for a lane that holds a
+// pair (all zeros: padding).  A pair next to a decision threshold (`rare`) contributes nothing
+// here, nor does one beyond tolerance_l2_max: both evaluate l2 = 2^100 and F is masked to +0
+// (gq ~ 2^-400 then: nothing at any scale).  Beyond the threshold window "l2 > tolerance_l2_max"
+// can be read off the high word alone, and below it the shifted function is positive
+// (pair_is_rare, pair_math.cuh), so no comparison of F is needed.
 template <int EXP, bool ANISO>
-__device__ __forceinline__ void row_pair(PairParams const &P, double dx, double dy, double dz,
-                                         bool valid, double &F, double &gq, bool &near1,
-                                         bool &nearthr)
+__device__ __forceinline__ void row_pair(PairParams const &P, RowConsts const &K, double dx,
+                                         double dy, double dz, int vm, double &F, double &gq,
+                                         bool &rare)
 {
   double ex = dx, ey = dy, ez = dz;
   double const u = pair_l2<ANISO, BC_NONE>(P, ex, ey, ez);
   int const uh = __double2hiint(u);
-  near1 = valid && ((unsigned)(uh - 0x3FEE0000) < 0x30000u);
-  nearthr = valid && ((unsigned)(uh - P.thr_lo_hi) <= P.thr_width);
-  int const keep = (valid && !near1 && !nearthr) ? -1 : 0;
+  rare = (((unsigned)(uh - 0x3FEE0000) < 0x30000u) || ((unsigned)(uh - K.thr_lo) <= K.thr_w)) &&
+         (vm != 0);
+  int const keep = (rare || uh > K.l2max_hi) ? 0 : vm;
   double const ue =
       __hiloint2double((uh & keep) | (0x46300000 & ~keep), __double2loint(u) & keep);
-  switching_fast<EXP, true>(ue, false, P, F, gq);
+  if constexpr (EXP > 0) {
+    double const um1 = ipow<EXP - 1>(ue);
+    double const q = fma(um1, ue, 1.0);
+    double const r = fast_rcp(q);
+    double const Fs = fma(r, P.inv1mt, P.ntol);
+    F = __hiloint2double(__double2hiint(Fs) & keep, __double2loint(Fs) & keep);
+    gq = um1 * (r * r);
+  } else {
+    switching_fast<0, true>(ue, false, P, F, gq);
+  }
 }
 
-__device__ __forceinline__ void queue_rare(unsigned long long *rare, unsigned rare_cap,
-                                           unsigned *rare_count, int atom1, int atom2)
+// Exact-pair queue of a warp.  Appending to the global queue costs an atomic on ONE counter for
+// the whole grid; at a few rare pairs per row that is tens of thousands of serialised
+// same-address atomics per step -- more than the pair arithmetic of a list step.  So a warp
+// collects its rare pairs in shared memory and appends them in one go (one atomic per RQ_CAP
+// entries or per block of rows).
+constexpr int RQ_CAP = 64;
+struct RareBuf {
+  unsigned long long e[RQ_CAP];
+};
+
+__device__ __forceinline__ void rare_flush(RareBuf &B, int &n, unsigned long long *rare,
+                                           unsigned rare_cap, unsigned *rare_count, int lane)
 {
-  unsigned const slot = atomicAdd(rare_count, 1u);
-  if (slot < rare_cap) {
-    rare[slot] = ((unsigned long long)(unsigned)atom1 << 32) | (unsigned long long)(unsigned)atom2;
+  if (n > 0) {
+    __syncwarp();
+    unsigned base = 0u;
+    if (lane == 0) base = atomicAdd(rare_count, (unsigned)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < n; k += 32) {
+      if (base + (unsigned)k < rare_cap) rare[base + k] = B.e[k];
+    }
+    __syncwarp();
+    n = 0;
   }
+}
+
+// warp-wide: lanes with `mine` append (atom1, atom2); n is warp-uniform
+__device__ __forceinline__ void rare_push(RareBuf &B, int &n, bool mine, int atom1, int atom2,
+                                          unsigned long long *rare, unsigned rare_cap,
+                                          unsigned *rare_count, int lane)
+{
+  unsigned const m = __ballot_sync(0xffffffffu, mine);
+  if (m == 0u) return;
+  int const add = __popc(m);
+  if (n + add > RQ_CAP) rare_flush(B, n, rare, rare_cap, rare_count, lane);
+  if (mine) {
+    B.e[n + __popc(m & ((1u << lane) - 1u))] =
+        ((unsigned long long)(unsigned)atom1 << 32) | (unsigned long long)(unsigned)atom2;
+  }
+  n += add;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -50,8 +108,9 @@ __device__ __forceinline__ double warp_sum(double v)
 template <int EXP, bool ANISO>
 __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_constant__ RowBuildArgs A)
 {
-  __shared__ int stage[WARPS][64];
+  __shared__ int stage[WARPS][96];  // up to 31 left over + two chunks of 32
   __shared__ int rbuf[WARPS][ROW_BUF];
+  __shared__ RareBuf rqs[WARPS];
   __shared__ double red[WARPS];
   __shared__ unsigned long long redn[WARPS];
   if (A.gate != nullptr && *A.gate != 1) {
@@ -62,9 +121,12 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
   unsigned const lt = (1u << lane) - 1u;
   int *const S = stage[warp];
   int *const R = rbuf[warp];
-  TileGrid const g = *A.grid;
+  RareBuf &RQ = rqs[warp];
+  int nrq = 0;
+  SortGrid const g = *A.grid;
   PairParams const &P = A.P;
   double const l2_pass = P.l2_max * (1.0 + 1.0e-9);
+  RowConsts const K{P.thr_lo_hi, P.thr_width, __double2hiint(P.l2_max)};
   double const cell1 = 1.0 / g.inv_cell[1], cell2 = 1.0 / g.inv_cell[2];
   double fsum = 0.0;
   unsigned long long npairs = 0ull;
@@ -78,10 +140,10 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
   for (int p = p_first; p < p_last; p++) {
     double const xo = A.own.xs[p], yo = A.own.ys[p], zo = A.own.zs[p];
     int const own_atom = A.own.sorted[p];
-    int const iy_lo = tile_cell(yo - A.cut[1], g.origin[1], g.inv_cell[1], g.dim[1]);
-    int const iy_hi = tile_cell(yo + A.cut[1], g.origin[1], g.inv_cell[1], g.dim[1]);
-    int const iz_lo = tile_cell(zo - A.cut[2], g.origin[2], g.inv_cell[2], g.dim[2]);
-    int const iz_hi = tile_cell(zo + A.cut[2], g.origin[2], g.inv_cell[2], g.dim[2]);
+    int const iy_lo = sort_cell(yo - A.cut[1], g.origin[1], g.inv_cell[1], g.dim[1]);
+    int const iy_hi = sort_cell(yo + A.cut[1], g.origin[1], g.inv_cell[1], g.dim[1]);
+    int const iz_lo = sort_cell(zo - A.cut[2], g.origin[2], g.inv_cell[2], g.dim[2]);
+    int const iz_hi = sort_cell(zo + A.cut[2], g.origin[2], g.inv_cell[2], g.dim[2]);
     int const nry = iy_hi - iy_lo + 1;
     int const nspan = nry * (iz_hi - iz_lo + 1);
     double gx = 0.0, gy = 0.0, gz = 0.0;
@@ -118,25 +180,26 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       int const q = S[valid ? lane : 0];
       double const dx = A.nbr.xs[q] - xo, dy = A.nbr.ys[q] - yo, dz = A.nbr.zs[q] - zo;
       double F, gq;
-      bool near1, nearthr;
-      row_pair<EXP, ANISO>(P, dx, dy, dz, valid, F, gq, near1, nearthr);
-      bool const canonical = A.self ? (q > p) : (A.canonical != 0);
-      fsum += canonical ? F : 0.0;
+      bool rare;
+      row_pair<EXP, ANISO>(P, K, dx, dy, dz, valid ? -1 : 0, F, gq, rare);
+      fsum += F;  // both sides of a selfCoordNum pair: halved at the end
       gx = fma(gq, dx, gx);
       gy = fma(gq, dy, gy);
       gz = fma(gq, dz, gz);
-      if (__builtin_expect((near1 || nearthr) && canonical, 0)) {
-        int const nbr_atom = A.nbr.sorted[q];
-        if (A.own_is_group1) queue_rare(A.rare, A.rare_cap, A.rare_count, own_atom, nbr_atom);
-        else queue_rare(A.rare, A.rare_cap, A.rare_count, nbr_atom, own_atom);
+      if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) {
+        // the canonical side hands the pair to exact_kernel
+        bool const mine = rare && (A.self ? (q > p) : (A.canonical != 0));
+        int const nbr_atom = mine ? A.nbr.sorted[q] : 0;
+        rare_push(RQ, nrq, mine, A.own_is_group1 ? own_atom : nbr_atom,
+                  A.own_is_group1 ? nbr_atom : own_atom, A.rare, A.rare_cap, A.rare_count, lane);
       }
       // in the row: listed by the sign of the shifted function; pairs next to a threshold are
       // listed (or not) by exact_kernel and live in the extras
-      bool const listed = valid && !near1 && !nearthr && __double_as_longlong(F) != 0ll;
+      bool const listed = valid && !rare && __double_as_longlong(F) != 0ll;
       unsigned const ml = __ballot_sync(0xffffffffu, listed);
       if (listed) R[rlen + __popc(ml & lt)] = q;
       rlen += __popc(ml);
-      npairs += (listed && canonical) ? 1ull : 0ull;
+      npairs += listed ? 1ull : 0ull;
       __syncwarp();
       if (rlen > ROW_BUF - 32) flush(false);
     };
@@ -160,8 +223,8 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
         double const r2 = fma(sz, sz, sy * sy);
         if (r2 <= l2_pass) {
           double const xr = sqrt(l2_pass - r2) / P.inv_r0[0] * (1.0 + 1.0e-9);
-          int const ix_lo = tile_cell(xo - xr, g.origin[0], g.inv_cell[0], g.dim[0]);
-          int const ix_hi = tile_cell(xo + xr, g.origin[0], g.inv_cell[0], g.dim[0]);
+          int const ix_lo = sort_cell(xo - xr, g.origin[0], g.inv_cell[0], g.dim[0]);
+          int const ix_hi = sort_cell(xo + xr, g.origin[0], g.inv_cell[0], g.dim[0]);
           int const row = (iz * g.dim[1] + iy) * g.dim[0];
           begin = A.nbr.cell_start[row + ix_lo];
           end = A.nbr.cell_start[row + ix_hi + 1];
@@ -171,26 +234,40 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       for (int s = 0; s < nsp; s++) {
         int const b = __shfl_sync(0xffffffffu, begin, s);
         int const e = __shfl_sync(0xffffffffu, end, s);
-        for (int q0 = b; q0 < e; q0 += 32) {
-          int const q = q0 + lane;
-          bool pass = false;
-          if (q < e) {
-            double dx = A.nbr.xs[q] - xo, dy = A.nbr.ys[q] - yo, dz = A.nbr.zs[q] - zo;
-            double const u = pair_l2<ANISO, BC_NONE>(P, dx, dy, dz);
-            pass = (u <= l2_pass) && !(A.self && q == p);
+        // two chunks of 32 candidates per trip: their loads are independent
+        for (int q0 = b; q0 < e; q0 += 64) {
+          int const qa = q0 + lane, qb = q0 + 32 + lane;
+          bool pa = false, pb = false;
+          double ua = 0.0, ub = 0.0;
+          if (qa < e) {
+            double dx = A.nbr.xs[qa] - xo, dy = A.nbr.ys[qa] - yo, dz = A.nbr.zs[qa] - zo;
+            ua = pair_l2<ANISO, BC_NONE>(P, dx, dy, dz);
+            pa = true;
           }
-          unsigned const m = __ballot_sync(0xffffffffu, pass);
-          if (m == 0u) continue;
-          if (pass) S[nst + __popc(m & lt)] = q;
-          nst += __popc(m);
+          if (qb < e) {
+            double dx = A.nbr.xs[qb] - xo, dy = A.nbr.ys[qb] - yo, dz = A.nbr.zs[qb] - zo;
+            ub = pair_l2<ANISO, BC_NONE>(P, dx, dy, dz);
+            pb = true;
+          }
+          pa = pa && (ua <= l2_pass) && !(A.self && qa == p);
+          pb = pb && (ub <= l2_pass) && !(A.self && qb == p);
+          unsigned const ma = __ballot_sync(0xffffffffu, pa);
+          unsigned const mb = __ballot_sync(0xffffffffu, pb);
+          if ((ma | mb) == 0u) continue;
+          if (pa) S[nst + __popc(ma & lt)] = qa;
+          nst += __popc(ma);
+          if (pb) S[nst + __popc(mb & lt)] = qb;
+          nst += __popc(mb);
           __syncwarp();
-          if (nst >= 32) {
+          while (nst >= 32) {
             evaluate(32);
-            int const rest = nst - 32;
-            int moved = 0;
-            if (lane < rest) moved = S[32 + lane];
+            int const rest = nst - 32;  // < 64
+            int m0 = 0, m1 = 0;
+            if (lane < rest) m0 = S[32 + lane];
+            if (lane + 32 < rest) m1 = S[64 + lane];
             __syncwarp();
-            if (lane < rest) S[lane] = moved;
+            if (lane < rest) S[lane] = m0;
+            if (lane + 32 < rest) S[32 + lane] = m1;
             nst = rest;
             __syncwarp();
           }
@@ -211,6 +288,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
     }
   }
 
+  rare_flush(RQ, nrq, A.rare, A.rare_cap, A.rare_count, lane);
   fsum = warp_sum(fsum);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, d);
@@ -226,16 +304,39 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       s += red[w];
       np += redn[w];
     }
-    A.partials[blockIdx.x] = s;
-    if (np) atomicAdd(reinterpret_cast<unsigned long long *>(A.counts + 4), np);
+    // selfCoordNum: every pair was seen from both of its atoms; coordNum: the scalar and the pair
+    // count belong to the rows of group1
+    bool const counts = A.self || A.canonical != 0;
+    A.partials[blockIdx.x] = A.self ? 0.5 * s : (counts ? s : 0.0);
+    // (selfCoordNum: entries, i.e. twice the pairs -- the host halves the total)
+    if (np && counts) atomicAdd(reinterpret_cast<unsigned long long *>(A.counts + 4), np);
   }
 }
 
 // ---- list step: one warp per row chunk ------------------------------------------------------------
+// The walk is a stream of dependent loads -- chunk header -> partner indices -> partner
+// coordinates -- over a 50 MB index array that comes from HBM every step (at BASELINE config 3),
+// so each warp runs a software pipeline over its block of rows: while row t is evaluated, the
+// header of row t + 2 is being loaded and the indices (and own coordinates) of row t + 1 are on
+// their way into a shared-memory buffer (cp.async), two buffers per warp.
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int EXP, bool ANISO>
-__global__ void __launch_bounds__(ROW_THREADS) row_walk_kernel(const __grid_constant__ RowWalkArgs A)
+__global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(const __grid_constant__ RowWalkArgs A)
 {
   __shared__ double red[WARPS];
+  __shared__ int sidx[WARPS][2][ROW_BUF];
+  __shared__ RareBuf rqs[WARPS];
   if (A.gate != nullptr && *A.gate != 0) {
     if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
     return;
@@ -256,64 +357,113 @@ __global__ void __launch_bounds__(ROW_THREADS) row_walk_kernel(const __grid_cons
   unsigned const per = (total + nwarps - 1) / nwarps;
   unsigned const t_first = gwarp * per;
   unsigned const t_last = min(t_first + per, total);
-  constexpr int U = 4;  // steps whose loads are issued together
-  for (unsigned t = t_first; t < t_last; t++) {
+  constexpr int U = B200CV_ROW_U;  // steps whose loads are issued together
+  RowConsts const K{P.thr_lo_hi, P.thr_width, __double2hiint(P.l2_max)};
+  RareBuf &RQ = rqs[warp];
+  int nrq = 0;
+
+  auto header = [&](unsigned t) -> int4 {
+    if (t >= t_last) return make_int4(0, 0, 0, 0);
     unsigned const slot = t < n0 ? (unsigned)A.row_begin[0] + t
                                  : (t < n0 + n1 ? A.chunk_base1 + (unsigned)A.row_begin[1] + (t - n0)
                                                 : A.chunk_extra + (t - n0 - n1));
-    int4 const ch = A.chunks[slot];
-    int const p = ch.x, start = ch.y, len = ch.z, dir = ch.w;
-    if (len <= 0) continue;
-    RowSideView const &O = A.side[A.self ? 0 : dir];
-    RowSideView const &N = A.side[A.self ? 0 : 1 - dir];
-    double const xo = O.xs[p], yo = O.ys[p], zo = O.zs[p];
-    double gx = 0.0, gy = 0.0, gz = 0.0;
-    for (int k = 0; k < len; k += 32 * U) {
-      int q[U];
-      bool valid[U];
-      double dx[U], dy[U], dz[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        int const kk = k + 32 * u + lane;
-        valid[u] = kk < len;
-        q[u] = A.idx[start + (valid[u] ? kk : 0)];
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        dx[u] = N.xs[q[u]] - xo;
-        dy[u] = N.ys[q[u]] - yo;
-        dz[u] = N.zs[q[u]] - zo;
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (k + 32 * u >= len) break;  // warp-uniform
+    return A.chunks[slot];
+  };
+  // indices of a chunk into one of the warp's two buffers (asynchronously)
+  auto prefetch = [&](int4 const &ch, int buf) {
+    int const len = min(ch.z, ROW_BUF);
+    for (int k = lane; k < len; k += 32) cp_async4(&sidx[warp][buf][k], A.idx + ch.y + k);
+    cp_async_commit();
+  };
+
+  int4 h1 = header(t_first), h2 = header(t_first + 1);
+  prefetch(h1, 0);
+  // own coordinates of the coming row, loaded one row ahead like its indices
+  double nxo = 0.0, nyo = 0.0, nzo = 0.0;
+  if (t_first < t_last) {
+    RowSideView const &O1 = A.side[A.self ? 0 : h1.w];
+    nxo = O1.xs[h1.x];
+    nyo = O1.ys[h1.x];
+    nzo = O1.zs[h1.x];
+  }
+  for (unsigned t = t_first; t < t_last; t++) {
+    int4 const ch = h1;
+    double const xo = nxo, yo = nyo, zo = nzo;
+    int const buf = (int)((t - t_first) & 1u);
+    h1 = h2;
+    h2 = header(t + 2);
+    prefetch(h1, buf ^ 1);  // (an empty group past the last row)
+    if (t + 1 < t_last) {
+      RowSideView const &O1 = A.side[A.self ? 0 : h1.w];
+      nxo = O1.xs[h1.x];
+      nyo = O1.ys[h1.x];
+      nzo = O1.zs[h1.x];
+    }
+    cp_async_wait<1>();  // this row's indices have landed (the next row's may still be in flight)
+    __syncwarp();
+    int const p = ch.x, len = min(ch.z, ROW_BUF), dir = ch.w;
+    if (len > 0) {
+      RowSideView const &O = A.side[A.self ? 0 : dir];
+      RowSideView const &N = A.side[A.self ? 0 : 1 - dir];
+      const int *const q_of = sidx[warp][buf];
+      double gx = 0.0, gy = 0.0, gz = 0.0, rsum = 0.0;
+      auto one_pair = [&](int q, double dx, double dy, double dz, int vm) {
         double F, gq;
-        bool near1, nearthr;
-        row_pair<EXP, ANISO>(P, dx[u], dy[u], dz[u], valid[u], F, gq, near1, nearthr);
-        bool const canonical = A.self ? (q[u] > p) : (dir == 0);
-        fsum += canonical ? F : 0.0;
-        gx = fma(gq, dx[u], gx);
-        gy = fma(gq, dy[u], gy);
-        gz = fma(gq, dz[u], gz);
-        if (__builtin_expect((near1 || nearthr) && canonical, 0)) {
-          int const own_atom = O.sorted[p], nbr_atom = N.sorted[q[u]];
-          if (dir == 0) queue_rare(A.rare, A.rare_cap, A.rare_count, own_atom, nbr_atom);
-          else queue_rare(A.rare, A.rare_cap, A.rare_count, nbr_atom, own_atom);
+        bool rare;
+        row_pair<EXP, ANISO>(P, K, dx, dy, dz, vm, F, gq, rare);
+        rsum += F;
+        gx = fma(gq, dx, gx);
+        gy = fma(gq, dy, gy);
+        gz = fma(gq, dz, gz);
+        if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) {
+          // the canonical side hands the pair to exact_kernel
+          bool const mine = rare && (A.self ? (q > p) : (dir == 0));
+          int const own_atom = O.sorted[p], nbr_atom = mine ? N.sorted[q] : 0;
+          rare_push(RQ, nrq, mine, dir == 0 ? own_atom : nbr_atom, dir == 0 ? nbr_atom : own_atom,
+                    A.rare, A.rare_cap, A.rare_count, lane);
+        }
+      };
+      // groups of U steps: all coordinate loads first (independent of each other), then the
+      // arithmetic; lanes beyond the end of the row read entry 0 and are masked out
+      for (int k = 0; k < len; k += 32 * U) {
+        int q[U], vm[U];
+        double dx[U], dy[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          int const kk = k + 32 * u + lane;
+          vm[u] = kk < len ? -1 : 0;
+          q[u] = q_of[kk & vm[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          dx[u] = N.xs[q[u]] - xo;
+          dy[u] = N.ys[q[u]] - yo;
+          dz[u] = N.zs[q[u]] - zo;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (k + 32 * u < len) one_pair(q[u], dx[u], dy[u], dz[u], vm[u]);  // warp-uniform test
+        }
+      }
+      // the scalar: both sides of a selfCoordNum pair are in rows (half each), a coordNum pair
+      // counts in the row of its group1 atom
+      fsum += A.self ? 0.5 * rsum : (dir == 0 ? rsum : 0.0);
+      if (A.want_grad) {
+        gx = warp_sum(gx);
+        gy = warp_sum(gy);
+        gz = warp_sum(gz);
+        if (lane == 0) {
+          int const own_atom = O.sorted[p];
+          atomicAdd(&O.grad[own_atom], -P.c_grad[0] * gx);
+          atomicAdd(&O.grad[O.gstride + own_atom], -P.c_grad[1] * gy);
+          atomicAdd(&O.grad[2 * O.gstride + own_atom], -P.c_grad[2] * gz);
         }
       }
     }
-    if (A.want_grad) {
-      gx = warp_sum(gx);
-      gy = warp_sum(gy);
-      gz = warp_sum(gz);
-      if (lane == 0) {
-        int const own_atom = O.sorted[p];
-        atomicAdd(&O.grad[own_atom], -P.c_grad[0] * gx);
-        atomicAdd(&O.grad[O.gstride + own_atom], -P.c_grad[1] * gy);
-        atomicAdd(&O.grad[2 * O.gstride + own_atom], -P.c_grad[2] * gz);
-      }
-    }
+    __syncwarp();  // the buffer is free for the row after next
   }
+  cp_async_wait<0>();
+  rare_flush(RQ, nrq, A.rare, A.rare_cap, A.rare_count, lane);
   fsum = warp_sum(fsum);
   if (lane == 0) red[warp] = fsum;
   __syncthreads();

@@ -2,7 +2,7 @@
 //
 // The reference keeps one bool per pair (src/colvarcomp_coordnums.cpp:147-151) and, between
 // rebuilds, evaluates exactly the pairs whose bool is set (:219-228).  Here every atom owns a row:
-// the sorted positions (cell order, tiles.cuh) of ALL its listed partners, so a pair appears
+// the sorted positions (cell order, cellsort.cuh) of ALL its listed partners, so a pair appears
 // twice, once in the row of each of its atoms (coordNum: rows of group1 atoms hold group2
 // partners and the other way round).  That doubles the pair evaluations of a list step and pays
 // for it several times over: a warp works on one row, 32 partners at a time, with coalesced index
@@ -33,7 +33,7 @@
 #include <cuda_runtime.h>
 
 #include "pair_math.cuh"
-#include "tiles.cuh"
+#include "cellsort.cuh"
 
 namespace b200cv {
 
@@ -48,8 +48,9 @@ struct RowList {
   // group2's -- and behind them the overflow chunks of rows with more than ROW_BUF entries
   int4 *d_chunks = nullptr;
   unsigned cap_chunks = 0;
-  // counters live in TileBuffers::d_counts: [0] overflow chunks of this build, [3] entries of this
-  // build, [4..5] canonical entries (= listed pairs in rows) of this build, [6] overflow chunks
+  // counters live in CellSort::d_counts: [0] overflow chunks of this build, [3] entries of this
+  // build, [4..5] entries of the canonical rows of this build (selfCoordNum: all rows, i.e. twice the
+  // pairs), [6] overflow chunks
   // of the current list
 };
 
@@ -64,7 +65,7 @@ struct RowSideView {
 
 struct RowBuildArgs {
   RowSideView own, nbr;
-  const TileGrid *grid;
+  const SortGrid *grid;
   int self;                    // own == nbr: skip the atom itself, canonical = partner later
   int canonical;               // coordNum: 1 for the rows of group1, 0 for the rows of group2
   int own_is_group1;           // rare-queue entries are (group1 atom << 32 | group2 atom)
@@ -76,7 +77,7 @@ struct RowBuildArgs {
   unsigned cap_chunks;
   unsigned chunk_base;         // slot of this group's row 0
   unsigned chunk_extra;        // first overflow slot (= number of rows of both groups)
-  unsigned *counts;            // TileBuffers::d_counts
+  unsigned *counts;            // CellSort::d_counts
   unsigned long long *rare;
   unsigned int rare_cap;
   unsigned int *rare_count;

@@ -513,6 +513,7 @@ int coordnum_b200::add_calc_value_node(
   }
   static_cast<boundaries_view const &>(boundary_conditions).push(engine);
   static_cast<boundaries_view const &>(boundary_conditions).numbers(frozen_cell);
+  dynamic_cell = graph_stale = false;  // a fresh capture: current cell, current addresses
   if (char const *f = std::getenv("B200CV_SHIM_FAKE_OVERFLOW_STEP")) fake_overflow_step = std::atoi(f);
   auto &b1 = group1->get_gpu_atom_group()->get_gpu_buffers();
   const double *p2 = group2 ? group2->get_gpu_atom_group()->get_gpu_buffers().d_atoms_pos : nullptr;
@@ -559,7 +560,7 @@ void CUDART_CB coordnum_b200::cell_check(void *self)
   c->current_cell(now);
   bool differs = false;
   for (int k = 0; k < 12; k++) differs = differs || (now[k] != c->frozen_cell[k]);
-  int const skip = (differs || c->dynamic_cell) ? 1 : 0;
+  int const skip = (differs || c->dynamic_cell || c->graph_stale) ? 1 : 0;
   b200cv_async_set_skip(c->engine, skip);
   c->launch_skipped.store(skip);
 }
@@ -592,7 +593,6 @@ int coordnum_b200::calc_value_after_gpu()
 {
   // the scheduler has synchronised the stream; the scalar sits in mapped pinned memory
   bool const skipped = launch_skipped.load() != 0;
-  bool rebuild_graphs = false;
   if (!skipped) {
     int rc = b200cv_value(engine, &x.real_value);
     if (rc == B200CV_OK && fake_overflow_step >= 0 &&
@@ -602,35 +602,23 @@ int coordnum_b200::calc_value_after_gpu()
     }
     if (rc == B200CV_MEMORY_ERROR) {
       // a queue of the captured evaluation overflowed (it cannot grow under the graph that
-      // holds its address): do this step directly -- that path grows the queues -- and have
-      // the graphs built again on the new buffers
+      // holds its address): do this step directly -- that path grows the queues -- and keep
+      // the captured kernels switched off from now on: they hold the old addresses
       cvmodule->log("b200cv: " + name + ": " + std::string(b200cv_last_error(engine)) +
-                    " -- evaluating this step directly and rebuilding the graphs\n");
-      int const erc = evaluate_now();
-      if (erc != COLVARS_OK) return erc;
-      rebuild_graphs = true;
-    } else if (rc != B200CV_OK) {
-      return b200_error(rc);
+                    " -- evaluating this step directly; the component stays outside the "
+                    "captured graph until the graphs are built again\n");
+      graph_stale = true;
+      return evaluate_now();
     }
+    if (rc != B200CV_OK) return b200_error(rc);
   } else {
+    if (!dynamic_cell && !graph_stale) {
+      dynamic_cell = true;
+      cvmodule->log("b200cv: " + name + ": the periodic cell has changed since the graph was "
+                    "captured; evaluating outside the captured graph from now on\n");
+    }
     int const erc = evaluate_now();
     if (erc != COLVARS_OK) return erc;
-    if (!dynamic_cell) {
-      long long const step = (long long)cvmodule->step_relative();
-      if (step - last_cell_change <= 1) {
-        dynamic_cell = true;  // two steps in a row: a barostat; stop re-capturing
-        cvmodule->log("b200cv: " + name + ": the periodic cell changes every step; evaluating "
-                      "outside the captured graph from now on\n");
-      } else {
-        rebuild_graphs = true;  // capture again with the new cell
-      }
-      last_cell_change = step;
-    }
-  }
-  if (rebuild_graphs && cvmodule->gpu_calc) {
-    // colvarmodule_gpu_calc::init (src/colvar_gpu_calc.cpp:724-735): every graph is built again
-    // on its next use, add_calc_value_node included
-    cvmodule->gpu_calc->init();
   }
   if (tolerance > 0) {
     // compute_coordnum's rebuild test (src/colvarcomp_coordnums.cpp:255) for the NEXT launch

@@ -72,12 +72,15 @@ protected:
   // i.e. after wait_for_extra_info_ready has delivered this step's lattice,
   // src/colvar_gpu_calc.cpp:753-757) that compares the proxy's cell with the frozen one and,
   // if they differ, makes the kernels of this launch do nothing; calc_value_after_gpu then
-  // evaluates the step directly (evaluate_now) and asks the scheduler to build its graphs again
-  // -- or, when the cell changes step after step (a barostat), keeps evaluating directly.
+  // evaluates the step directly (evaluate_now) with the proxy's cell of now, on this and every
+  // later step (a cell that has moved once belongs to a barostat), until the scheduler builds
+  // its graphs again (colvarmodule_gpu_calc::init) and add_calc_value_node captures afresh.
+  // The same switch serves a queue overflow of a captured evaluation: evaluate_now grows the
+  // queue, the captured kernels -- they hold the old address -- stay off.
   double frozen_cell[12] = {0};     // periodic flags + unit cell the captured graph was built with
   std::atomic<int> launch_skipped{0};
-  bool dynamic_cell = false;        // the cell changes every step: the graph's nodes stay switched off
-  long long last_cell_change = -10;
+  bool dynamic_cell = false;        // the cell has moved: the graph's nodes stay switched off
+  bool graph_stale = false;         // a queue was re-allocated: likewise
   int fake_overflow_step = -1;      // B200CV_SHIM_FAKE_OVERFLOW_STEP: exercise the recovery path
   void current_cell(double out[12]);
   static void CUDART_CB cell_check(void *self);

@@ -234,11 +234,12 @@ int b200cv_get_tolerance_l2_max(const b200cv_cvc *h, double *l2_max);
 int b200cv_pairlist_count(b200cv_cvc *h, size_t *count);
 int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *h_indices, size_t capacity);
 /* How the current list is kept: form 0 = packed (i, j) entries as the all-pairs sweep compacts
- * them, 1 = entries in cell order (cell-list rebuild, periodic cells), 2 = masked 32 x 32
- * cluster tiles + a few entries (open systems, sparse lists), -1 = no rebuild yet; listed pairs,
- * of them as packed entries, tile units and tiles (pairs / (1024 tiles) is the tile fill). */
+ * them, 1 = entries in cell order (cell-list rebuild, periodic cells), 2 = neighbour rows + a
+ * few entries (open systems, sparse lists: every atom keeps all its partners, so a pair sits in
+ * two rows), -1 = no rebuild yet; listed pairs, of them as packed entries, entries of all rows,
+ * row chunks. */
 int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entries,
-                          size_t *tile_units, size_t *tiles);
+                          size_t *row_entries, size_t *row_chunks);
 /* Counters of the last calc_value: kernels launched, pairs sent to the exact
  * (reference-order) path. */
 int b200cv_last_stats(b200cv_cvc *h, int *kernel_launches, size_t *exact_pairs);

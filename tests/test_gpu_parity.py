@@ -238,6 +238,41 @@ def test_pairlist_thresholds_are_decided_like_the_reference():
     assert abs(v - ov) <= 1e-12 * max(abs(ov), 1e-6)
 
 
+def test_nearly_orthogonal_cell_follows_the_reference():
+    """Cell vectors with off-diagonal terms below the reference's tolerance (1e-5,
+    src/colvars_system.h:120-140) keep the type "orthogonal" there: fractional coordinates are
+    rounded with the full vectors, the lattice combination subtracted with the full vectors, and
+    the neighbouring images are NOT searched.  Pairs at half a box length included."""
+    cb = _cb()
+    L = 20.0
+    rng = np.random.default_rng(31)
+    n1, n2 = 150, 600
+    proxy = (rng.random((n1 + n2, 3)) * 2.0 - 0.5) * L
+    # pairs exactly half a cell vector apart (the rounding decides the image)
+    proxy[n1:n1 + 20] = proxy[:20] + np.array([0.5 * L, 0.0, 0.0])
+    proxy[n1 + 20:n1 + 40] = proxy[20:40] + np.array([0.0, 0.55 * L, 0.0])
+    proxy = np.ascontiguousarray(proxy)
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    cell = ((1, 1, 1), (L, 4e-6, -3e-6), (2e-6, 1.1 * L, 5e-6), (-6e-6, 1e-6, 0.9 * L))
+    p = O.make_params((4.0,) * 3, boundaries=cell)
+    assert p.bc.type == O.BC_PBC_ORTHOGONAL
+    for kw in (dict(), dict(tolerance=0.01, pairlist_freq=2)):
+        cv = cb.CoordNum("coordNum", i1, i2, cutoff=4.0, **kw)
+        cv.set_boundaries(*cell)
+        pp = O.make_params((4.0,) * 3, 6, 12, kw.get("tolerance", 0.0), boundaries=cell)
+        pl = np.ones(n1 * n2, dtype=np.uint8) if kw else None
+        for step in range(3 if kw else 1):
+            v = cv.calc_host(proxy, step=step)
+            ov, og1, og2 = O.coordnum(pp, proxy[i1], proxy[i2], pairlist=pl, rebuild=step % 2 == 0)
+            close_val(v, ov)
+            close_arr(cv.gradients(1), og1)
+            close_arr(cv.gradients(2), og2)
+            if kw and step % 2 == 0:
+                assert np.array_equal(cv.pairlist(), np.flatnonzero(pl).astype(np.uint64))
+        cv.close()
+
+
 @pytest.mark.parametrize("bc", ["ortho", "triclinic", "mixed"])
 @pytest.mark.parametrize("kind", ["coordNum", "selfCoordNum"])
 def test_periodic_boundaries(bc, kind):
@@ -659,19 +694,16 @@ def test_duplicate_atoms_in_a_group_are_rejected():
                     np.array([5, 6], dtype=np.int32))
 
 
-@pytest.mark.parametrize("form", ["entries", "tiles", "rows"])
+@pytest.mark.parametrize("form", ["entries", "rows"])
 def test_captured_pairlist_overflow_is_an_error_not_a_truncation(form, monkeypatch):
     """A captured graph holds the list's address, so the list cannot grow under it: when a
     rebuild finds more pairs than were reserved, the step's value must come back as an error --
-    and reserving again on the new positions plus a re-capture must recover.  The tile form of
-    the list stores 32 x 32 masks per tile, so the same compression only fills its tiles: it has
-    to come out right without any error."""
+    and reserving again on the new positions plus a re-capture must recover.  Both sparse
+    forms: packed entries in cell order, neighbour rows."""
     import torch
     cb = _cb()
     if form == "entries":
-        monkeypatch.setenv("B200CV_NO_TILES", "1")
-    elif form == "tiles":
-        monkeypatch.setenv("B200CV_LIST_FORM", "tiles")
+        monkeypatch.setenv("B200CV_NO_ROWS", "1")
     rng = np.random.default_rng(9)
     n = 6000
     pos = rng.random((n, 3)) * 60.0
@@ -707,16 +739,14 @@ def test_captured_pairlist_overflow_is_an_error_not_a_truncation(form, monkeypat
     dense.eval(p1, None, cb.EF_GRADIENTS | cb.EF_USE_PAIRLIST | cb.EF_REBUILD_PAIRLIST, gd, None)
     vd = dense.value()
     assert len(dense.pairlist()) > (1 << 20)
-    if form != "tiles":
-        # rows keep two entries per pair: 27x the pairs do not fit either
-        with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
-            cv.value()
-        # recover: size the list on the positions of now, capture again
-        graph = capture()
-        cv.pairlist_set_rebuild(True)
-        g1.zero_()
-        graph.replay()
-        torch.cuda.synchronize()
+    with pytest.raises(cb.B200cvError, match="pair-list overflow in a captured evaluation"):
+        cv.value()
+    # recover: size the list on the positions of now, capture again
+    graph = capture()
+    cv.pairlist_set_rebuild(True)
+    g1.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
     close_val(cv.value(), vd, 1e-13)
     close_arr(g1.cpu().numpy(), gd.cpu().numpy(), 1e-13)
     assert np.array_equal(cv.pairlist(), dense.pairlist())
@@ -765,21 +795,19 @@ def test_handles_are_independent_across_host_threads():
     assert not errors, errors
 
 
-@pytest.mark.parametrize("form", ["rows", "tiles", "cells"])
+@pytest.mark.parametrize("form", ["rows", "cells"])
 @pytest.mark.parametrize("kind,aniso", [("selfCoordNum", False), ("coordNum", False),
                                         ("coordNum", True), ("selfCoordNum", True)])
 def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso, form, monkeypatch):
     """Once a rebuild has shown the list to be sparse (< 2 % of the pairs), later rebuilds only
     visit pairs in neighbouring cells; everything else is exactly zero in the reference as well
     (l2 > tolerance_l2_max returns before anything is evaluated), so value, gradients and list
-    must not change.  Three forms of the sparse list in an open system: neighbour rows
-    (csrc/rows.cu, the default), masked cluster tiles (csrc/tiles.cu) and packed entries in cell
-    order (csrc/cells.cu)."""
+    must not change.  Two forms of the sparse list in an open system: neighbour rows
+    (csrc/rows.cu, the default) and packed entries in cell order (csrc/cells.cu, what periodic
+    cells use)."""
     cb = _cb()
     if form == "cells":
-        monkeypatch.setenv("B200CV_NO_TILES", "1")
-    elif form == "tiles":
-        monkeypatch.setenv("B200CV_LIST_FORM", "tiles")
+        monkeypatch.setenv("B200CV_NO_ROWS", "1")
     rng = np.random.default_rng(77)
     n1, n2 = (3000, 0) if kind == "selfCoordNum" else (700, 5000)
     L = 70.0  # ~0.01 atoms / A^3: a few listed pairs per atom

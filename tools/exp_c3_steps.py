@@ -21,7 +21,6 @@ for step in range(nsteps):
     v = cv.value()
     if step % 10 == 0:
         st = cv.pairlist_stats()
-        fill = st["pairs"] / (1024.0 * st["tiles"]) if st["tiles"] else None
-        print(step, st, "tile fill", fill, "launches", cv.last_stats()[0], flush=True)
+        print(step, st, "launches", cv.last_stats()[0], flush=True)
     pos = synth.displace(pos, seed=1000 + step, sigma=0.05)
 print("value", v)

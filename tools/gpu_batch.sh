@@ -1,8 +1,13 @@
 #!/bin/bash
 # scratch: the GPU-box side of one gpurun call (edited per experiment)
 out=gpurun_out/$1; mkdir -p $out
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sparse or overflow or pairlist or fused or cell_list" > $out/parity.log 2>&1; tail -5 $out/parity.log
-python -m pytest tests/test_gpu_baseline_sizes.py -x -q -m gpu -k c3 > $out/c3.log 2>&1; tail -3 $out/c3.log
-python tools/exp_cells.py 50000 > $out/forms.txt 2>&1; cat $out/forms.txt
-ncu --set full --clock-control none --import-source on -k regex:row_walk -s 2 -c 1 -o $out/rowwalk_full python tools/exp_c3_steps.py 50000 14 > $out/ncu_full.log 2>&1; tail -2 $out/ncu_full.log
-ncu --set full --clock-control none --import-source on -k regex:row_build -c 1 -o $out/rowbuild_full python tools/exp_c3_steps.py 50000 12 > $out/ncu_full2.log 2>&1; tail -2 $out/ncu_full2.log
+for v in "" _m6u4 _m8u2; do echo "== variant $v"; B200CV_LIB=$PWD/colvars_b200/libb200cv$v.so python tools/exp_cells.py 50000 2>&1 | tail -3; done > $out/variants.txt 2>&1; cat $out/variants.txt
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_sizes.py -x -q -m gpu -k "sparse or overflow or pairlist or fused or cell_list or nearly or periodic or c3" > $out/parity.log 2>&1; tail -4 $out/parity.log
+python bench.py --no-e2e --no-cpu-baseline --no-parity --steps 5 --warmup 3 > $out/bench.json 2> $out/bench.err; tail -c 300 $out/bench.err; python - $out <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]+'/bench.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['roofline']['frac'])
+    for k,v in d.get('other_workloads',{}).items(): print(k, {a:v.get(a) for a in ('value','ms_per_step','calc_value_ms','graph_step_ms','roofline_frac','pairlist','error')})
+except Exception as e: print('bench parse failed', e)
+PY
