@@ -1063,8 +1063,7 @@ int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entri
     unsigned counts[8];
     CUDA_OK(h, cudaMemcpy(counts, h->sort.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
     chunks = (size_t)row_slots(h) / (size_t)h->world + counts[6];
-    // both directions of every pair that is kept in rows
-    rentries = 2 * (size_t)(h->pl_n - h->pl_entries);
+    rentries = (size_t)h->row_entries;
   }
   if (form) *form = !h->pl_valid ? -1 : (h->pl_rows ? 2 : (h->pl_sorted ? 1 : 0));
   if (pairs) *pairs = (size_t)h->pl_n;

@@ -663,9 +663,7 @@ int post_sync(b200cv_cvc *h, bool &redo)
 {
   redo = false;
   unsigned long long const rare_n = h->h_counters[0], pl_n = h->h_counters[1];
-  unsigned long long const units = h->h_counters[3];
-  // listed pairs kept in rows: selfCoordNum counts both directions of a pair
-  unsigned long long const row_pairs = h->h_counters[4] / (h->self() ? 2ull : 1ull);
+  unsigned long long const units = h->h_counters[3], row_pairs = h->h_counters[4];
   // gated (captured) evaluations: finalize_kernel reports the mode the finished launch ran in
   bool const rebuild = h->gated ? (h->h_counters[2] == 1)
                                 : (bool)(h->last_flags & B200CV_EF_REBUILD_PAIRLIST);
@@ -711,6 +709,7 @@ int post_sync(b200cv_cvc *h, bool &redo)
       redo = true;
     } else {
       h->pl_entries = pl_n;
+      h->row_entries = rows_built ? row_entries : 0ull;
       h->pl_n = pl_n + (rows_built ? row_pairs : 0ull);
       h->pl_valid = true;
     }

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       unsigned const ml = __ballot_sync(0xffffffffu, listed);
       if (listed) R[rlen + __popc(ml & lt)] = q;
       rlen += __popc(ml);
-      npairs += listed ? 1ull : 0ull;
+      npairs += (listed && (!A.self || q > p)) ? 1ull : 0ull;  // the canonical side counts the pair
       __syncwarp();
       if (rlen > ROW_BUF - 32) flush(false);
     };
@@ -308,7 +308,6 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
     // count belong to the rows of group1
     bool const counts = A.self || A.canonical != 0;
     A.partials[blockIdx.x] = A.self ? 0.5 * s : (counts ? s : 0.0);
-    // (selfCoordNum: entries, i.e. twice the pairs -- the host halves the total)
     if (np && counts) atomicAdd(reinterpret_cast<unsigned long long *>(A.counts + 4), np);
   }
 }

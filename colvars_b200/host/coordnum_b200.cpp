@@ -287,6 +287,7 @@ int coordnum_b200::create_engine(b200cv_config const &cfg_in)
     std::string err;
     int const jrc = join_shards(engine, env, err);
     if (jrc != COLVARS_OK) return cvmodule->error("Error: " + err + "\n", jrc);
+    sharded = true;
     cvmodule->log("b200cv: component \"" + name + "\" sharded, rank " + cvm::to_str(env.rank) +
                   " of " + cvm::to_str(env.world) + " on device " + cvm::to_str(env.device) + "\n");
   }
@@ -524,7 +525,8 @@ int coordnum_b200::add_calc_value_node(
     // The list cannot grow under a graph, so size it now on the positions the read_data graph
     // has just produced (src/colvar_gpu_calc.cpp:249-251 synchronises before this point).
     flags |= B200CV_EF_USE_PAIRLIST;
-    if (b200cv_pairlist_reserve(engine, b1.d_atoms_pos, p2, 2.0, capture_stream) != B200CV_OK) {
+    if (!sharded &&
+        b200cv_pairlist_reserve(engine, b1.d_atoms_pos, p2, 2.0, capture_stream) != B200CV_OK) {
       return b200_error(COLVARS_ERROR);
     }
   }
@@ -535,6 +537,9 @@ int coordnum_b200::add_calc_value_node(
     if (cudaLaunchHostFunc(capture_stream, &coordnum_b200::cell_check, this) != cudaSuccess) {
       return (int)B200CV_ERROR;
     }
+    // a sharded component keeps its collective out of the scheduler's graph: it is evaluated
+    // on the proxy's stream in calc_value_after_gpu (device-resident all the same)
+    if (sharded) return (int)B200CV_OK;
     return b200cv_eval_async(engine, b1.d_atoms_pos, p2, flags, nullptr, nullptr, capture_stream);
   });
   if (rc != COLVARS_OK) return b200_error(COLVARS_ERROR);
@@ -560,7 +565,7 @@ void CUDART_CB coordnum_b200::cell_check(void *self)
   c->current_cell(now);
   bool differs = false;
   for (int k = 0; k < 12; k++) differs = differs || (now[k] != c->frozen_cell[k]);
-  int const skip = (differs || c->dynamic_cell || c->graph_stale) ? 1 : 0;
+  int const skip = (differs || c->dynamic_cell || c->graph_stale || c->sharded) ? 1 : 0;
   b200cv_async_set_skip(c->engine, skip);
   c->launch_skipped.store(skip);
 }
@@ -612,7 +617,7 @@ int coordnum_b200::calc_value_after_gpu()
     }
     if (rc != B200CV_OK) return b200_error(rc);
   } else {
-    if (!dynamic_cell && !graph_stale) {
+    if (!dynamic_cell && !graph_stale && !sharded) {
       dynamic_cell = true;
       cvmodule->log("b200cv: " + name + ": the periodic cell has changed since the graph was "
                     "captured; evaluating outside the captured graph from now on\n");

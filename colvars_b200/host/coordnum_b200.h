@@ -64,6 +64,7 @@ protected:
   bool dummy2 = false;
   cvm::atom_pos dummy2_pos;  // as parsed from `dummyAtom`
   b200cv_cvc *engine = nullptr;
+  bool sharded = false;  // one rank of several (join_shards): group1 rows split, results all-reduced
 #if defined(COLVARS_CUDA)
   cudaStream_t capture_stream = nullptr;
   // A captured evaluation freezes the periodic cell (and the addresses of the engine's queues).

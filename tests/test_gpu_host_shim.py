@@ -159,7 +159,12 @@ def test_sharded_components_through_the_reference_host(case, route, tmp_path):
             [str(runner), "-c", f"{d.name}/test.in", "-t", "trajectory.xyz", "-o",
              f"{d.name}/test_out", "--force"], cwd=wd, env=env, stdout=subprocess.PIPE,
             stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+    try:
+        outs = [p.communicate(timeout=120)[0] for p in procs]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
     gold = R.GOLDEN / f"{case}_harmonic-fixed" / "AutoDiff"
     gtraj = np.loadtxt(gold / "test_out.colvars.traj", comments="#")
     for rank in range(2):
