@@ -25,9 +25,9 @@ BUG_ERROR = 1 << 3
 FILE_ERROR = 1 << 4
 MEMORY_ERROR = 1 << 5
 
-COORDNUM, SELFCOORDNUM, GROUPCOORD, DISTANCEINV = 0, 1, 2, 3
+COORDNUM, SELFCOORDNUM, GROUPCOORD, DISTANCEINV, DISTANCEPAIRS = 0, 1, 2, 3, 4
 KIND_BY_NAME = {"coordNum": COORDNUM, "selfCoordNum": SELFCOORDNUM, "groupCoord": GROUPCOORD,
-                "distanceInv": DISTANCEINV}
+                "distanceInv": DISTANCEINV, "distancePairs": DISTANCEPAIRS}
 
 EF_NULL = 0
 EF_GRADIENTS = 1
@@ -67,7 +67,7 @@ SYMBOLS = [
     "b200cv_set_group", "b200cv_set_fitting", "b200cv_set_boundaries", "b200cv_read_data",
     "b200cv_calc_value", "b200cv_step", "b200cv_calc_fit_gradients", "b200cv_value", "b200cv_apply_force",
     "b200cv_eval", "b200cv_eval_async", "b200cv_accumulate_gradients",
-    "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_async_set_skip", "b200cv_eval_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
+    "b200cv_pairlist_reserve", "b200cv_pairlist_set_rebuild", "b200cv_async_set_skip", "b200cv_eval_host", "b200cv_eval_pairs_host", "b200cv_distance_pairs_host", "b200cv_distance_pairs_force_host", "b200cv_calc_host", "b200cv_apply_force_host", "b200cv_get_positions",
     "b200cv_get_gradients", "b200cv_get_fit_gradients", "b200cv_get_centers",
     "b200cv_get_rotation", "b200cv_get_tolerance_l2_max", "b200cv_pairlist_count",
     "b200cv_pairlist_export", "b200cv_pairlist_stats", "b200cv_last_stats", "b200cv_kernel_launches", "b200cv_current_device", "b200cv_comm_unique_id",
@@ -109,6 +109,9 @@ def load():
     L.b200cv_pairlist_set_rebuild.argtypes = [H, C.c_int]
     L.b200cv_async_set_skip.argtypes = [H, C.c_int]
     L.b200cv_eval_host.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
+    L.b200cv_eval_pairs_host.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
+    L.b200cv_distance_pairs_host.argtypes = [H, _dp, _dp, _dp]
+    L.b200cv_distance_pairs_force_host.argtypes = [H, _dp, _dp, _dp]
     L.b200cv_calc_host.argtypes = [H, vp, sz, ll, C.c_int, _dp]
     L.b200cv_apply_force_host.argtypes = [H, C.c_double, vp, sz]
     L.b200cv_get_positions.argtypes = [H, C.c_int, _dp]
@@ -321,6 +324,29 @@ class CoordNum:
         self._check(self._L.b200cv_eval_host(self._h, _as_dp(pos1), _as_dp(pos2), int(flags),
                                              _as_dp(grad1), _as_dp(grad2), C.byref(v)))
         return v.value
+
+    def eval_pairs_host(self, pos1, pos2, flags=EF_GRADIENTS, grad1=None, grad2=None):
+        """Batch of single pairs (k, k); numpy SoA arrays (3, n); returns the sum."""
+        v = C.c_double()
+        self._check(self._L.b200cv_eval_pairs_host(self._h, _as_dp(pos1), _as_dp(pos2),
+                                                   int(flags), _as_dp(grad1), _as_dp(grad2),
+                                                   C.byref(v)))
+        return v.value
+
+    def distance_pairs_host(self, pos1, pos2):
+        """distancePairs value: numpy SoA (3, n) positions -> (n1 * n2,) distances."""
+        out = np.zeros(self.n1 * self.n2)
+        self._check(self._L.b200cv_distance_pairs_host(self._h, _as_dp(pos1), _as_dp(pos2),
+                                                       _as_dp(out)))
+        return out
+
+    def distance_pairs_force_host(self, force):
+        """Forces on the atoms of both groups for a force vector on the distances."""
+        f1, f2 = np.zeros(3 * self.n1), np.zeros(3 * self.n2)
+        force = np.ascontiguousarray(force, dtype=np.float64)
+        self._check(self._L.b200cv_distance_pairs_force_host(self._h, _as_dp(force), _as_dp(f1),
+                                                             _as_dp(f2)))
+        return f1.reshape(3, self.n1).T.copy(), f2.reshape(3, self.n2).T.copy()
 
     # -- host-buffer step (CPU proxy arrays, AoS) ---------------------------------------------
     def calc_host(self, proxy_pos_aos, step=0, gradients=True):

@@ -235,7 +235,15 @@ int b200cv_create(const b200cv_config *cfg, b200cv_cvc **out)
   if (!cfg || !out) return fail(nullptr, B200CV_BUG_ERROR, "null argument");
   *out = nullptr;
   b200cv_config c = *cfg;
-  if (c.kind < 0 || c.kind > 3) return fail(nullptr, B200CV_INPUT_ERROR, "unknown component kind");
+  if (c.kind < 0 || c.kind > 4) return fail(nullptr, B200CV_INPUT_ERROR, "unknown component kind");
+  if (c.kind == B200CV_DISTANCEPAIRS) {
+    // colvar::distance_pairs has no keywords beyond its groups
+    c.tolerance = 0.0;
+    c.group1_center_only = c.group2_center_only = 0;
+    c.exp_numer = 6;
+    c.exp_denom = 12;
+    c.cutoff3[0] = c.cutoff3[1] = c.cutoff3[2] = 1.0;
+  }
   if (c.kind == B200CV_DISTANCEINV) {
     // distance_inv::init (src/colvarcomp_distances.cpp:384-391)
     if (c.exp_numer % 2) {
@@ -352,6 +360,7 @@ int b200cv_destroy(b200cv_cvc *h)
   cellsort_free(h->sort);
   rows_free(h->rows);
   free_dev(h->d_stage_pos);
+  free_dev(h->d_pairs);
   if (h->h_value) cudaFreeHost(h->h_value);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_mode) cudaFreeHost(h->h_mode);
@@ -399,7 +408,8 @@ int b200cv_set_group(b200cv_cvc *h, int which, const int *proxy_index, const dou
   }
   // atom_group::overlap (src/colvaratoms.cpp:1096-1105), O(N) here
   Group &O = h->g[2 - which];
-  if (!h->self() && !O.h_index.empty()) {
+  // (colvar::distance_pairs does not mind atoms common to both groups)
+  if (!h->self() && h->cfg.kind != B200CV_DISTANCEPAIRS && !O.h_index.empty()) {
     std::unordered_set<int> seen(O.h_index.begin(), O.h_index.end());
     for (int i = 0; i < n; i++) {
       if (seen.count(proxy_index[i])) {

@@ -133,6 +133,10 @@ struct b200cv_cvc {
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
 
+  // distancePairs: the n1 x n2 matrix of distances (or of force components) on the device
+  double *d_pairs = nullptr;
+  size_t pairs_cap = 0;
+
   // host staging (calc_host / apply_force_host)
   double *d_stage_pos = nullptr;
   size_t stage_n = 0;

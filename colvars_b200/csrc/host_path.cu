@@ -66,6 +66,175 @@ int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, 
   return B200CV_OK;
 }
 
+// A batch of independent single pairs: pair k = (atom k of group1, atom k of group2), k < n1 = n2.
+// What colvar::alpha_angles asks of its hydrogen-bond terms (src/colvarcomp_protein.cpp:153-166,
+// :213-231): every term is one compute_pair_coordnum, and the component needs their sum (all
+// terms carry the same weight) and, per atom, the gradient.  One launch of exact_kernel -- the
+// reference's operation order for every pair, there are only a handful -- over the entries (k, k).
+int b200cv_eval_pairs_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2, int flags,
+                           double *h_grad1, double *h_grad2, double *value_sum)
+{
+  if (!h || !value_sum || !h_pos1 || !h_pos2) return B200CV_BUG_ERROR;
+  if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
+  if (h->cfg.kind != B200CV_COORDNUM || h->g[0].n != h->g[1].n || h->center1() || h->center2() ||
+      h->cfg.tolerance > 0 || h->world > 1) {
+    return fail(h, B200CV_INPUT_ERROR,
+                "a pair batch needs a coordNum handle with n1 == n2, no centre-only group, no "
+                "pair list and no sharding");
+  }
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->own_stream;
+  if (h->unchecked) CUDA_OK_RC(sync_and_check(h));
+  int const n = h->g[0].n;
+  CUDA_OK_RC(ensure_rare_capacity(h, (unsigned long long)n));
+  CUDA_OK_RC(ensure_partials(h, PARTIALS_TAIL));
+  int rc = reset_gradients(h, s);
+  if (rc) return rc;
+  const double *hp[2] = {h_pos1, h_pos2};
+  for (int k = 0; k < 2; k++) {
+    Group &G = h->g[k];
+    CUDA_OK(h, cudaMemcpy2DAsync(G.d_pos, sizeof(double) * G.stride, hp[k], sizeof(double) * G.n,
+                                 sizeof(double) * G.n, 3, cudaMemcpyHostToDevice, s));
+  }
+  flags &= B200CV_EF_GRADIENTS;
+  CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, 16, s));
+  CUDA_OK(h, launch_fill_diagonal(h->d_rare, h->rare_count(), n, s));
+  Group &G1 = h->g[0], &G2 = h->g[1];
+  ExactArgs E{};
+  E.x1 = G1.d_pos; E.y1 = G1.d_pos + G1.stride; E.z1 = G1.d_pos + 2 * G1.stride;
+  E.x2 = G2.d_pos; E.y2 = G2.d_pos + G2.stride; E.z2 = G2.d_pos + 2 * G2.stride;
+  E.g1x = G1.d_grad; E.g1y = G1.d_grad + G1.stride; E.g1z = G1.d_grad + 2 * G1.stride;
+  E.g2x = G2.d_grad; E.g2y = G2.d_grad + G2.stride; E.g2z = G2.d_grad + 2 * G2.stride;
+  E.list = h->d_rare;
+  E.count32 = h->rare_count();
+  E.cap = h->rare_cap;
+  E.partials = h->d_partials;
+  E.flags = flags;
+  E.fin_ticket = h->fin_ticket();
+  E.fin = FinalizeArgs{};
+  E.fin.partials = h->d_partials;
+  E.fin.n = EXACT_BLOCKS;
+  E.fin.d_value = h->d_value;
+  E.fin.h_value = h->h_value_dev;
+  E.P = h->P;
+  CUDA_OK(h, launch_exact(E, s));
+  CUDA_OK(h, cudaStreamSynchronize(s));
+  h->launches = 2;
+  h->last_stream = s;
+  h->last_flags = flags;
+  h->have_calc = true;
+  h->data_read = true;
+  h->async_eval = h->gated = h->unchecked = false;
+  *value_sum = *h->h_value;
+  if (flags & B200CV_EF_GRADIENTS) {
+    double *hg[2] = {h_grad1, h_grad2};
+    if (h->h_stage_count < h->reduce_count) {
+      if (h->h_stage_grad) cudaFreeHost(h->h_stage_grad);
+      h->h_stage_grad = nullptr;
+      CUDA_OK(h, cudaHostAlloc(&h->h_stage_grad, sizeof(double) * h->reduce_count,
+                               cudaHostAllocDefault));
+      h->h_stage_count = h->reduce_count;
+    }
+    CUDA_OK(h, cudaMemcpyAsync(h->h_stage_grad, h->d_reduce, sizeof(double) * h->reduce_count,
+                               cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    for (int k = 0; k < 2; k++) {
+      if (!hg[k]) continue;
+      Group &G = h->g[k];
+      const double *g = h->h_stage_grad + (G.d_grad - h->d_reduce);
+      for (int d = 0; d < 3; d++) {
+        for (int i = 0; i < G.n; i++) hg[k][(size_t)d * G.n + i] += g[(size_t)d * G.stride + i];
+      }
+    }
+  }
+  return B200CV_OK;
+}
+
+// ---- distancePairs (src/colvarcomp_distances.cpp:486-548) ---------------------------------------
+// The value is the whole matrix of distances, so the staging buffer d_pairs holds n1 * n2
+// doubles (and the force matrix on the way back).
+
+static int distance_pairs_common(b200cv_cvc *h, const double *h_pos1, const double *h_pos2)
+{
+  if (!groups_ready(h)) return fail(h, B200CV_INPUT_ERROR, "atom groups are not defined");
+  if (h->cfg.kind != B200CV_DISTANCEPAIRS) {
+    return fail(h, B200CV_INPUT_ERROR, "not a distancePairs handle");
+  }
+  CUDA_OK(h, cudaSetDevice(h->cfg.device));
+  size_t const total = (size_t)h->g[0].n * (size_t)h->g[1].n;
+  if (h->pairs_cap < total) {
+    free_dev(h->d_pairs);
+    CUDA_OK(h, cudaMalloc(&h->d_pairs, sizeof(double) * total));
+    h->pairs_cap = total;
+  }
+  if (h_pos1 && h_pos2) {
+    const double *hp[2] = {h_pos1, h_pos2};
+    for (int k = 0; k < 2; k++) {
+      Group &G = h->g[k];
+      CUDA_OK(h, cudaMemcpy2DAsync(G.d_pos, sizeof(double) * G.stride, hp[k], sizeof(double) * G.n,
+                                   sizeof(double) * G.n, 3, cudaMemcpyHostToDevice, h->own_stream));
+    }
+    h->data_read = true;
+  }
+  return B200CV_OK;
+}
+
+static DistPairsArgs distance_pairs_args(b200cv_cvc *h)
+{
+  Group &G1 = h->g[0], &G2 = h->g[1];
+  DistPairsArgs A{};
+  A.x1 = G1.d_pos; A.y1 = G1.d_pos + G1.stride; A.z1 = G1.d_pos + 2 * G1.stride;
+  A.x2 = G2.d_pos; A.y2 = G2.d_pos + G2.stride; A.z2 = G2.d_pos + 2 * G2.stride;
+  A.n1 = G1.n;
+  A.n2 = G2.n;
+  A.f1x = G1.d_grad; A.f1y = G1.d_grad + G1.stride; A.f1z = G1.d_grad + 2 * G1.stride;
+  A.f2x = G2.d_grad; A.f2y = G2.d_grad + G2.stride; A.f2z = G2.d_grad + 2 * G2.stride;
+  A.P = h->P;
+  return A;
+}
+
+int b200cv_distance_pairs_host(b200cv_cvc *h, const double *h_pos1, const double *h_pos2,
+                               double *h_dist)
+{
+  if (!h || !h_pos1 || !h_pos2 || !h_dist) return B200CV_BUG_ERROR;
+  CUDA_OK_RC(distance_pairs_common(h, h_pos1, h_pos2));
+  cudaStream_t s = h->own_stream;
+  DistPairsArgs A = distance_pairs_args(h);
+  A.dist = h->d_pairs;
+  A.force = nullptr;
+  CUDA_OK(h, launch_distance_pairs(A, s));
+  CUDA_OK(h, cudaMemcpyAsync(h_dist, h->d_pairs, sizeof(double) * (size_t)A.n1 * (size_t)A.n2,
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_OK(h, cudaStreamSynchronize(s));
+  h->launches = 1;
+  return B200CV_OK;
+}
+
+int b200cv_distance_pairs_force_host(b200cv_cvc *h, const double *h_force, double *h_f1,
+                                     double *h_f2)
+{
+  if (!h || !h_force || !h_f1 || !h_f2) return B200CV_BUG_ERROR;
+  if (!h->data_read) return fail(h, B200CV_BUG_ERROR, "distance_pairs force before its value");
+  CUDA_OK_RC(distance_pairs_common(h, nullptr, nullptr));
+  cudaStream_t s = h->own_stream;
+  DistPairsArgs A = distance_pairs_args(h);
+  size_t const total = (size_t)A.n1 * (size_t)A.n2;
+  CUDA_OK_RC(reset_gradients(h, s));
+  CUDA_OK(h, cudaMemcpyAsync(h->d_pairs, h_force, sizeof(double) * total, cudaMemcpyHostToDevice, s));
+  A.dist = nullptr;
+  A.force = h->d_pairs;
+  CUDA_OK(h, launch_distance_pairs(A, s));
+  double *out[2] = {h_f1, h_f2};
+  for (int k = 0; k < 2; k++) {
+    Group &G = h->g[k];
+    CUDA_OK(h, cudaMemcpy2DAsync(out[k], sizeof(double) * G.n, G.d_grad, sizeof(double) * G.stride,
+                                 sizeof(double) * G.n, 3, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_OK(h, cudaStreamSynchronize(s));
+  h->launches = 1;
+  return B200CV_OK;
+}
+
 // ---- host-buffer step --------------------------------------------------------------------------
 // Sharded runs (b200cv_comm_init): every rank passes the same proxy array, as the ranks of a
 // replicated-data engine hold it.  Each rank uploads 1/world of it over its own PCIe link and the

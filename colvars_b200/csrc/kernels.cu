@@ -232,6 +232,21 @@ int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks)
   return (int)cudaGetLastError();
 }
 
+// entries (k, k), k < n, and their count: a batch of independent single pairs for exact_kernel
+__global__ void fill_diagonal_kernel(unsigned long long *list, unsigned int *count, int n)
+{
+  int const k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) list[k] = ((unsigned long long)(unsigned)k << 32) | (unsigned long long)(unsigned)k;
+  if (k == 0) *count = (unsigned)n;
+}
+
+int launch_fill_diagonal(unsigned long long *list, unsigned int *count, int n, cudaStream_t stream)
+{
+  fill_diagonal_kernel<<<(n + 255) / 256, 256, 0, stream>>>(list, count, n);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
 // ============================ dense fallback ==================================================
 
 __global__ void __launch_bounds__(EXACT_THREADS) dense_kernel(const __grid_constant__ DenseArgs A)
@@ -275,6 +290,58 @@ __global__ void __launch_bounds__(EXACT_THREADS) dense_kernel(const __grid_const
 int launch_dense(const DenseArgs &args, cudaStream_t stream)
 {
   dense_kernel<<<EXACT_BLOCKS, EXACT_THREADS, 0, stream>>>(args);
+  note_launch();
+  return (int)cudaGetLastError();
+}
+
+// ============================ distancePairs ====================================================
+// colvar::distance_pairs (src/colvarcomp_distances.cpp:486-548): no reduction at all -- the
+// value IS the N1 x N2 matrix of distances, the force of pair (i, j) its force component times
+// the unit vector.  One thread per pair, reference operation order (position_distance,
+// rvector::norm / unit, src/colvartypes.h:837-841); HBM-bound: 8 B written per pair.
+__device__ __forceinline__ double pair_distance_exact(PairParams const &P, double x1, double y1,
+                                                      double z1, double x2, double y2, double z2,
+                                                      double &dx, double &dy, double &dz)
+{
+  position_distance_exact(P, x1, y1, z1, x2, y2, z2, dx, dy, dz);
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+__global__ void __launch_bounds__(256) distance_pairs_kernel(const __grid_constant__ DistPairsArgs A)
+{
+  size_t const total = (size_t)A.n1 * (size_t)A.n2;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    int const i = (int)(e / (size_t)A.n2), j = (int)(e % (size_t)A.n2);
+    double dx, dy, dz;
+    double const d = pair_distance_exact(A.P, A.x1[i], A.y1[i], A.z1[i], A.x2[j], A.y2[j], A.z2[j],
+                                         dx, dy, dz);
+    if (A.force == nullptr) {
+      A.dist[e] = d;
+    } else {
+      // f2 = force_ij * dv.unit(); group1 atom gets -f2, group2 atom +f2
+      double const f = A.force[e];
+      double ux = 1.0, uy = 0.0, uz = 0.0;
+      if (d > 0.0) {
+        ux = __ddiv_rn(dx, d);
+        uy = __ddiv_rn(dy, d);
+        uz = __ddiv_rn(dz, d);
+      }
+      double const fx = __dmul_rn(f, ux), fy = __dmul_rn(f, uy), fz = __dmul_rn(f, uz);
+      atomicAdd(&A.f1x[i], -fx);
+      atomicAdd(&A.f1y[i], -fy);
+      atomicAdd(&A.f1z[i], -fz);
+      atomicAdd(&A.f2x[j], fx);
+      atomicAdd(&A.f2y[j], fy);
+      atomicAdd(&A.f2z[j], fz);
+    }
+  }
+}
+
+int launch_distance_pairs(const DistPairsArgs &args, cudaStream_t stream)
+{
+  size_t const total = (size_t)args.n1 * (size_t)args.n2;
+  int const blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  distance_pairs_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(args);
   note_launch();
   return (int)cudaGetLastError();
 }

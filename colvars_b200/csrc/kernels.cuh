@@ -100,6 +100,8 @@ constexpr int WALK_BLOCKS = 1184;
 // [row build (| rows of group2) | its exact queue | row walk | its exact lists]
 constexpr int PARTIALS_TAIL = 6144;
 int launch_exact(const ExactArgs &args, cudaStream_t stream, int blocks = EXACT_BLOCKS);
+// list[k] = (k, k) for k < n, *count = n: a batch of independent single pairs for exact_kernel
+int launch_fill_diagonal(unsigned long long *list, unsigned int *count, int n, cudaStream_t stream);
 
 // Dense fallback for boundary conditions the tile sweep does not specialise (mixed /
 // triclinic): every pair through pair_exact, gradients by atomics.  self: i < j only.
@@ -139,6 +141,20 @@ struct CenterArgs {
   PairParams P;
 };
 int launch_center(const CenterArgs &args, cudaStream_t stream);
+
+// colvar::distance_pairs: dist[i * n2 + j] = |position_distance(p1_i, p2_j)| (force == NULL), or
+// the forces f1_i -= force_ij * unit, f2_j += force_ij * unit accumulated into the f planes
+struct DistPairsArgs {
+  const double *x1, *y1, *z1;
+  const double *x2, *y2, *z2;
+  int n1, n2;
+  double *dist;         // [n1 * n2]
+  const double *force;  // [n1 * n2] or NULL
+  double *f1x, *f1y, *f1z;
+  double *f2x, *f2y, *f2z;
+  PairParams P;
+};
+int launch_distance_pairs(const DistPairsArgs &args, cudaStream_t stream);
 
 int launch_finalize(const FinalizeArgs &args, cudaStream_t stream);
 

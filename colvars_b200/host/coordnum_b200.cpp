@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "colvaratoms.h"
+#include "colvarcomp_coordnums.h"
 #include "colvarproxy.h"
 #include "colvars_system.h"
 
@@ -51,6 +52,8 @@ struct component_registry : public colvar {
     global_cvc_map["groupCoord"] = []() -> colvar::cvc * { return new groupcoordnum_b200(); };
     global_cvc_map["distanceInv"] = []() -> colvar::cvc * { return new distanceinv_b200(); };
     global_cvc_map["hBond"] = []() -> colvar::cvc * { return new hbond_b200(); };
+    global_cvc_map["alpha"] = []() -> colvar::cvc * { return new alpha_b200(); };
+    global_cvc_map["distancePairs"] = []() -> colvar::cvc * { return new distancepairs_b200(); };
   }
 };
 
@@ -429,6 +432,165 @@ void hbond_b200::evaluate(int flags)
 void hbond_b200::calc_value() { evaluate(B200CV_EF_NULL); }
 
 void hbond_b200::calc_gradients() { evaluate(B200CV_EF_GRADIENTS); }
+
+// ---- distancePairs (src/colvarcomp_distances.cpp:466-548) ----------------------------------------
+
+distancepairs_b200::~distancepairs_b200()
+{
+  if (engine) b200cv_destroy(engine);
+}
+
+int distancepairs_b200::init(std::string const &conf)
+{
+  int error_code = colvar::distance_pairs::init(conf);
+  if (error_code != COLVARS_OK || !group1 || !group2) return error_code;
+  b200cv_config cfg;
+  b200cv_config_defaults(&cfg);
+  cfg.kind = B200CV_DISTANCEPAIRS;
+  cfg.n1 = (int)group1->size();
+  cfg.n2 = (int)group2->size();
+  cfg.device = read_shard_env().device;
+  int rc = b200cv_create(&cfg, &engine);
+  if (rc != B200CV_OK) {
+    return cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
+  }
+  rc = set_engine_group(engine, 1, group1);
+  if (rc == B200CV_OK) rc = set_engine_group(engine, 2, group2);
+  if (rc != B200CV_OK) {
+    return cvmodule->error(std::string(b200cv_last_error(engine)) + "\n", rc);
+  }
+  return error_code;
+}
+
+void distancepairs_b200::calc_value()
+{
+  size_t const n = group1->size() * group2->size();
+  x.vector1d_value.resize(n);
+  static_cast<boundaries_view const &>(boundary_conditions).push(engine);
+  std::vector<double> d(n);
+  int const rc = b200cv_distance_pairs_host(engine, &group1->pos_x(0), &group2->pos_x(0), d.data());
+  if (rc != B200CV_OK) {
+    cvmodule->error(std::string(b200cv_last_error(engine)) + "\n", rc);
+    return;
+  }
+  for (size_t k = 0; k < n; k++) x.vector1d_value[k] = d[k];
+}
+
+void distancepairs_b200::apply_force(colvarvalue const &force)
+{
+  size_t const n1 = group1->size(), n2 = group2->size();
+  std::vector<double> f(n1 * n2), f1(3 * n1), f2(3 * n2);
+  for (size_t k = 0; k < n1 * n2; k++) f[k] = force[k];
+  int const rc = b200cv_distance_pairs_force_host(engine, f.data(), f1.data(), f2.data());
+  if (rc != B200CV_OK) {
+    cvmodule->error(std::string(b200cv_last_error(engine)) + "\n", rc);
+    return;
+  }
+  auto group1_force_obj = group1->get_group_force_object();
+  auto group2_force_obj = group2->get_group_force_object();
+  for (size_t i = 0; i < n1; i++) {
+    group1_force_obj.add_atom_force(i, cvm::rvector(f1[i], f1[n1 + i], f1[2 * n1 + i]));
+  }
+  for (size_t j = 0; j < n2; j++) {
+    group2_force_obj.add_atom_force(j, cvm::rvector(f2[j], f2[n2 + j], f2[2 * n2 + j]));
+  }
+}
+
+// ---- alpha (src/colvarcomp_protein.cpp:18-330) ---------------------------------------------------
+
+alpha_b200::~alpha_b200()
+{
+  if (engine) b200cv_destroy(engine);
+}
+
+int alpha_b200::init(std::string const &conf)
+{
+  // keywords, index groups / residue range, the angle and h_bond terms: the reference's own
+  int error_code = colvar::alpha_angles::init(conf);
+  if (error_code != COLVARS_OK || hb.empty()) return error_code;
+  // the h_bond terms as a batch: pair k = (acceptor of term k, donor of term k)
+  b200cv_config cfg;
+  b200cv_config_defaults(&cfg);
+  cfg.kind = B200CV_COORDNUM;
+  cfg.n1 = cfg.n2 = (int)hb.size();
+  cfg.cutoff3[0] = cfg.cutoff3[1] = cfg.cutoff3[2] = r0;
+  cfg.exp_numer = en;
+  cfg.exp_denom = ed;
+  cfg.device = read_shard_env().device;  // a handful of pairs: never sharded
+  int rc = b200cv_create(&cfg, &engine);
+  if (rc != B200CV_OK) {
+    return cvmodule->error(std::string(b200cv_last_error(nullptr)) + "\n", rc);
+  }
+  std::vector<int> acc(hb.size()), don(hb.size());
+  for (size_t k = 0; k < hb.size(); k++) {
+    acc[k] = hb[k]->atom_groups[0]->id(0);
+    don[k] = hb[k]->atom_groups[0]->id(1);
+  }
+  rc = b200cv_set_group(engine, 1, acc.data(), nullptr, (int)acc.size());
+  if (rc == B200CV_OK) rc = b200cv_set_group(engine, 2, don.data(), nullptr, (int)don.size());
+  if (rc != B200CV_OK) {
+    return cvmodule->error(std::string(b200cv_last_error(engine)) + "\n", rc);
+  }
+  return error_code;
+}
+
+// all hydrogen-bond terms in one call; with gradients they land in the terms' own atom groups
+// (atom 0 = acceptor gets -G, atom 1 = donor +G: src/colvarcomp_coordnums.cpp:447-469)
+int alpha_b200::evaluate_hbonds(int flags, double &sum)
+{
+  size_t const n = hb.size();
+  std::vector<double> p1(3 * n), p2(3 * n), g1(3 * n, 0.0), g2(3 * n, 0.0);
+  for (size_t k = 0; k < n; k++) {
+    cvm::atom_group const &g = *hb[k]->atom_groups[0];
+    p1[k] = g.pos_x(0); p1[n + k] = g.pos_y(0); p1[2 * n + k] = g.pos_z(0);
+    p2[k] = g.pos_x(1); p2[n + k] = g.pos_y(1); p2[2 * n + k] = g.pos_z(1);
+  }
+  int const rc = b200cv_eval_pairs_host(engine, p1.data(), p2.data(), flags, g1.data(),
+                                        g2.data(), &sum);
+  if (rc != B200CV_OK) {
+    return cvmodule->error(std::string(b200cv_last_error(engine)) + "\n", rc);
+  }
+  if (flags & B200CV_EF_GRADIENTS) {
+    for (size_t k = 0; k < n; k++) {
+      cvm::atom_group &g = *hb[k]->atom_groups[0];
+      g.grad_x(0) += g1[k]; g.grad_y(0) += g1[n + k]; g.grad_z(0) += g1[2 * n + k];
+      g.grad_x(1) += g2[k]; g.grad_y(1) += g2[n + k]; g.grad_z(1) += g2[2 * n + k];
+    }
+  }
+  return COLVARS_OK;
+}
+
+void alpha_b200::calc_value()
+{
+  x.real_value = 0.0;
+  // angle terms: the reference's objects and the reference's weighting
+  // (src/colvarcomp_protein.cpp:187-210)
+  if (theta.size()) {
+    cvm::real const theta_norm = (1.0 - hb_coeff) / cvm::real(theta.size());
+    for (size_t i = 0; i < theta.size(); i++) {
+      theta[i]->calc_value();
+      cvm::real const t = (theta[i]->value().real_value - theta_ref) / theta_tol;
+      cvm::real const f = (1.0 - (t * t)) / (1.0 - (t * t * t * t));
+      x.real_value += theta_norm * f;
+    }
+  }
+  // hydrogen-bond terms (:213-231): same weight for all, so their sum is all that is needed
+  if (hb.size() && engine) {
+    double sum = 0.0;
+    if (evaluate_hbonds(B200CV_EF_NULL, sum) == COLVARS_OK) {
+      x.real_value += (hb_coeff / cvm::real(hb.size())) * sum;
+    }
+  }
+}
+
+void alpha_b200::calc_gradients()
+{
+  for (size_t i = 0; i < theta.size(); i++) theta[i]->calc_gradients();
+  if (hb.size() && engine) {
+    double sum = 0.0;
+    evaluate_hbonds(B200CV_EF_GRADIENTS, sum);
+  }
+}
 
 void coordnum_b200::calc_value()
 {

@@ -131,4 +131,39 @@ private:
   void evaluate(int flags);
 };
 
+/// colvar::alpha_angles, "alpha" (src/colvarcomp.h:807-846, src/colvarcomp_protein.cpp:18-330):
+/// the Calpha-Calpha-Calpha angle terms stay the reference's own objects; the hydrogen-bond
+/// terms -- a vector of colvar::h_bond, i.e. one compute_pair_coordnum each -- are evaluated as
+/// ONE batch of single pairs behind the C ABI (b200cv_eval_pairs_host).  Keywords, index groups,
+/// collect_gradients and apply_force are the base class's: the batch writes its gradients into
+/// the h_bond terms' own atom groups, where the base class looks for them.
+class alpha_b200 : public colvar::alpha_angles {
+public:
+  alpha_b200() = default;
+  ~alpha_b200() override;
+  int init(std::string const &conf) override;
+  void calc_value();
+  void calc_gradients();
+
+private:
+  int evaluate_hbonds(int flags, double &sum);
+  b200cv_cvc *engine = nullptr;
+};
+
+/// Widening: colvar::distance_pairs, "distancePairs"
+/// (src/colvarcomp.h:561-584, src/colvarcomp_distances.cpp:466-548): the vector of all
+/// group1 x group2 distances, forces per pair.  Everything but calc_value and apply_force is the
+/// base class's.
+class distancepairs_b200 : public colvar::distance_pairs {
+public:
+  distancepairs_b200() = default;
+  ~distancepairs_b200() override;
+  int init(std::string const &conf) override;
+  void calc_value() override;
+  void apply_force(colvarvalue const &force) override;
+
+private:
+  b200cv_cvc *engine = nullptr;
+};
+
 #endif

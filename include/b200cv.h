@@ -69,6 +69,10 @@ extern "C" {
  * (sum / (N1 N2))^(-1/n).  exp_numer carries the keyword "exponent" (even, > 0, default 6);
  * cutoff3, exp_denom, tolerance and the *_center_only flags are ignored. */
 #define B200CV_DISTANCEINV 3
+/* widening: colvar::distance_pairs, "distancePairs" (src/colvarcomp_distances.cpp:486-548): the
+ * value is the vector of all N1 x N2 distances; only n1, n2 and the device are read from the
+ * config, and only b200cv_distance_pairs_host / _force_host evaluate it. */
+#define B200CV_DISTANCEPAIRS 4
 
 /* evaluation flags, same values as colvar::coordnum::ef_* (src/colvarcomp_coordnums.h:32-37) */
 #define B200CV_EF_NULL 0
@@ -205,6 +209,27 @@ int b200cv_accumulate_gradients(b200cv_cvc *h, double *d_grad1, double *d_grad2,
  * This is the entry the `colvar::cvc` shim of colvars_b200/host calls from calc_value(). */
 int b200cv_eval_host(b200cv_cvc *h, const double *h_pos1_soa, const double *h_pos2_soa,
                      int flags, double *h_grad1_soa, double *h_grad2_soa, double *value);
+
+/* A batch of independent single pairs on a coordNum handle with n1 == n2: pair k is (atom k of
+ * group1, atom k of group2).  *value_sum = sum over k of the switching function, gradients
+ * accumulate into h_grad1 / h_grad2 (SoA double[3*n], may be NULL).  This is the hydrogen-bond
+ * part of colvar::alpha_angles -- a vector of colvar::h_bond terms, each one
+ * compute_pair_coordnum, all with the same weight (src/colvarcomp_protein.cpp:153-166,
+ * :213-231) -- and any other batch of hBond-like terms.  Every pair is evaluated in the
+ * reference's operation order. */
+int b200cv_eval_pairs_host(b200cv_cvc *h, const double *h_pos1_soa, const double *h_pos2_soa,
+                           int flags, double *h_grad1_soa, double *h_grad2_soa,
+                           double *value_sum);
+
+/* colvar::distance_pairs::calc_value (src/colvarcomp_distances.cpp:486-517): group positions as
+ * SoA host arrays (atom_group::atoms_pos), h_dist[i1 * n2 + i2] = |position_distance(p1, p2)|.
+ * ... ::apply_force (:526-548): h_force[i1 * n2 + i2] is the force on that distance; the forces
+ * on the atoms of the two groups are WRITTEN to h_f1 / h_f2 (SoA double[3*n]), computed on the
+ * positions of the last b200cv_distance_pairs_host call. */
+int b200cv_distance_pairs_host(b200cv_cvc *h, const double *h_pos1_soa, const double *h_pos2_soa,
+                               double *h_dist);
+int b200cv_distance_pairs_force_host(b200cv_cvc *h, const double *h_force, double *h_f1_soa,
+                                     double *h_f2_soa);
 
 /* ---- host-buffer step (CPU proxy arrays; host<->device copies included) ---------------
  * h_proxy_pos: AoS rvector array double[3*n_proxy] (src/colvarproxy.h:275).

@@ -677,3 +677,40 @@ double cvo_distance_inv(const cvo_boundaries *bc, int exponent, size_t n1, const
   for (size_t k = 0; k < 3 * n2; k++) grad2[k] = grad2[k] * dxdsum;
   return value;
 }
+
+/* src/colvarcomp_distances.cpp:486-548 (colvar::distance_pairs): dist[i1*n2 + i2] =
+ * |position_distance(p1, p2)|; with force != NULL also the atom forces of apply_force,
+ * f2 = force_ij * dv.unit() (src/colvartypes.h:837-841), f1 -= f2, accumulated in loop order. */
+void cvo_distance_pairs(const cvo_boundaries *bc, size_t n1, const double *pos1, size_t n2,
+                        const double *pos2, double *dist, const double *force, double *f1,
+                        double *f2)
+{
+  for (size_t i1 = 0; i1 < n1; i1++) {
+    double const a1[3] = {pos1[i1], pos1[n1 + i1], pos1[2 * n1 + i1]};
+    double g1[3] = {0, 0, 0};
+    for (size_t i2 = 0; i2 < n2; i2++) {
+      double const a2[3] = {pos2[i2], pos2[n2 + i2], pos2[2 * n2 + i2]};
+      double dv[3];
+      cvo_position_distance(bc, a1, a2, dv);
+      double const d = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+      dist[i1 * n2 + i2] = d;
+      if (force) {
+        double u[3] = {1.0, 0.0, 0.0};
+        if (d > 0.0) {
+          u[0] = dv[0] / d;
+          u[1] = dv[1] / d;
+          u[2] = dv[2] / d;
+        }
+        for (int k = 0; k < 3; k++) {
+          double const f = force[i1 * n2 + i2] * u[k];
+          g1[k] += -f;
+          f2[k * n2 + i2] += f;
+        }
+      }
+    }
+    if (force) {
+      for (int k = 0; k < 3; k++) f1[k * n1 + i1] += g1[k];
+    }
+  }
+}
+

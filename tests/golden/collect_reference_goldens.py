@@ -23,8 +23,20 @@ CASES = [
 ]
 
 
+# cases whose directory is not <name>_harmonic-fixed: distancePairs,
+# a vector-valued component under a linear bias
+OTHER_DIRS = ["distancepairs_linear-distancepairs"]
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    for name in OTHER_DIRS:
+        d = OUT / name
+        (d / "AutoDiff").mkdir(parents=True, exist_ok=True)
+        shutil.copy(REF / name / "test.in", d / "test.in")
+        for g in sorted((REF / name / "AutoDiff").iterdir()):
+            if g.name.endswith(".colvars.traj") or "_forces_" in g.name:
+                shutil.copy(g, d / "AutoDiff" / g.name)
     for f in ("trajectory.xyz", "index.ndx"):
         shutil.copy(REF / f, OUT / f)
     for c in CASES:

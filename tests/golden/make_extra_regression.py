@@ -72,6 +72,22 @@ CASES = {
         group2 { indexGroup group2 }
     }
 """,
+    # colvar::alpha_angles (SURVEY.md section 8f rank 2): six hydrogen-bond terms O(i)-N(i+4) --
+    # the batch of single pairs -- next to eight Calpha angle terms, from the index groups
+    # prot_CA / prot_N / prot_O of the reference's index.ndx
+    "alpha": """    alpha {
+        prefix prot_
+        hBondCoeff 0.5
+    }
+""",
+    "alpha-hbonds-only": """    alpha {
+        prefix prot_
+        hBondCoeff 1.0
+        hBondCutoff 3.5
+        hBondExpNumer 4
+        hBondExpDenom 10
+    }
+""",
     "selfcoordnum-aniso-exp": """    selfCoordNum {
         debugGradients on
         cutoff3 (3.0, 6.0, 4.0)
@@ -98,7 +114,7 @@ def main():
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise SystemExit(f"{name}: reference failed\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
-        for junk in (d / "AutoDiff").glob("*.state"):
+        for junk in list((d / "AutoDiff").glob("*.state")) + list((d / "AutoDiff").glob("*.BAK")):
             junk.unlink()
         print(name, (d / "AutoDiff" / "test_out.colvars.traj").read_text().splitlines()[1])
 

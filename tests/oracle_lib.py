@@ -108,6 +108,9 @@ def lib():
                                              _dp, _dp]
     L.cvo_calc_fit_gradients.argtypes = [C.POINTER(FitState), C.c_size_t, _dp, _dp, C.c_size_t,
                                          _dp, _dp, _dp]
+    L.cvo_distance_pairs.argtypes = [C.POINTER(Boundaries), C.c_size_t, _dp, C.c_size_t, _dp, _dp,
+                                     _dp, _dp, _dp]
+    L.cvo_distance_pairs.restype = None
     _lib = L
     return L
 
@@ -262,3 +265,22 @@ def distance_inv(pos1, pos2, exponent=6, boundaries=None, omp=0):
     v = L.cvo_distance_inv(C.byref(p.bc), int(exponent), n1, _ptr(soa(pos1)), n2,
                            _ptr(soa(pos2)), _ptr(g1), _ptr(g2), int(omp))
     return v, unsoa(g1, n1), unsoa(g2, n2)
+
+
+def distance_pairs(pos1, pos2, force=None, boundaries=None):
+    """distance_pairs::calc_value / apply_force (src/colvarcomp_distances.cpp:486-548).  Returns
+    the distances (n1 * n2,) and, with a force vector, the forces (n1,3), (n2,3) on the atoms."""
+    L = lib()
+    p = make_params(boundaries=boundaries)
+    n1, n2 = len(pos1), len(pos2)
+    dist = np.zeros(n1 * n2)
+    if force is None:
+        L.cvo_distance_pairs(C.byref(p.bc), n1, _ptr(soa(pos1)), n2, _ptr(soa(pos2)), _ptr(dist),
+                             None, None, None)
+        return dist
+    f1, f2 = np.zeros(3 * n1), np.zeros(3 * n2)
+    force = np.ascontiguousarray(force, dtype=np.float64)
+    L.cvo_distance_pairs(C.byref(p.bc), n1, _ptr(soa(pos1)), n2, _ptr(soa(pos2)), _ptr(dist),
+                         _ptr(force), _ptr(f1), _ptr(f2))
+    return dist, unsoa(f1, n1), unsoa(f2, n2)
+

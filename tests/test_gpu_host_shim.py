@@ -90,8 +90,10 @@ def test_reference_host_with_b200_components(case, route, tmp_path):
         assert "atom-group kernels: b200" in r.stdout
         assert "optimal-rotation kernels: b200" in r.stdout
         on_graph = "graph route: yes" in r.stdout
-        # one acceptor-donor pair (hBond) and a dummy-atom group2 stay on the CPU-buffer route
-        assert on_graph == ("dummy" not in case and case != "hbond"), r.stdout[-500:]
+        # one acceptor-donor pair (hBond), the pair batch of alpha and a dummy-atom group2 stay
+        # on the CPU-buffer route
+        assert on_graph == ("dummy" not in case and case != "hbond" and
+                            not case.startswith("alpha")), r.stdout[-500:]
 
 
 @pytest.mark.parametrize("case", ["coordnum", "selfcoordnum-pairlist", "coordnum-aniso"])
@@ -255,3 +257,39 @@ def test_overflow_of_a_captured_evaluation_recovers_on_the_graph_route(case, tmp
         f = np.loadtxt(d / f"test_out_forces_{k}.dat")
         g = np.loadtxt(gold / f"test_out_forces_{k}.dat")
         assert f.shape == g.shape and _close(f, g), k
+
+
+@pytest.mark.parametrize("route", ["cpu-proxy", "smp-gpu"])
+def test_distance_pairs_through_the_reference_host(route, tmp_path):
+    """colvar::distance_pairs replaced by distancepairs_b200: the reference's own regression
+    input distancepairs_linear-distancepairs (a 16-component vector under a linear bias) and its
+    golden files, through the unmodified host on both routes."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    runner = RUNNER_GPU if route == "smp-gpu" else RUNNER
+    for f in ("trajectory.xyz", "index.ndx"):
+        shutil.copy(R.GOLDEN / f, tmp_path / f)
+    name = "distancepairs_linear-distancepairs"
+    d = tmp_path / name
+    d.mkdir()
+    shutil.copy(R.GOLDEN / name / "test.in", d / "test.in")
+    r = subprocess.run([str(runner), "-c", f"{name}/test.in", "-t", "trajectory.xyz", "-o",
+                        f"{name}/test_out", "--force"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    gold = R.GOLDEN / name / "AutoDiff"
+    import re
+    num = re.compile(r"[-+]?\d\.\d+e[-+]\d+")
+
+    def rows(path):
+        return np.array([[float(v) for v in num.findall(line)]
+                         for line in path.read_text().splitlines()
+                         if line.strip() and not line.startswith("#")])
+    traj, gtraj = rows(d / "test_out.colvars.traj"), rows(gold / "test_out.colvars.traj")
+    assert traj.shape == gtraj.shape == (5, 32) and _close(traj, gtraj)
+    for k in range(5):
+        f = np.loadtxt(d / f"test_out_forces_{k}.dat")
+        g = np.loadtxt(gold / f"test_out_forces_{k}.dat")
+        assert f.shape == g.shape and _close(f, g), k
+
