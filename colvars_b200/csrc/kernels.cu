@@ -496,56 +496,72 @@ int launch_distinv_post(const DistInvPostArgs &args, cudaStream_t stream)
 
 // ============================ atom-group kernels ================================================
 
-__global__ void gather_kernel(const double *__restrict__ proxy, size_t pstride, int aos,
-                              const int *__restrict__ idx, int n, double *__restrict__ pos,
-                              size_t stride)
+__global__ void __launch_bounds__(256) gather_kernel(const double *__restrict__ proxy,
+                                                     size_t pstride, int aos, GroupView g);
+
+// Four atoms per thread: one 128-bit index load, twelve coordinate loads in flight, and per plane
+// one 32-byte run of stores (the planes are padded to multiples of 32 atoms and 256-byte aligned,
+// alloc_group).  HBM-bound: 4 B index + 24 B in + 24 B out per atom.
+__device__ __forceinline__ void gather_four(const double *__restrict__ proxy, size_t pstride,
+                                            int aos, GroupView const &g, int q)
 {
-  int const i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  size_t const p = (size_t)idx[i];
-  if (aos) {
-    pos[i] = proxy[3 * p];
-    pos[stride + i] = proxy[3 * p + 1];
-    pos[2 * stride + i] = proxy[3 * p + 2];
+  int const i0 = 4 * q;
+  if (i0 >= g.n) return;
+  if (i0 + 4 <= g.n) {
+    int4 const p4 = __ldg(reinterpret_cast<const int4 *>(g.idx) + q);
+    size_t const p[4] = {(size_t)p4.x, (size_t)p4.y, (size_t)p4.z, (size_t)p4.w};
+    double v[3][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) v[d][a] = aos ? proxy[3 * p[a] + d] : proxy[d * pstride + p[a]];
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double2 *out = reinterpret_cast<double2 *>(g.data + d * g.stride + i0);
+      out[0] = make_double2(v[d][0], v[d][1]);
+      out[1] = make_double2(v[d][2], v[d][3]);
+    }
   } else {
-    pos[i] = proxy[p];
-    pos[stride + i] = proxy[pstride + p];
-    pos[2 * stride + i] = proxy[2 * pstride + p];
+    for (int i = i0; i < g.n; i++) {
+      size_t const p = (size_t)g.idx[i];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        g.data[d * g.stride + i] = aos ? proxy[3 * p + d] : proxy[d * pstride + p];
+      }
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const double *__restrict__ proxy,
+                                                     size_t pstride, int aos, GroupView g)
+{
+  gather_four(proxy, pstride, aos, g, (int)(blockIdx.x * blockDim.x + threadIdx.x));
 }
 
 int launch_gather(const double *proxy, size_t pstride, int aos, const int *idx, int n,
                   double *pos, size_t stride, cudaStream_t stream)
 {
   if (n <= 0) return 0;
-  gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(proxy, pstride, aos, idx, n, pos, stride);
+  GroupView const g{idx, n, pos, stride, nullptr};
+  gather_kernel<<<(n + 1023) / 1024, 256, 0, stream>>>(proxy, pstride, aos, g);
   note_launch();
   return (int)cudaGetLastError();
 }
 
-__global__ void gather2_kernel(const double *__restrict__ proxy, size_t pstride, int aos,
-                               GroupView a, GroupView b, int blocks_a)
+__global__ void __launch_bounds__(256) gather2_kernel(const double *__restrict__ proxy,
+                                                      size_t pstride, int aos, GroupView a,
+                                                      GroupView b, int blocks_a)
 {
   bool const first = (int)blockIdx.x < blocks_a;
-  GroupView const &g = first ? a : b;
-  int const i = ((int)blockIdx.x - (first ? 0 : blocks_a)) * (int)blockDim.x + (int)threadIdx.x;
-  if (i >= g.n) return;
-  size_t const p = (size_t)g.idx[i];
-  if (aos) {
-    g.data[i] = proxy[3 * p];
-    g.data[g.stride + i] = proxy[3 * p + 1];
-    g.data[2 * g.stride + i] = proxy[3 * p + 2];
-  } else {
-    g.data[i] = proxy[p];
-    g.data[g.stride + i] = proxy[pstride + p];
-    g.data[2 * g.stride + i] = proxy[2 * pstride + p];
-  }
+  int const q = ((int)blockIdx.x - (first ? 0 : blocks_a)) * (int)blockDim.x + (int)threadIdx.x;
+  gather_four(proxy, pstride, aos, first ? a : b, q);
 }
 
 int launch_gather2(const double *proxy, size_t pstride, int aos, const GroupView &a,
                    const GroupView &b, cudaStream_t stream)
 {
-  int const ba = (a.n + 255) / 256, bb = (b.n + 255) / 256;
+  int const ba = (a.n + 1023) / 1024, bb = (b.n + 1023) / 1024;
   if (ba + bb <= 0) return 0;
   gather2_kernel<<<ba + bb, 256, 0, stream>>>(proxy, pstride, aos, a, b, ba);
   note_launch();
