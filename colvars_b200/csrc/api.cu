@@ -800,7 +800,8 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
   }
   if (rows_usable(h) && sparse_list(h)) {
     // the row form: two entries per listed pair, one chunk per atom and per ROW_BUF entries
-    double const ent = headroom * 2.0 * (double)h->pl_n + 65536.0;
+    // (every chunk padded to a multiple of 32 entries)
+    double const ent = headroom * 2.0 * (double)h->pl_n + 32.0 * (double)row_slots(h) + 65536.0;
     double const chk = (double)row_slots(h) + headroom * ent / ROW_BUF + 4096.0;
     if ((unsigned)std::min(4.0e9, ent) > h->rows.cap_idx ||
         (unsigned)std::min(4.0e9, chk) > h->rows.cap_chunks) {
@@ -1015,6 +1016,7 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
       if (len <= 0 || (size_t)start + (size_t)len > used) continue;
       for (int e = start; e < start + len; e++) {
         int const q = idx[(size_t)e];
+        if (q >= J.n) continue;        // padding (the far-away point, cellsort.cuh)
         if (self && q <= p) continue;  // listed from the other atom's row
         if (k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent row list");
         out[k++] = canonical((unsigned long long)oi[(size_t)p], (unsigned long long)oj[(size_t)q]);

@@ -120,7 +120,7 @@ unsigned row_slots(const b200cv_cvc *h)
 static void row_estimate(const b200cv_cvc *h, unsigned &entries, unsigned &chunks)
 {
   unsigned long long const atoms = (unsigned long long)h->g[0].n + (h->self() ? 0ull : (unsigned long long)h->g[1].n);
-  unsigned long long const e = 2ull * h->pl_n + h->pl_n / 2ull + 65536ull;
+  unsigned long long const e = 2ull * h->pl_n + h->pl_n / 2ull + 32ull * atoms + 65536ull;  // chunks are padded to 32
   unsigned long long const c = atoms + e / (unsigned long long)ROW_BUF + 4096ull;
   entries = (unsigned)std::min<unsigned long long>(e, 0xfffffff0ull);
   chunks = (unsigned)std::min<unsigned long long>(c, 0xfffffff0ull);
@@ -417,7 +417,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       bool const periodic = cell_list_frac(h, frac);
       CUDA_OK(h, cells_build(h->cells, x2, y2, z2, G2.n, cut, periodic ? frac : nullptr, gate,
                              stream));
-      h->launches += 5;
+      h->launches += 3 + keysort_launches(h->cells.sort);  // grid, keys, sort, gather
       CellPairArgs C{};
       C.x1 = x1; C.y1 = y1; C.z1 = z1; C.x2 = x2; C.y2 = y2; C.z2 = z2;
       C.g1x = g1x; C.g1y = g1y; C.g1z = g1z; C.g2x = g2x; C.g2y = g2y; C.g2z = g2z;
@@ -493,7 +493,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
                                   int &nparts) -> int {
       CellSort &B = h->sort;
       CUDA_OK(h, cellsort_build(B, x1, y1, z1, x2, y2, z2, gate, stream));
-      h->launches += h->self() ? 5 : 8;
+      // bounding box, grid; keys and sort per group
+      h->launches += 2 + (h->self() ? 1 : 2) * (1 + keysort_launches(B.side[1].sort));
       CUDA_OK(h, cellsort_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
       h->launches++;
       RowSideView s1, s2;

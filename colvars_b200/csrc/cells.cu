@@ -5,7 +5,6 @@
 #include <algorithm>
 #include <cmath>
 
-#include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
 
@@ -103,12 +102,11 @@ __device__ __forceinline__ int cell_coord_periodic(CellGrid const &g, int a, dou
 
 __global__ void cell_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                 const double *__restrict__ z, int n,
-                                const CellGrid *__restrict__ grid, int *key, int *val,
-                                const int *gate)
+                                const CellGrid *__restrict__ grid, int *key, const int *gate)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (gate != nullptr && *gate != 1) return;  // keys of the last rebuild stay: still sortable
+  if (gate != nullptr && *gate != 1) return;
   CellGrid const g = *grid;
   int cx, cy, cz;
   if (g.periodic) {
@@ -121,25 +119,8 @@ __global__ void cell_key_kernel(const double *__restrict__ x, const double *__re
     cz = min(max(cell_coord(z[i], g.origin[2], g.inv_cell[2], g.dim[2]), 0), g.dim[2] - 1);
   }
   key[i] = (cz * g.dim[1] + cy) * g.dim[0] + cx;
-  val[i] = i;
 }
 
-// cell_start[c] = first position of the sorted keys with key >= c, for c in [0, ncells]
-__global__ void cell_start_kernel(const int *__restrict__ key_sorted, int n,
-                                  const CellGrid *__restrict__ grid, int *cell_start,
-                                  const int *gate)
-{
-  int const c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gate != nullptr && *gate != 1) return;
-  if (c > grid->ncells) return;
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int const mid = (lo + hi) >> 1;
-    if (key_sorted[mid] < c) lo = mid + 1;
-    else hi = mid;
-  }
-  cell_start[c] = lo;
-}
 
 // coordinates in cell order: the pair kernel's candidate loads become contiguous
 __global__ void cell_gather_kernel(const double *__restrict__ x, const double *__restrict__ y,
@@ -362,9 +343,8 @@ int cells_setup(CellBuffers &B, int n2)
   if ((e = cudaMalloc(&B.d_grid, sizeof(CellGrid))) != cudaSuccess) return (int)e;
   size_t const nb = sizeof(int) * (size_t)std::max(n2, 1);
   if ((e = cudaMalloc(&B.d_key, nb)) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&B.d_key_sorted, nb)) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&B.d_val, nb)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_sorted, nb)) != cudaSuccess) return (int)e;
+  if (int const rc = keysort_setup(B.sort, n2, CELL_MAX)) return rc;
   size_t const nbd = sizeof(double) * (size_t)std::max(n2, 1);
   if ((e = cudaMalloc(&B.d_xs, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&B.d_ys, nbd)) != cudaSuccess) return (int)e;
@@ -373,11 +353,6 @@ int cells_setup(CellBuffers &B, int n2)
   if ((e = cudaMalloc(&B.d_cell_start, sizeof(int) * ((size_t)CELL_MAX + 2))) != cudaSuccess) {
     return (int)e;
   }
-  B.temp_bytes = 0;
-  e = cub::DeviceRadixSort::SortPairs(nullptr, B.temp_bytes, B.d_key, B.d_key_sorted, B.d_val,
-                                      B.d_sorted, n2, 0, 22);
-  if (e != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&B.d_temp, std::max<size_t>(B.temp_bytes, 16))) != cudaSuccess) return (int)e;
   return 0;
 }
 
@@ -385,15 +360,13 @@ void cells_free(CellBuffers &B)
 {
   cudaFree(B.d_grid);
   cudaFree(B.d_key);
-  cudaFree(B.d_key_sorted);
-  cudaFree(B.d_val);
   cudaFree(B.d_sorted);
+  keysort_free(B.sort);
   cudaFree(B.d_xs);
   cudaFree(B.d_ys);
   cudaFree(B.d_zs);
   cudaFree(B.d_gs);
   cudaFree(B.d_cell_start);
-  cudaFree(B.d_temp);
   B = CellBuffers();
 }
 
@@ -438,17 +411,9 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
                                                 gate);
   }
   note_launch();
-  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, B.d_val,
-                                                        gate);
+  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, gate);
   note_launch();
-  size_t bytes = B.temp_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(B.d_temp, bytes, B.d_key, B.d_key_sorted,
-                                                  B.d_val, B.d_sorted, n2, 0, 22, stream);
-  if (e != cudaSuccess) return (int)e;
-  note_launch();
-  cell_start_kernel<<<(CELL_MAX + 1 + 255) / 256, 256, 0, stream>>>(B.d_key_sorted, n2, B.d_grid,
-                                                                   B.d_cell_start, gate);
-  note_launch();
+  if (int const rc = keysort_run(B.sort, B.d_key, 0, B.d_sorted, B.d_cell_start, gate, stream)) return rc;
   return launch_cell_gather(B, x2, y2, z2, n2, gate, 1, stream);
 }
 

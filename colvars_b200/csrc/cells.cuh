@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "pair_math.cuh"
+#include "keysort.cuh"
 
 namespace b200cv {
 
@@ -36,13 +37,12 @@ struct CellGrid {
 
 struct CellBuffers {
   CellGrid *d_grid = nullptr;
-  int *d_key = nullptr, *d_key_sorted = nullptr;  // cell id per group2 atom
-  int *d_val = nullptr, *d_sorted = nullptr;      // atom index, sorted by cell
-  int *d_cell_start = nullptr;                    // [CELL_MAX + 1]
+  int *d_key = nullptr;         // cell id per group2 atom
+  int *d_sorted = nullptr;      // atom index, sorted by cell (keysort.cuh)
+  int *d_cell_start = nullptr;  // [CELL_MAX + 2]
+  KeySort sort;
   double *d_xs = nullptr, *d_ys = nullptr, *d_zs = nullptr;  // group2 coordinates in cell order
   double *d_gs = nullptr;  // 3 planes of n2: group2 gradients in cell order (list walk)
-  void *d_temp = nullptr;                         // radix-sort scratch
-  size_t temp_bytes = 0;
   int n2 = 0;
 };
 

@@ -5,8 +5,6 @@
 #include <cmath>
 #include <cstring>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "kernels.cuh"
 
 namespace b200cv {
@@ -121,12 +119,11 @@ __global__ void sort_grid_kernel(unsigned long long *box, int n, int cell_bits, 
 
 __global__ void sort_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                 const double *__restrict__ z, int n,
-                                const SortGrid *__restrict__ grid, int *key, int *val,
-                                const int *gate)
+                                const SortGrid *__restrict__ grid, int *key, const int *gate)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (gate != nullptr && *gate != 1) return;  // keys of the last rebuild stay: still sortable
+  if (gate != nullptr && *gate != 1) return;
   SortGrid const g = *grid;
   int const cx = sort_cell(x[i], g.origin[0], g.inv_cell[0], g.dim[0]);
   int const cy = sort_cell(y[i], g.origin[1], g.inv_cell[1], g.dim[1]);
@@ -137,24 +134,6 @@ __global__ void sort_key_kernel(const double *__restrict__ x, const double *__re
   int const fine = (int)fmin(fmax(fx * (double)(1 << SORT_FINE_BITS), 0.0),
                              (double)((1 << SORT_FINE_BITS) - 1));
   key[i] = ((((cz * g.dim[1] + cy) * g.dim[0]) + cx) << SORT_FINE_BITS) | fine;
-  val[i] = i;
-}
-
-// cell_start[c] = first sorted position whose cell is >= c, for c in [0, ncells]
-__global__ void sort_cell_start_kernel(const int *__restrict__ key_sorted, int n,
-                                       const SortGrid *__restrict__ grid, int *cell_start,
-                                       const int *gate)
-{
-  int const c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gate != nullptr && *gate != 1) return;
-  if (c > grid->ncells) return;
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int const mid = (lo + hi) >> 1;
-    if ((key_sorted[mid] >> SORT_FINE_BITS) < c) lo = mid + 1;
-    else hi = mid;
-  }
-  cell_start[c] = lo;
 }
 
 // coordinates into sorted order; both sides in one launch
@@ -169,6 +148,7 @@ __global__ void sort_gather_kernel(const double *__restrict__ x1, const double *
   if (gate != nullptr && *gate != gate_on) return;
   if ((int)blockIdx.x < blocks1) {
     int const p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) xs1[n1] = ys1[n1] = zs1[n1] = SORT_FAR;
     if (p >= n1) return;
     int const i = s1[p];
     xs1[p] = x1[i];
@@ -176,6 +156,7 @@ __global__ void sort_gather_kernel(const double *__restrict__ x1, const double *
     zs1[p] = z1[i];
   } else {
     int const p = ((int)blockIdx.x - blocks1) * blockDim.x + threadIdx.x;
+    if (p == 0) xs2[n2] = ys2[n2] = zs2[n2] = SORT_FAR;
     if (p >= n2) return;
     int const j = s2[p];
     xs2[p] = x2[j];
@@ -187,9 +168,8 @@ __global__ void sort_gather_kernel(const double *__restrict__ x1, const double *
 void side_free(SortedGroup &S)
 {
   cudaFree(S.d_key);
-  cudaFree(S.d_key_sorted);
-  cudaFree(S.d_val);
   cudaFree(S.d_sorted);
+  keysort_free(S.sort);
   cudaFree(S.d_cell_start);
   cudaFree(S.d_xs);
   cudaFree(S.d_ys);
@@ -203,10 +183,9 @@ int side_setup(SortedGroup &S, int n, int cell_bits)
   cudaError_t e;
   size_t const nb = sizeof(int) * (size_t)std::max(n, 1);
   if ((e = cudaMalloc(&S.d_key, nb)) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&S.d_key_sorted, nb)) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&S.d_val, nb)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&S.d_sorted, nb)) != cudaSuccess) return (int)e;
-  size_t const nbd = sizeof(double) * (size_t)std::max(n, 1);
+  if (int const rc = keysort_setup(S.sort, n, 1 << cell_bits)) return rc;
+  size_t const nbd = sizeof(double) * ((size_t)std::max(n, 1) + 1);  // + the far-away point
   if ((e = cudaMalloc(&S.d_xs, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&S.d_ys, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&S.d_zs, nbd)) != cudaSuccess) return (int)e;
@@ -219,20 +198,9 @@ int side_setup(SortedGroup &S, int n, int cell_bits)
 int sort_side(CellSort &B, SortedGroup &S, const double *x, const double *y, const double *z,
               const int *gate, cudaStream_t stream)
 {
-  sort_key_kernel<<<(S.n + 255) / 256, 256, 0, stream>>>(x, y, z, S.n, B.d_grid, S.d_key, S.d_val,
-                                                         gate);
+  sort_key_kernel<<<(S.n + 255) / 256, 256, 0, stream>>>(x, y, z, S.n, B.d_grid, S.d_key, gate);
   note_launch();
-  size_t bytes = B.temp_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(B.d_temp, bytes, S.d_key, S.d_key_sorted,
-                                                  S.d_val, S.d_sorted, S.n, 0,
-                                                  B.cell_bits + SORT_FINE_BITS, stream);
-  if (e != cudaSuccess) return (int)e;
-  note_launch();
-  int const ncell_max = 1 << B.cell_bits;
-  sort_cell_start_kernel<<<(ncell_max + 1 + 255) / 256, 256, 0, stream>>>(
-      S.d_key_sorted, S.n, B.d_grid, S.d_cell_start, gate);
-  note_launch();
-  return (int)cudaGetLastError();
+  return keysort_run(S.sort, S.d_key, SORT_FINE_BITS, S.d_sorted, S.d_cell_start, gate, stream);
 }
 
 }  // namespace
@@ -270,13 +238,6 @@ int cellsort_setup(CellSort &B, int n1, int n2)
     rc = side_setup(B.side[0], n1, bits);
     if (rc) return rc;
   }
-  int const nmax = std::max(n1, n2);
-  B.temp_bytes = 0;
-  e = cub::DeviceRadixSort::SortPairs(nullptr, B.temp_bytes, B.side[1].d_key,
-                                      B.side[1].d_key_sorted, B.side[1].d_val, B.side[1].d_sorted,
-                                      nmax, 0, bits + SORT_FINE_BITS);
-  if (e != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&B.d_temp, std::max<size_t>(B.temp_bytes, 16))) != cudaSuccess) return (int)e;
   return 0;
 }
 
@@ -285,7 +246,6 @@ void cellsort_free(CellSort &B)
   cudaFree(B.d_grid);
   cudaFree(B.d_box);
   cudaFree(B.d_counts);
-  cudaFree(B.d_temp);
   side_free(B.side[0]);
   side_free(B.side[1]);
   B = CellSort();

@@ -10,11 +10,11 @@ namespace b200cv {
 namespace {
 
 constexpr int WARPS = ROW_THREADS / 32;
-#ifndef B200CV_ROW_U
-#define B200CV_ROW_U 2
+#ifndef B200CV_ROW_HOIST
+#define B200CV_ROW_HOIST 1  // constants of the walk's pair loop pinned in registers
 #endif
 #ifndef B200CV_ROW_MINB
-#define B200CV_ROW_MINB 8  // CTAs per SM the walk's register allocation targets
+#define B200CV_ROW_MINB 5  // CTAs per SM the walk's register allocation targets
 #endif
 
 // decision thresholds of the pair function as integers (high words of l2), kept in registers
@@ -22,7 +22,23 @@ struct RowConsts {
   int thr_lo;       // window around tolerance_l2_max and the root of f0 = tolerance ...
   unsigned thr_w;   // ... [thr_lo, thr_lo + thr_w]
   int l2max_hi;     // high word of tolerance_l2_max
+  double s[3];      // isotropic: s[0] = 1/r0^2; per-axis cut-offs: 1/r0 of each axis
+  double inv1mt, ntol;
 };
+
+template <bool ANISO> __device__ __forceinline__ RowConsts row_consts(PairParams const &P)
+{
+  RowConsts K;
+  K.thr_lo = P.thr_lo_hi;
+  K.thr_w = P.thr_width;
+  K.l2max_hi = __double2hiint(P.l2_max);
+  K.s[0] = ANISO ? P.inv_r0[0] : P.inv_r0sq[0];
+  K.s[1] = P.inv_r0[1];
+  K.s[2] = P.inv_r0[2];
+  K.inv1mt = P.inv1mt;
+  K.ntol = P.ntol;
+  return K;
+}
 
 // One pair of a row, branch-free: d = x_partner - x_own, vm = all ones for a lane that holds a
 // pair (all zeros: padding).  A pair next to a decision threshold (`rare`) contributes nothing
@@ -35,8 +51,14 @@ __device__ __forceinline__ void row_pair(PairParams const &P, RowConsts const &K
                                          double dy, double dz, int vm, double &F, double &gq,
                                          bool &rare)
 {
-  double ex = dx, ey = dy, ez = dz;
-  double const u = pair_l2<ANISO, BC_NONE>(P, ex, ey, ez);
+  // (pair_l2 of sweep.cuh without boundary conditions, constants from K)
+  double u;
+  if constexpr (ANISO) {
+    double const sx = dx * K.s[0], sy = dy * K.s[1], sz = dz * K.s[2];
+    u = fma(sz, sz, fma(sy, sy, sx * sx));
+  } else {
+    u = fma(dz, dz, fma(dy, dy, dx * dx)) * K.s[0];
+  }
   int const uh = __double2hiint(u);
   rare = (((unsigned)(uh - 0x3FEE0000) < 0x30000u) || ((unsigned)(uh - K.thr_lo) <= K.thr_w)) &&
          (vm != 0);
@@ -47,7 +69,7 @@ __device__ __forceinline__ void row_pair(PairParams const &P, RowConsts const &K
     double const um1 = ipow<EXP - 1>(ue);
     double const q = fma(um1, ue, 1.0);
     double const r = fast_rcp(q);
-    double const Fs = fma(r, P.inv1mt, P.ntol);
+    double const Fs = fma(r, K.inv1mt, K.ntol);
     F = __hiloint2double(__double2hiint(Fs) & keep, __double2loint(Fs) & keep);
     gq = um1 * (r * r);
   } else {
@@ -126,7 +148,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
   SortGrid const g = *A.grid;
   PairParams const &P = A.P;
   double const l2_pass = P.l2_max * (1.0 + 1.0e-9);
-  RowConsts const K{P.thr_lo_hi, P.thr_width, __double2hiint(P.l2_max)};
+  RowConsts const K = row_consts<ANISO>(P);
   double const cell1 = 1.0 / g.inv_cell[1], cell2 = 1.0 / g.inv_cell[2];
   double fsum = 0.0;
   unsigned long long npairs = 0ull;
@@ -156,18 +178,21 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
     auto flush = [&](bool last) {
       if (rlen > 0 || (last && first)) {
         unsigned start = 0u, c = A.chunk_base + (unsigned)p;
+        // a whole number of steps of the walk: padded with the far-away point behind the
+        // partner coordinates (cellsort.cuh), so chunks start on 128-byte boundaries
+        int const plen = (rlen + 31) & ~31;
         if (lane == 0) {
-          if (rlen > 0) start = atomicAdd(A.counts + 3, (unsigned)rlen);
+          if (rlen > 0) start = atomicAdd(A.counts + 3, (unsigned)plen);
           if (!first) c = A.chunk_extra + atomicAdd(A.counts, 1u);
         }
         start = __shfl_sync(0xffffffffu, start, 0);
         c = __shfl_sync(0xffffffffu, c, 0);
-        bool const fits = (unsigned long long)start + (unsigned)rlen <= A.cap_idx;
+        bool const fits = (unsigned long long)start + (unsigned)plen <= A.cap_idx;
         if (fits) {
-          for (int k = lane; k < rlen; k += 32) A.idx[start + k] = R[k];
+          for (int k = lane; k < plen; k += 32) A.idx[start + k] = k < rlen ? R[k] : A.nbr.n;
         }
         if (lane == 0 && c < A.cap_chunks) {
-          A.chunks[c] = make_int4(p, (int)start, fits ? rlen : 0, A.dir);
+          A.chunks[c] = make_int4(p, (int)start, fits ? plen : 0, A.dir);
         }
         __syncwarp();
         rlen = 0;
@@ -317,10 +342,15 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
 // coordinates -- over a 50 MB index array that comes from HBM every step (at BASELINE config 3),
 // so each warp runs a software pipeline over its block of rows: while row t is evaluated, the
 // header of row t + 2 is being loaded and the indices (and own coordinates) of row t + 1 are on
-// their way into a shared-memory buffer (cp.async), two buffers per warp.
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+// their way into a shared-memory buffer (cp.async, 16 bytes per lane: chunks start on 128-byte
+// boundaries), two buffers per warp; inside a row the partner coordinates of the next two steps
+// are loaded while the current two are evaluated.  A chunk is a whole number of steps (the build
+// pads it with the index of the far-away point behind the sorted coordinates), so the pair loop
+// has no lane masks, and it is straight-line code: one vote per two steps sends the few pairs
+// that have drifted next to a decision threshold to the queue.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gmem_src)
                : "memory");
 }
@@ -330,12 +360,34 @@ template <int N> __device__ __forceinline__ void cp_async_wait()
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// sums of three per-lane values over the warp in 12 shuffles instead of 30: the halves of the warp
+// swap what the other half keeps.  Lane 0 returns the sum of a, lane 8 of b, lane 16 of c.
+__device__ __forceinline__ double warp_sum3(double a, double b, double c, int lane)
+{
+  bool const h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+  double k0 = h16 ? c : a, k1 = h16 ? 0.0 : b;
+  double const s0 = h16 ? a : c, s1 = h16 ? b : 0.0;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  double k = h8 ? k1 : k0;
+  double const s = h8 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
 template <int EXP, bool ANISO>
 __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(const __grid_constant__ RowWalkArgs A)
 {
   __shared__ double red[WARPS];
-  __shared__ int sidx[WARPS][2][ROW_BUF];
+  __shared__ __align__(16) int sidx[WARPS][2][ROW_BUF];
   __shared__ RareBuf rqs[WARPS];
+  // (the grid is one wave of CTAs; the final sum reads ROW_BLOCKS partial sums)
+  if (blockIdx.x == 0) {
+    for (unsigned b = gridDim.x + threadIdx.x; b < (unsigned)ROW_BLOCKS; b += ROW_THREADS) A.partials[b] = 0.0;
+  }
   if (A.gate != nullptr && *A.gate != 0) {
     if (threadIdx.x == 0) A.partials[blockIdx.x] = 0.0;
     return;
@@ -356,8 +408,14 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
   unsigned const per = (total + nwarps - 1) / nwarps;
   unsigned const t_first = gwarp * per;
   unsigned const t_last = min(t_first + per, total);
-  constexpr int U = B200CV_ROW_U;  // steps whose loads are issued together
-  RowConsts const K{P.thr_lo_hi, P.thr_width, __double2hiint(P.l2_max)};
+  // the constants of the pair loop, through shared memory: values the assembler cannot trace
+  // back to the parameter bank stay in registers instead of being re-read on every trip
+  __shared__ RowConsts kshared;
+  if (B200CV_ROW_HOIST) {
+    if (threadIdx.x == 0) kshared = row_consts<ANISO>(P);
+    __syncthreads();
+  }
+  RowConsts const K = B200CV_ROW_HOIST ? kshared : row_consts<ANISO>(P);
   RareBuf &RQ = rqs[warp];
   int nrq = 0;
 
@@ -371,23 +429,26 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
   // indices of a chunk into one of the warp's two buffers (asynchronously)
   auto prefetch = [&](int4 const &ch, int buf) {
     int const len = min(ch.z, ROW_BUF);
-    for (int k = lane; k < len; k += 32) cp_async4(&sidx[warp][buf][k], A.idx + ch.y + k);
+    for (int k = 4 * lane; k < len; k += 128) cp_async16(&sidx[warp][buf][k], A.idx + ch.y + k);
     cp_async_commit();
   };
 
   int4 h1 = header(t_first), h2 = header(t_first + 1);
   prefetch(h1, 0);
-  // own coordinates of the coming row, loaded one row ahead like its indices
+  // own coordinates (and atom) of the coming row, loaded one row ahead like its indices
   double nxo = 0.0, nyo = 0.0, nzo = 0.0;
+  int nown = 0;
   if (t_first < t_last) {
     RowSideView const &O1 = A.side[A.self ? 0 : h1.w];
     nxo = O1.xs[h1.x];
     nyo = O1.ys[h1.x];
     nzo = O1.zs[h1.x];
+    nown = O1.sorted[h1.x];
   }
   for (unsigned t = t_first; t < t_last; t++) {
     int4 const ch = h1;
     double const xo = nxo, yo = nyo, zo = nzo;
+    int const own_atom = nown;
     int const buf = (int)((t - t_first) & 1u);
     h1 = h2;
     h2 = header(t + 2);
@@ -397,65 +458,71 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
       nxo = O1.xs[h1.x];
       nyo = O1.ys[h1.x];
       nzo = O1.zs[h1.x];
+      nown = O1.sorted[h1.x];
     }
     cp_async_wait<1>();  // this row's indices have landed (the next row's may still be in flight)
     __syncwarp();
-    int const p = ch.x, len = min(ch.z, ROW_BUF), dir = ch.w;
+    int const p = ch.x, len = min(ch.z, ROW_BUF), dir = ch.w;  // len: a multiple of 32
     if (len > 0) {
       RowSideView const &O = A.side[A.self ? 0 : dir];
       RowSideView const &N = A.side[A.self ? 0 : 1 - dir];
-      const int *const q_of = sidx[warp][buf];
+      const double *const nx = N.xs, *const ny = N.ys, *const nz = N.zs;
+      const int *const qp = sidx[warp][buf] + lane;
       double gx = 0.0, gy = 0.0, gz = 0.0, rsum = 0.0;
-      auto one_pair = [&](int q, double dx, double dy, double dz, int vm) {
+      auto load = [&](int k, double &x, double &y, double &z) {
+        int const q = qp[k];
+        x = nx[q];
+        y = ny[q];
+        z = nz[q];
+      };
+      auto eval = [&](double x, double y, double z, bool &rare) {
+        double const dx = x - xo, dy = y - yo, dz = z - zo;
         double F, gq;
-        bool rare;
-        row_pair<EXP, ANISO>(P, K, dx, dy, dz, vm, F, gq, rare);
+        row_pair<EXP, ANISO>(P, K, dx, dy, dz, -1, F, gq, rare);
         rsum += F;
         gx = fma(gq, dx, gx);
         gy = fma(gq, dy, gy);
         gz = fma(gq, dz, gz);
-        if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) {
-          // the canonical side hands the pair to exact_kernel
-          bool const mine = rare && (A.self ? (q > p) : (dir == 0));
-          int const own_atom = O.sorted[p], nbr_atom = mine ? N.sorted[q] : 0;
-          rare_push(RQ, nrq, mine, dir == 0 ? own_atom : nbr_atom, dir == 0 ? nbr_atom : own_atom,
-                    A.rare, A.rare_cap, A.rare_count, lane);
-        }
       };
-      // groups of U steps: all coordinate loads first (independent of each other), then the
-      // arithmetic; lanes beyond the end of the row read entry 0 and are masked out
-      for (int k = 0; k < len; k += 32 * U) {
-        int q[U], vm[U];
-        double dx[U], dy[U], dz[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          int const kk = k + 32 * u + lane;
-          vm[u] = kk < len ? -1 : 0;
-          q[u] = q_of[kk & vm[u]];
+      // the canonical side hands a pair next to a threshold to exact_kernel
+      auto queue = [&](int k, bool rare) {
+        int const q = qp[k];
+        bool const mine = rare && (A.self ? (q > p) : (dir == 0));
+        int const nbr_atom = mine ? N.sorted[q] : 0;
+        rare_push(RQ, nrq, mine, dir == 0 ? own_atom : nbr_atom, dir == 0 ? nbr_atom : own_atom,
+                  A.rare, A.rare_cap, A.rare_count, lane);
+      };
+      double ax0, ay0, az0, ax1 = 0.0, ay1 = 0.0, az1 = 0.0;
+      load(0, ax0, ay0, az0);
+      if (len > 32) load(32, ax1, ay1, az1);
+      int k = 0;
+      for (; k + 64 <= len; k += 64) {
+        double bx0, by0, bz0, bx1, by1, bz1;  // (read only where they were loaded)
+        if (k + 64 < len) load(k + 64, bx0, by0, bz0);
+        if (k + 96 < len) load(k + 96, bx1, by1, bz1);
+        bool r0, r1;
+        eval(ax0, ay0, az0, r0);
+        eval(ax1, ay1, az1, r1);
+        if (__builtin_expect(__any_sync(0xffffffffu, r0 || r1), 0)) {
+          queue(k, r0);
+          queue(k + 32, r1);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          dx[u] = N.xs[q[u]] - xo;
-          dy[u] = N.ys[q[u]] - yo;
-          dz[u] = N.zs[q[u]] - zo;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          if (k + 32 * u < len) one_pair(q[u], dx[u], dy[u], dz[u], vm[u]);  // warp-uniform test
-        }
+        ax0 = bx0, ay0 = by0, az0 = bz0;
+        ax1 = bx1, ay1 = by1, az1 = bz1;
+      }
+      if (k < len) {
+        bool r0;
+        eval(ax0, ay0, az0, r0);
+        if (__builtin_expect(__any_sync(0xffffffffu, r0), 0)) queue(k, r0);
       }
       // the scalar: both sides of a selfCoordNum pair are in rows (half each), a coordNum pair
       // counts in the row of its group1 atom
       fsum += A.self ? 0.5 * rsum : (dir == 0 ? rsum : 0.0);
       if (A.want_grad) {
-        gx = warp_sum(gx);
-        gy = warp_sum(gy);
-        gz = warp_sum(gz);
-        if (lane == 0) {
-          int const own_atom = O.sorted[p];
-          atomicAdd(&O.grad[own_atom], -P.c_grad[0] * gx);
-          atomicAdd(&O.grad[O.gstride + own_atom], -P.c_grad[1] * gy);
-          atomicAdd(&O.grad[2 * O.gstride + own_atom], -P.c_grad[2] * gz);
+        double const g = warp_sum3(gx, gy, gz, lane);
+        if ((lane & 7) == 0 && lane < 24) {
+          int const c = lane >> 3;
+          atomicAdd(&O.grad[(size_t)c * O.gstride + own_atom], -P.c_grad[c] * g);
         }
       }
     }
@@ -519,14 +586,34 @@ int launch_row_build(const RowBuildArgs &args, int exp_special, bool aniso, cuda
   return (int)cudaGetLastError();
 }
 
+// one wave of CTAs: what the device holds at once (rows are dealt out in equal blocks; a second,
+// partly filled wave would run at a fraction of the occupancy)
+template <int EXP, bool ANISO> static int walk_grid()
+{
+  static int grid = 0;
+  if (grid == 0) {
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, row_walk_kernel<EXP, ANISO>, ROW_THREADS, 0);
+    grid = std::max(1, std::min(ROW_BLOCKS, sms * std::max(per_sm, 1)));
+  }
+  return grid;
+}
+
+template <int EXP, bool ANISO> static void walk_launch(const RowWalkArgs &args, cudaStream_t stream)
+{
+  row_walk_kernel<EXP, ANISO><<<walk_grid<EXP, ANISO>(), ROW_THREADS, 0, stream>>>(args);
+}
+
 int launch_row_walk(const RowWalkArgs &args, int exp_special, bool aniso, cudaStream_t stream)
 {
   if (exp_special == 3) {
-    if (aniso) row_walk_kernel<3, true><<<ROW_BLOCKS, ROW_THREADS, 0, stream>>>(args);
-    else row_walk_kernel<3, false><<<ROW_BLOCKS, ROW_THREADS, 0, stream>>>(args);
+    if (aniso) walk_launch<3, true>(args, stream);
+    else walk_launch<3, false>(args, stream);
   } else {
-    if (aniso) row_walk_kernel<0, true><<<ROW_BLOCKS, ROW_THREADS, 0, stream>>>(args);
-    else row_walk_kernel<0, false><<<ROW_BLOCKS, ROW_THREADS, 0, stream>>>(args);
+    if (aniso) walk_launch<0, true>(args, stream);
+    else walk_launch<0, false>(args, stream);
   }
   note_launch();
   return (int)cudaGetLastError();

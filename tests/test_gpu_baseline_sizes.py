@@ -1,7 +1,8 @@
 """Parity at the BASELINE.json sizes themselves (configs 3, 4, 5), exactly as bench.py runs
 them: device-resident SoA proxy buffers -> read_data -> calc_value (-> fit gradients) ->
 apply_force, against the OpenMP row-parallel form of the oracle (same pair arithmetic as the
-reference-order oracle, per-row partial sums; tests/test_oracle_ref_vectors.py pins it).
+reference-order oracle, per-row partial sums, scalar summed in long double;
+tests/test_oracle_omp_cpu.py pins it to the reference-order oracle).
 
 Bar: pair-list indices bit-exact at every rebuild; values, gradients and forces within 1e-12
 (max-norm scaled for arrays, see test_gpu_parity.py).  Fitted groups: geometry 1e-13 against

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../colvars_b200/csrc"
 make -j8 > /dev/null
 NVCC=/usr/local/cuda/bin/nvcc
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fopenmp"
-OBJS="kernels sweep_inst api planner calc graph_step comm host_path measure fit cells cellsort rows"
+OBJS="kernels sweep_inst api planner calc graph_step comm host_path measure fit cells cellsort keysort rows"
 while [ $# -ge 3 ]; do
   name=$1; src=$2; defs=$3; shift 3
   $NVCC $FLAGS $defs -c $src -o /tmp/variant_$name.o
