@@ -433,16 +433,19 @@ def ncu_traffic(key, world):
     import glob
     for path in sorted(glob.glob(str(ROOT / "profiles" / "r0*_c5_sweep_*ncu_raw.csv")), reverse=True):
         try:
+            # `ncu --page raw --csv`: one column per metric, a row of units, then one row per launch
             rows = list(csv.reader(open(path)))
-            hdr = next(r for r in rows if "Metric Name" in r)
-            mi, vi, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name")
-            ui = hdr.index("Metric Unit")
+            hdr, units = rows[0], rows[1]
+            ki = hdr.index("Kernel Name")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot = 0.0
-            for r in rows:
-                if len(r) > vi and "sweep_kernel" in r[ki] and r[mi] in ("dram__bytes_read.sum",
-                                                                       "dram__bytes_write.sum"):
-                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1.0)
-                    tot += float(r[vi].replace(",", "")) * scale
+            for r in rows[2:]:
+                if len(r) <= ki or "sweep_kernel" not in r[ki]:
+                    continue
+                for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    c = hdr.index(name)
+                    tot += float(r[c].replace(",", "")) * scale.get(units[c], 1.0)
+                break
             if tot > 0:
                 return tot, str(Path(path).relative_to(ROOT))
         except Exception:

@@ -144,6 +144,10 @@ void reset_boundaries(PairParams &P)
   std::memset(P.tri_shift, 0, sizeof(P.tri_shift));
   P.tri_margin = 0.0;
   P.tri_search = 1;
+  std::memset(P.recipf, 0, sizeof(P.recipf));
+  std::memset(P.cell2f, 0, sizeof(P.cell2f));
+  std::memset(P.tri_nf, 0, sizeof(P.tri_nf));
+  P.tri_marginf = 0.0f;
 }
 
 // tables of the tile sweep's image search in mixed / triclinic cells (general_image,
@@ -170,6 +174,15 @@ void fill_general_cell_tables(PairParams &P)
     for (int d = 0; d < 3; d++) P.cell2[a][d] = 2.0 * P.cell[a][d];
   }
   P.tri_margin = std::ldexp(max_n, -26);
+  // single-precision copies (decisions of general_image)
+  for (int a = 0; a < 3; a++) {
+    for (int d = 0; d < 3; d++) {
+      P.recipf[a][d] = (float)P.recip[a][d];
+      P.cell2f[a][d] = (float)P.cell2[a][d];
+    }
+  }
+  for (int k = 0; k < 13; k++) P.tri_nf[k] = (float)std::min(P.tri_n[k], 3.0e38);
+  P.tri_marginf = (float)std::ldexp(max_n, -15);
 }
 
 int alloc_group(b200cv_cvc *h, Group &G, int n)
@@ -538,7 +551,10 @@ int b200cv_set_boundaries(b200cv_cvc *h, int px, int py, int pz, const double A[
   if (P.bc_type == 1 || P.bc_type == 3) fill_general_cell_tables(P);
   if (!P.tri_search) {
     // no image search: no direction can ever win in general_image
-    for (int k = 0; k < 13; k++) P.tri_n[k] = 1.0e300;
+    for (int k = 0; k < 13; k++) {
+      P.tri_n[k] = 1.0e300;
+      P.tri_nf[k] = 3.0e38f;
+    }
   }
   return B200CV_OK;
 }

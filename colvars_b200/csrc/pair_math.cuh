@@ -58,6 +58,12 @@ struct PairParams {
   // (1e-5; src/colvars_system.h:120-140 keeps type "orthogonal" for it): the reference rounds the
   // fractional coordinates with the full vectors but does not search the neighbouring images
   int tri_search;
+  // single-precision copies for the DECISIONS of general_image (which integers, which image):
+  // reciprocal vectors, 2 * cell vectors, |s_k|^2 (3e38: not periodic), decision margin
+  float recipf[3][3];
+  float cell2f[3][3];
+  float tri_nf[13];
+  float tri_marginf;
 };
 
 // the 13 lattice directions of get_triclinic_shift (src/colvars_system.h:194-219) up to sign:
@@ -318,24 +324,38 @@ __device__ inline void position_distance_exact(PairParams const &P, double x1, d
   }
 }
 
-// position_distance for mixed / triclinic cells on the tile sweep.  Steps 1-2 (fractional
-// rounding, subtraction of the lattice combination) run in the reference's operation order, so
-// the reduced vector is bit-identical to the reference's.  Step 3, get_triclinic_shift
-// (src/colvars_system.h:194-219: the shortest of the 27 neighbouring images, zero shift and
-// then loop order winning ties), is decided on
-//     |d +- s_k|^2 - |d|^2 = |s_k|^2 +- 2 d.s_k ,   min over the sign = |s_k|^2 - |2 d.s_k|
-// for the 13 directions s_k (three dot products, ten sums, thirteen differences, a running
-// minimum that carries k in the four lowest mantissa bits).  The chosen shift is added as the
-// reference adds it (tab[k] holds s_k in the reference's operation order; the sign flip is
-// exact), so the image vector is bit-identical whenever the decision is.  A decision that
-// another candidate -- or the zero shift -- comes within tri_margin (2^-26 of the largest
-// |s_k|^2, nine orders of magnitude above the rounding of either evaluation) of overturning is
-// not taken here: the function returns true and the pair goes to the exact-pair queue, where
-// pair_exact runs the reference's loop.
+// position_distance for mixed / triclinic cells on the tile sweep.
+//
+// The reference (src/colvars_system.h:161-219) takes two kinds of decisions per pair -- the three
+// integers of the fractional rounding (steps 1-2) and which of the 27 neighbouring images is the
+// shortest (step 3, get_triclinic_shift: zero shift and then loop order winning ties) -- and
+// otherwise does a handful of double-precision operations with them.  Here the DECISIONS are
+// taken in single precision (the FP32 pipe runs next to the FP64 pipe and at eight times its
+// rate), each with a margin several times the worst single-precision error; the arithmetic
+// with the decided integers / image is then done in double precision in the reference's
+// operation order, so the image vector is bit-identical whenever the decisions are.  A decision
+// inside its margin is not taken: the function returns true and the pair goes to the exact-pair
+// queue, where pair_exact runs the reference's loop (4 pairs in 10^4 in a rhombic dodecahedron;
+// taking the decision again in double precision in the loop -- a call, for the lanes concerned --
+// was measured and costs more than it saves: the warp waits for it once in 30 pairs).
+//   steps 1-2  u = recip_a . d in single precision, error below 2^-21.5 * sum |terms|; floor(u + 1/2)
+//              is the integer next to u unless u is within the margin, 2^-19 * sum |terms|, of a
+//              half-integer
+//   step 3     |d +- s_k|^2 - |d|^2 = |s_k|^2 +- 2 d.s_k ,  min over the sign = |s_k|^2 - |2 d.s_k|
+//              for the 13 directions s_k (three dot products, ten sums, thirteen differences, a
+//              running minimum that carries k in the four lowest mantissa bits).  Error of a
+//              score (rounding + the tag) below 2^-17.8 of the largest |s_k|^2; margin 2^-15 of it:
+//              another candidate -- or the zero shift -- within the margin of the best one makes
+//              the pair ambiguous.
+// The chosen shift is added as the reference adds it (tab[k] holds s_k in the reference's
+// operation order; the sign flip is exact).
 // tab: 14 x 3 doubles in shared memory, rows 0..12 = P.tri_shift, row 13 = 0.
-__device__ __forceinline__ bool general_image(PairParams const &P, const double *tab, double &dx,
-                                              double &dy, double &dz)
+// (B200CV_TRI_FP64: double precision only.)
+// every decision in double precision (margin 2^-26 of the largest |s_k|^2)
+__device__ __forceinline__ bool general_image_f64(PairParams const &P, const double *tab, double &dx,
+                                                  double &dy, double &dz)
 {
+
   double const xs = floor(__dadd_rn(dot3_exact(P.recip[0], dx, dy, dz), 0.5));
   double const ys = floor(__dadd_rn(dot3_exact(P.recip[1], dx, dy, dz), 0.5));
   double const zs = floor(__dadd_rn(dot3_exact(P.recip[2], dx, dy, dz), 0.5));
@@ -377,6 +397,77 @@ __device__ __forceinline__ bool general_image(PairParams const &P, const double 
   dz = fma(sgn, sz, dz);
   return ambiguous;
 }
+
+// the decisions in single precision
+__device__ __forceinline__ bool general_image_f32(PairParams const &P, const double *tab, double &dx,
+                                                  double &dy, double &dz)
+{
+  bool amb = false;
+  double sh[3];
+  {
+    float const fx = (float)dx, fy = (float)dy, fz = (float)dz;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      // floor(u + 1/2) is the integer next to u unless u is next to a half-integer
+      float const t0 = P.recipf[a][0] * fx, t1 = P.recipf[a][1] * fy, t2 = P.recipf[a][2] * fz;
+      float const u = (t0 + t1) + t2;
+      float const mag = (fabsf(t0) + fabsf(t1)) + fabsf(t2);
+      float const r = rintf(u);
+      float const dev = fabsf(u - r);  // in [0, 1/2]
+      amb = amb || !(fmaf(mag, 0x1p-19f, dev) < 0.5f - 0x1p-30f);  // (a NaN is ambiguous)
+      sh[a] = (double)r;
+    }
+  }
+  dx = __dsub_rn(dx, __dadd_rn(__dadd_rn(__dmul_rn(sh[0], P.cell[0][0]), __dmul_rn(sh[1], P.cell[1][0])),
+                               __dmul_rn(sh[2], P.cell[2][0])));
+  dy = __dsub_rn(dy, __dadd_rn(__dadd_rn(__dmul_rn(sh[0], P.cell[0][1]), __dmul_rn(sh[1], P.cell[1][1])),
+                               __dmul_rn(sh[2], P.cell[2][1])));
+  dz = __dsub_rn(dz, __dadd_rn(__dadd_rn(__dmul_rn(sh[0], P.cell[0][2]), __dmul_rn(sh[1], P.cell[1][2])),
+                               __dmul_rn(sh[2], P.cell[2][2])));
+  float const gx = (float)dx, gy = (float)dy, gz = (float)dz;
+  float const pa = fmaf(gz, P.cell2f[0][2], fmaf(gy, P.cell2f[0][1], gx * P.cell2f[0][0]));
+  float const pb = fmaf(gz, P.cell2f[1][2], fmaf(gy, P.cell2f[1][1], gx * P.cell2f[1][0]));
+  float const pc = fmaf(gz, P.cell2f[2][2], fmaf(gy, P.cell2f[2][1], gx * P.cell2f[2][0]));
+  float const pab = pa + pb, pamb = pa - pb;
+  float const q[13] = {pa,      pb,      pc,       pab,      pamb,      pa + pc,  pa - pc,
+                       pb + pc, pb - pc, pab + pc, pab - pc, pamb + pc, pamb - pc};
+  float m[13];
+#pragma unroll
+  for (int k = 0; k < 13; k++) {
+    float const v = P.tri_nf[k] - fabsf(q[k]);
+    m[k] = __int_as_float((__float_as_int(v) & ~15) | k);
+  }
+  // minimum as a tree (depth 4): the search of one pair is a single dependency chain otherwise
+  float const b0 = fminf(m[0], m[1]), b1 = fminf(m[2], m[3]), b2 = fminf(m[4], m[5]);
+  float const b3 = fminf(m[6], m[7]), b4 = fminf(m[8], m[9]), b5 = fminf(m[10], m[11]);
+  float const c0 = fminf(b0, b1), c1 = fminf(b2, b3), c2 = fminf(b4, b5);
+  float const best = fminf(fminf(c0, c1), fminf(c2, m[12]));
+  float const thr = best + P.tri_marginf;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 13; k++) cnt += (m[k] < thr) ? 1 : 0;
+  bool const shifted = best < P.tri_marginf;
+  amb = amb || (shifted && (cnt >= 2 || best > -P.tri_marginf)) || !(best == best);
+  int const idx = shifted ? (__float_as_int(best) & 15) : 13;
+  double const sx = tab[3 * idx], sy = tab[3 * idx + 1], sz = tab[3 * idx + 2];
+  double const t = fma(dz, sz, fma(dy, sy, dx * sx));
+  double const sgn = t > 0.0 ? -1.0 : 1.0;
+  dx = fma(sgn, sx, dx);
+  dy = fma(sgn, sy, dy);
+  dz = fma(sgn, sz, dz);
+  return amb;
+}
+
+__device__ __forceinline__ bool general_image(PairParams const &P, const double *tab, double &dx,
+                                              double &dy, double &dz)
+{
+#if defined(B200CV_TRI_FP64)
+  return general_image_f64(P, tab, dx, dy, dz);
+#else
+  return general_image_f32(P, tab, dx, dy, dz);
+#endif
+}
+
 
 // switching_function<flags> (src/colvarcomp_coordnums.h:168-224)
 __device__ inline double switching_exact(double l2, double &dFdl2, PairParams const &P,

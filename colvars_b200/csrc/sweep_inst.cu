@@ -3,6 +3,10 @@
 
 #include <atomic>
 
+#ifndef B200CV_GEN_MINB
+#define B200CV_GEN_MINB SWEEP_MINB
+#endif
+
 namespace b200cv {
 
 // ============================ sweep dispatch =================================================
@@ -12,7 +16,9 @@ bool sweep_has_special(int en, int ed) { return en == 6 && ed == 12; }
 template <int EXP, bool ANISO, int PBC, bool PL>
 static int launch_sweep_t(const SweepArgs &args, int nitems, cudaStream_t stream)
 {
-  auto kern = sweep_kernel<EXP, ANISO, PBC, PL, SWEEP_R, SWEEP_W, SWEEP_MINB>;
+  // general cells: the image search wants its registers less than the other sweeps want theirs
+  constexpr int MINB = PBC == BC_GENERAL ? B200CV_GEN_MINB : SWEEP_MINB;
+  auto kern = sweep_kernel<EXP, ANISO, PBC, PL, SWEEP_R, SWEEP_W, MINB>;
   // the opt-in shared-memory size is a per-device function attribute
   static std::atomic<unsigned long long> attr_done{0ull};
   int dev = 0;

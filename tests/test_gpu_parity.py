@@ -1050,6 +1050,33 @@ def test_general_cells_through_the_tile_sweep(cell, kind, tol):
             assert np.array_equal(cv.pairlist(), np.flatnonzero(pl).astype(np.uint64))
 
 
+@pytest.mark.parametrize("cell", ["dodecahedron", "skewed", "mixed-skewed"])
+def test_general_cells_atoms_far_outside_the_unit_cell(cell):
+    """Unwrapped coordinates, tens of cells away from each other: the integers of the fractional
+    rounding are large, the single-precision decisions of general_image lose bits there and
+    must hand over (exact-pair queue) instead of deciding wrongly."""
+    cb = _cb()
+    L = 18.0
+    per, A, B, Cc = _scaled_cell(cell, L)
+    n1, n2 = 256, 2048
+    rng = np.random.default_rng(1234)
+    frac = rng.random((n1 + n2, 3)) * 80.0 - 40.0
+    proxy = np.ascontiguousarray(frac @ np.array([A, B, Cc]))
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32)
+    cv = cb.CoordNum("coordNum", i1, i2, cutoff=5.0)
+    cv.set_boundaries(per, A, B, Cc)
+    p = O.make_params((5.0,) * 3, boundaries=(per, A, B, Cc))
+    v = cv.calc_host(proxy)
+    ov, og1, og2 = O.coordnum(p, proxy[i1], proxy[i2])
+    close_val(v, ov)
+    close_arr(cv.gradients(1), og1)
+    close_arr(cv.gradients(2), og2)
+    # ... and it is a hand-over of a small share of the pairs, not of all of them (2.4 % of the
+    # pairs are in the queue anyway: |l2 - 1| < 2^-4)
+    assert cv.last_stats()[1] < 0.04 * n1 * n2, cv.last_stats()
+
+
 def test_general_cell_image_ties_follow_the_reference():
     """Pairs whose reduced vector lies on (or an ulp or two beside) a plane where two images are
     equally long: the reference keeps the zero shift, then the first candidate in loop order.

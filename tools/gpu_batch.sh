@@ -1,4 +1,4 @@
 #!/bin/bash
 out=gpurun_out/$1; mkdir -p $out
-python tools/exp_steps_all.py 50000 2>&1 | tail -2
-python tools/exp_steps_all.py 200000 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "general or tric or mixed or orthogonal or cell" > $out/tests.log 2>&1; tail -5 $out/tests.log
+python tools/exp_tric.py 4 2>&1 | tail -2
