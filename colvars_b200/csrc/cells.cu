@@ -1,4 +1,4 @@
-// cells.cu -- see cells.cuh.  Grid construction (bounding box, cell ids, radix sort, cell
+// cells.cu -- see cells.cuh.  Grid construction (bounding box, cell ids, cell order (keysort.cuh), cell
 // offsets) and the neighbour-cell pair kernel of the pair-list rebuild.
 #include "cells.cuh"
 

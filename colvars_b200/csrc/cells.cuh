@@ -74,7 +74,7 @@ struct CellPairArgs {
 int cells_setup(CellBuffers &B, int n2);
 void cells_free(CellBuffers &B);
 // grid + sort of the group2 atoms; cut[d] = cut-off radius along axis d
-// gate (may be NULL): see CellPairArgs::gate; the radix sort itself always runs.
+// gate (may be NULL): see CellPairArgs::gate.
 // periodic_frac: NULL for a non-periodic system (grid = bounding box of group2, found on the
 // device), else the reciprocal vectors of the cell, row by row (diag(1 / edge) for an
 // orthorhombic cell); the grid is then fixed by the host.  cells_periodic_dims tells whether the
