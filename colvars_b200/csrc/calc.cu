@@ -493,8 +493,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
                                   int &nparts) -> int {
       CellSort &B = h->sort;
       CUDA_OK(h, cellsort_build(B, x1, y1, z1, x2, y2, z2, gate, stream));
-      // bounding box, grid; keys and sort per group
-      h->launches += 2 + (h->self() ? 1 : 2) * (1 + keysort_launches(B.side[1].sort));
+      // bounding box + grid; keys and sort per group
+      h->launches += 1 + (h->self() ? 1 : 2) * (1 + keysort_launches(B.side[1].sort));
       CUDA_OK(h, cellsort_gather(B, x1, y1, z1, x2, y2, z2, gate, 1, stream));
       h->launches++;
       RowSideView s1, s2;

@@ -102,7 +102,8 @@ __device__ __forceinline__ int cell_coord_periodic(CellGrid const &g, int a, dou
 
 __global__ void cell_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                 const double *__restrict__ z, int n,
-                                const CellGrid *__restrict__ grid, int *key, const int *gate)
+                                const CellGrid *__restrict__ grid, int *key, int *cnt,
+                                const int *gate)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -119,6 +120,7 @@ __global__ void cell_key_kernel(const double *__restrict__ x, const double *__re
     cz = min(max(cell_coord(z[i], g.origin[2], g.inv_cell[2], g.dim[2]), 0), g.dim[2] - 1);
   }
   key[i] = (cz * g.dim[1] + cy) * g.dim[0] + cx;
+  keysort_count(cnt, key[i]);
 }
 
 
@@ -411,7 +413,8 @@ int cells_build(CellBuffers &B, const double *x2, const double *y2, const double
                                                 gate);
   }
   note_launch();
-  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key, gate);
+  cell_key_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(x2, y2, z2, n2, B.d_grid, B.d_key,
+                                                        B.sort.d_cnt, gate);
   note_launch();
   if (int const rc = keysort_run(B.sort, B.d_key, 0, B.d_sorted, B.d_cell_start, gate, stream)) return rc;
   return launch_cell_gather(B, x2, y2, z2, n2, gate, 1, stream);

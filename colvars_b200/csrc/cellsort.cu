@@ -31,10 +31,13 @@ __device__ __forceinline__ double from_ordered_bits(unsigned long long u)
 
 constexpr int BBOX_THREADS = 256;
 
-// box[0..2] = min, box[3..5] = max (ordered bits); armed by sort_grid_kernel for the next time
+__device__ void sort_grid(unsigned long long *box, int n, int cell_bits, SortGrid *grid);
+
+// box[0..2] = min, box[3..5] = max (ordered bits); armed by sort_grid for the next time
 __global__ void __launch_bounds__(BBOX_THREADS)
 sort_bbox_kernel(const double *__restrict__ x, const double *__restrict__ y,
-                 const double *__restrict__ z, int n, unsigned long long *box, const int *gate)
+                 const double *__restrict__ z, int n, unsigned long long *box, int cell_bits,
+                 SortGrid *grid, const int *gate)
 {
   __shared__ double red[6][BBOX_THREADS / 32];
   if (gate != nullptr && *gate != 1) return;
@@ -66,16 +69,27 @@ sort_bbox_kernel(const double *__restrict__ x, const double *__restrict__ y,
     for (int w = 1; w < BBOX_THREADS / 32; w++) v = d < 3 ? fmin(v, red[d][w]) : fmax(v, red[d][w]);
     if (d < 3) atomicMin(&box[d], ordered_bits(v));
     else atomicMax(&box[d], ordered_bits(v));
+    __threadfence();
+  }
+  // the CTA that arrives last turns the box into the grid (box[6]: ticket, re-armed)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned *const ticket = reinterpret_cast<unsigned *>(box + 6);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      *ticket = 0u;
+      sort_grid(box, n, cell_bits, grid);
+    }
   }
 }
 
-__global__ void sort_grid_kernel(unsigned long long *box, int n, int cell_bits, SortGrid *grid,
-                                 const int *gate)
+// the grid from the finished box (one thread: the last CTA of sort_bbox_kernel)
+__device__ void sort_grid(unsigned long long *box, int n, int cell_bits, SortGrid *grid)
 {
-  if (gate != nullptr && *gate != 1) return;
   double a[3], ext[3], emax = 0.0;
   for (int d = 0; d < 3; d++) {
-    double const l = from_ordered_bits(box[d]), h = from_ordered_bits(box[3 + d]);
+    double const l = from_ordered_bits(((volatile unsigned long long *)box)[d]);
+    double const h = from_ordered_bits(((volatile unsigned long long *)box)[3 + d]);
     a[d] = l;
     ext[d] = fmax(h - l, 0.0);
     emax = fmax(emax, ext[d]);
@@ -119,7 +133,8 @@ __global__ void sort_grid_kernel(unsigned long long *box, int n, int cell_bits, 
 
 __global__ void sort_key_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                 const double *__restrict__ z, int n,
-                                const SortGrid *__restrict__ grid, int *key, const int *gate)
+                                const SortGrid *__restrict__ grid, int *key, int *cnt,
+                                const int *gate)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -133,7 +148,9 @@ __global__ void sort_key_kernel(const double *__restrict__ x, const double *__re
   double const fx = (x[i] - g.origin[0]) * g.inv_cell[0] - (double)cx;
   int const fine = (int)fmin(fmax(fx * (double)(1 << SORT_FINE_BITS), 0.0),
                              (double)((1 << SORT_FINE_BITS) - 1));
-  key[i] = ((((cz * g.dim[1] + cy) * g.dim[0]) + cx) << SORT_FINE_BITS) | fine;
+  int const cell = ((cz * g.dim[1] + cy) * g.dim[0]) + cx;
+  key[i] = (cell << SORT_FINE_BITS) | fine;
+  keysort_count(cnt, cell);
 }
 
 // coordinates into sorted order; both sides in one launch
@@ -198,7 +215,8 @@ int side_setup(SortedGroup &S, int n, int cell_bits)
 int sort_side(CellSort &B, SortedGroup &S, const double *x, const double *y, const double *z,
               const int *gate, cudaStream_t stream)
 {
-  sort_key_kernel<<<(S.n + 255) / 256, 256, 0, stream>>>(x, y, z, S.n, B.d_grid, S.d_key, gate);
+  sort_key_kernel<<<(S.n + 255) / 256, 256, 0, stream>>>(x, y, z, S.n, B.d_grid, S.d_key,
+                                                         S.sort.d_cnt, gate);
   note_launch();
   return keysort_run(S.sort, S.d_key, SORT_FINE_BITS, S.d_sorted, S.d_cell_start, gate, stream);
 }
@@ -218,7 +236,8 @@ int cellsort_setup(CellSort &B, int n1, int n2)
   B.cell_bits = bits;
   cudaError_t e;
   if ((e = cudaMalloc(&B.d_grid, sizeof(SortGrid))) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&B.d_box, 6 * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+  if ((e = cudaMalloc(&B.d_box, 7 * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+  if ((e = cudaMemset(B.d_box, 0, 7 * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
   {
     // min slots at +1e300, max slots at -1e300 (ordered bits, see sort_bbox_kernel)
     auto ordered = [](double v) {
@@ -257,9 +276,8 @@ int cellsort_build(CellSort &B, const double *x1, const double *y1, const double
 {
   SortedGroup &J = B.side[1];
   int const bb = std::max(1, std::min(296, (J.n + BBOX_THREADS * 4 - 1) / (BBOX_THREADS * 4)));
-  sort_bbox_kernel<<<bb, BBOX_THREADS, 0, stream>>>(x2, y2, z2, J.n, B.d_box, gate);
-  note_launch();
-  sort_grid_kernel<<<1, 1, 0, stream>>>(B.d_box, J.n, B.cell_bits, B.d_grid, gate);
+  sort_bbox_kernel<<<bb, BBOX_THREADS, 0, stream>>>(x2, y2, z2, J.n, B.d_box, B.cell_bits, B.d_grid,
+                                                    gate);
   note_launch();
   int rc = sort_side(B, J, x2, y2, z2, gate, stream);
   if (rc) return rc;

@@ -13,15 +13,6 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_PER_THREAD = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
 
-__global__ void keysort_count_kernel(const int *__restrict__ key, int n, int fine_bits, int *cnt,
-                                     const int *gate)
-{
-  int const i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (gate != nullptr && *gate != 1) return;
-  atomicAdd(&cnt[key[i] >> fine_bits], 1);
-}
-
 // exclusive scan inside a tile of SCAN_TILE cells; the tile's total goes to tile[blockIdx.x]
 __global__ void __launch_bounds__(SCAN_THREADS)
 keysort_scan_kernel(const int *__restrict__ cnt, int ncells, int *cell_start, int *tile,
@@ -148,7 +139,7 @@ void keysort_free(KeySort &S)
 
 int keysort_launches(const KeySort &S)
 {
-  return (S.ncells_max + 2 + SCAN_TILE - 1) / SCAN_TILE > 1 ? 5 : 4;
+  return (S.ncells_max + 2 + SCAN_TILE - 1) / SCAN_TILE > 1 ? 4 : 3;
 }
 
 int keysort_run(KeySort &S, const int *key, int fine_bits, int *sorted, int *cell_start,
@@ -156,8 +147,6 @@ int keysort_run(KeySort &S, const int *key, int fine_bits, int *sorted, int *cel
 {
   int const n = S.n, nc = S.ncells_max + 2;
   int const blocks = std::max(1, (n + 255) / 256), tiles = (nc + SCAN_TILE - 1) / SCAN_TILE;
-  keysort_count_kernel<<<blocks, 256, 0, stream>>>(key, n, fine_bits, S.d_cnt, gate);
-  note_launch();
   keysort_scan_kernel<<<tiles, SCAN_THREADS, 0, stream>>>(S.d_cnt, nc, cell_start, S.d_tile, gate);
   note_launch();
   if (tiles > 1) {

@@ -5,7 +5,7 @@
 // their atoms by an integer key = cell << fine_bits | fine.  A library radix sort does that in
 // five kernels that a captured graph cannot switch off: the list steps of a captured evaluation
 // (gate word != 1) would sort again on every launch.  Here
-//   count     cnt[cell]++ per atom
+//   count     cnt[cell]++ per atom (by the caller's key kernel: keysort_count)
 //   scan      cell_start[c] = atoms in cells < c, c in [0, ncells_max + 1]: tiles of 4096 cells, then
 //             the tile offsets
 //   scatter   atoms into the slots of their cell, in arrival order (cnt counts down to zero again)
@@ -28,9 +28,13 @@ struct KeySort {
 
 int keysort_setup(KeySort &S, int n, int ncells_max);
 void keysort_free(KeySort &S);
-// key[i] of atom i (cell = key >> fine_bits < ncells_max) -> sorted[p] = atom at position p,
+// the count step, for the kernel that computes the keys
+__device__ __forceinline__ void keysort_count(int *cnt, int cell) { atomicAdd(&cnt[cell], 1); }
+
+// key[i] of atom i (cell = key >> fine_bits < ncells_max), counted into S.d_cnt by the caller's
+// key kernel -> sorted[p] = atom at position p,
 // cell_start[c] for c in [0, ncells_max + 1] (= n from the first empty cell behind the last atom
-// on).  gate (may be NULL): work only when *gate == 1.  Four kernels (five beyond 4096 cells).
+// on).  gate (may be NULL): work only when *gate == 1.  Three kernels (four beyond 4096 cells).
 // kernels keysort_run launches
 int keysort_launches(const KeySort &S);
 int keysort_run(KeySort &S, const int *key, int fine_bits, int *sorted, int *cell_start,

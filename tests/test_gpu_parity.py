@@ -841,10 +841,51 @@ def test_sparse_pairlist_rebuild_through_the_cell_list(kind, aniso, form, monkey
     assert used_cells == 3  # every rebuild after the first one
 
 
+@pytest.mark.parametrize("form", ["rows", "cells"])
+@pytest.mark.parametrize("kind", ["selfCoordNum", "coordNum"])
+def test_sparse_pairlist_of_a_droplet_with_far_outliers(kind, form, monkeypatch):
+    """A dense droplet and a few atoms hundreds of Angstrom away: the bounding box is almost
+    empty, the grid's cells are sized for its mean density, so the droplet sits in a handful of
+    cells with hundreds of atoms each -- the counting sort's rank pass and the row build work on
+    long cells, duplicated coordinates included (equal keys: ties go by atom index)."""
+    cb = _cb()
+    if form == "cells":
+        monkeypatch.setenv("B200CV_NO_ROWS", "1")
+    rng = np.random.default_rng(2024)
+    n1, n2 = (2600, 0) if kind == "selfCoordNum" else (500, 2600)
+    n = n1 + n2
+    pos = rng.normal(0.0, 14.0, (n, 3))            # the droplet
+    far = rng.choice(n, 40, replace=False)
+    pos[far] = rng.random((40, 3)) * 3000.0 - 1500.0  # the outliers
+    dup = rng.choice(np.setdiff1d(np.arange(n), far), 16, replace=False)
+    pos[dup[:8]] = pos[dup[8:]] + np.array([0.0, 2.5, 0.0])  # same x: equal fine keys
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n, dtype=np.int32) if n2 else None
+    tol, freq = 0.01, 2
+    cv = cb.CoordNum(kind, i1, i2, cutoff=3.0, tolerance=tol, pairlist_freq=freq)
+    p = O.make_params((3.0,) * 3, tolerance=tol)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    for step in range(5):
+        frame = np.ascontiguousarray(pos + rng.normal(0, 0.1, pos.shape) * step)
+        v = cv.calc_host(frame, step=step)
+        rebuild = step % freq == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+            close_arr(cv.gradients(2), og2)
+        close_val(v, ov)
+        close_arr(cv.gradients(1), og1)
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64))
+    assert pl.sum() * 50 < npairs  # sparse: the later rebuilds went through the cell order
+
+
 def test_cell_list_rebuild_inside_the_fused_step_graph():
     """b200cv_step keeps one captured graph per flag set; a rebuild exists in two forms (tile
     sweep for the first one, cell list once the list is known to be sparse) and both have to
-    replay correctly, CUB's radix sort included."""
+    replay correctly, the cell sort included."""
     import torch
     cb = _cb()
     rng = np.random.default_rng(5)
