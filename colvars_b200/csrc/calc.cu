@@ -457,7 +457,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     // exact-pair queue (and, on list steps, the extras) on the groups' own arrays: the rows queue
     // atom indices.  Partial sums of the exact kernel at `partials`.
     auto enqueue_row_exact = [&](int exact_flags, bool walk, double *partials, int nparts,
-                                 const int *gate, int gate_on) -> int {
+                                 const int *gate, int gate_on, int blocks = EXACT_BLOCKS) -> int {
       ExactArgs E{};
       E.x1 = x1; E.y1 = y1; E.z1 = z1; E.x2 = x2; E.y2 = y2; E.z2 = z2;
       E.g1x = g1x; E.g1y = g1y; E.g1z = g1z; E.g2x = g2x; E.g2y = g2y; E.g2z = g2z;
@@ -484,7 +484,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
         finalized = true;
       }
       E.P = h->P;
-      CUDA_OK(h, launch_exact(E, stream));
+      CUDA_OK(h, launch_exact(E, stream, blocks));
       h->launches++;
       return B200CV_OK;
     };
@@ -535,7 +535,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       nparts = ndir * ROW_BLOCKS + EXACT_BLOCKS;
       return enqueue_row_exact(build_flags, false, partials + ndir * ROW_BLOCKS, nparts, gate, 1);
     };
-    // list step.  Partial sums: [ROW_BLOCKS | EXACT_BLOCKS]
+    // list step.  Partial sums: [ROW_BLOCKS | ROW_EXACT_BLOCKS]
     auto enqueue_rows_walk = [&](double *partials, const int *gate) -> int {
       CellSort &B = h->sort;
       CUDA_OK(h, cellsort_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
@@ -564,7 +564,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       CUDA_OK(h, launch_row_walk(T, h->exp_special, h->aniso, stream));
       h->launches++;
       return enqueue_row_exact(flags & ~B200CV_EF_REBUILD_PAIRLIST, true, partials + ROW_BLOCKS,
-                               ROW_BLOCKS + EXACT_BLOCKS, gate, 0);
+                               ROW_BLOCKS + ROW_EXACT_BLOCKS, gate, 0, ROW_EXACT_BLOCKS);
     };
 
     if (gated) {
@@ -573,13 +573,13 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       int nparts = 0;
       int rc;
       if (rows_gated) {
-        static_assert(3 * ROW_BLOCKS + 2 * EXACT_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
+        static_assert(3 * ROW_BLOCKS + EXACT_BLOCKS + ROW_EXACT_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
         int nb = 0;
         rc = enqueue_rows_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate(), nb);
         if (rc) return rc;
         rc = enqueue_rows_walk(h->d_partials + nb, h->gate());
         if (rc) return rc;
-        npart = nb + ROW_BLOCKS + EXACT_BLOCKS;
+        npart = nb + ROW_BLOCKS + ROW_EXACT_BLOCKS;
       } else {
         if (cells_usable(h) && sparse_list(h)) {
           // sized and found sparse by b200cv_pairlist_reserve before the capture
@@ -597,7 +597,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       int rc = h->pl_rows ? enqueue_rows_walk(h->d_partials, nullptr)
                           : enqueue_walk(h->d_partials, nullptr);
       if (rc) return rc;
-      npart = h->pl_rows ? ROW_BLOCKS + EXACT_BLOCKS : WALK_BLOCKS;
+      npart = h->pl_rows ? ROW_BLOCKS + ROW_EXACT_BLOCKS : WALK_BLOCKS;
     } else if (rows_eval) {
       int rc = enqueue_rows_build(flags, h->d_partials, nullptr, npart);
       if (rc) return rc;

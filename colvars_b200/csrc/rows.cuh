@@ -39,6 +39,13 @@ namespace b200cv {
 
 constexpr int ROW_THREADS = 128;   // 4 warps per CTA
 constexpr int ROW_BLOCKS = 148 * 8;
+#ifndef B200CV_ROW_EXACT_BLOCKS
+#define B200CV_ROW_EXACT_BLOCKS 592
+#endif
+// CTAs of the exact kernel behind the walk: the extras (the pairs next to a threshold when the
+// list was built, most of them still there) take the reference-order path, a long dependent
+// chain per pair -- one pair per thread
+constexpr int ROW_EXACT_BLOCKS = B200CV_ROW_EXACT_BLOCKS;
 constexpr int ROW_BUF = 512;       // row entries buffered per warp before they are written out
 
 struct RowList {

@@ -1,3 +1,5 @@
+"""calc_value of the selfCoordNum pair-list case (BASELINE config 3 at N atoms), every step:
+GPU time (events), host time to enqueue, host time until the value is there."""
 import sys
 import numpy as np
 import torch
@@ -26,3 +28,6 @@ for step in range(31):
     out.append((step, round(e0.elapsed_time(e1) * 1e3), round((t1 - t0) * 1e6), round((t2 - t0) * 1e6)))
 print("step, gpu us, host enqueue us, host total us")
 print(out)
+lst = [g for st, g, _, _ in out if st > 10 and st % 10]
+reb = [g for st, g, _, _ in out if st > 10 and st % 10 == 0]
+print("list steps gpu us: median", float(np.median(lst)), "min", min(lst), "; rebuild steps:", reb)
