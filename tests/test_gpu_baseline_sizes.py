@@ -88,6 +88,60 @@ def test_c3_selfcoordnum_50k_pairlist_cycle_with_moving_atoms():
     assert launches[1] > launches[0], launches
 
 
+@pytest.mark.parametrize("kind", ["selfCoordNum", "coordNum"])
+def test_rows_longer_than_one_chunk(kind):
+    """A core of 1300 atoms inside one list radius in a dilute gas of 24 k: the list is sparse
+    (0.2 % of the pairs), but every core atom has more than a thousand listed partners -- its
+    row is written as several chunks (ROW_BUF = 512 entries each, csrc/rows.cuh: the row's own
+    slot and overflow chunks behind the per-row slots).  Value, gradients and the bit-exact
+    list over a rebuild through the all-pairs sweep, list steps, a rebuild through the rows
+    and more list steps."""
+    cb = _cb()
+    rng = np.random.default_rng(31)
+    core = rng.normal(0.0, 1.6, (1300, 3)) + 150.0
+    gas = rng.random((24000, 3)) * 300.0
+    if kind == "selfCoordNum":
+        pos0 = np.concatenate([core, gas])
+        rng.shuffle(pos0)
+        n1, n2 = len(pos0), 0
+    else:
+        g1 = np.concatenate([core[:150], gas[:350]])
+        g2 = np.concatenate([core[150:], gas[350:]])
+        rng.shuffle(g1)
+        rng.shuffle(g2)
+        pos0 = np.concatenate([g1, g2])
+        n1, n2 = len(g1), len(g2)
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n1 + n2, dtype=np.int32) if n2 else None
+    tol, freq = 0.01, 3
+    cv = cb.CoordNum(kind, i1, i2, cutoff=4.0, tolerance=tol, pairlist_freq=freq)
+    p = O.make_params((4.0,) * 3, 6, 12, tol)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    nthr = _threads()
+    forms = []
+    for step in range(2 * freq + 1):
+        frame = np.ascontiguousarray(pos0 + rng.normal(0, 0.03, pos0.shape) * step)
+        v = cv.calc_host(frame, step=step)
+        rebuild = step % freq == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame, pairlist=pl, rebuild=rebuild, omp=nthr)
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild,
+                                      omp=nthr)
+            assert _rel(cv.gradients(2), og2) <= RTOL, step
+        assert abs(v - ov) <= RTOL * abs(ov), (step, v, ov)
+        assert _rel(cv.gradients(1), og1) <= RTOL, step
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64)), step
+            forms.append(cv.pairlist_stats())
+    assert pl.sum() * 50 < npairs  # sparse
+    st = forms[-1]
+    assert st["form"] == 2, st                       # neighbour rows
+    rows = n1 + n2 if kind == "coordNum" else n1
+    assert st["row_chunks"] > rows + 200, st          # ... with overflow chunks
+
+
 def test_c4_aniso_fitted_10k_x_500k():
     """BASELINE config 4 as benchmarked: coordNum 10 k x 500 k, cutoff3 (3, 6, 4), group1
     centred and rotated onto its reference positions (fitted on itself, fit gradients on);
