@@ -6,9 +6,10 @@
 // twice, once in the row of each of its atoms (coordNum: rows of group1 atoms hold group2
 // partners and the other way round).  That doubles the pair evaluations of a list step and pays
 // for it several times over: a warp works on one row, 32 partners at a time, with coalesced index
-// loads, partner coordinates that sit next to each other in cell order, no mask and no empty
-// slots, and -- because a row only ever updates the gradient of its own atom -- no atomics and no
-// shuffles in the pair loop: the own gradient is a register sum, reduced once per row.
+// loads, partner coordinates that sit next to each other in cell order, no mask (a row is padded
+// to whole steps with the index of a far-away point, cellsort.cuh) and -- because a row only
+// ever updates the gradient of its own atom -- no atomics and no shuffles in the pair loop: the
+// own gradient is a register sum, reduced once per row.
 //
 //   value      one side of every pair is CANONICAL (selfCoordNum: the partner comes later in cell
 //              order; coordNum: the rows of group1): only there F is added to the scalar.
@@ -26,7 +27,7 @@
 //              cheap pass l2 <= tolerance_l2_max (everything else returns 0 in the reference
 //              before anything is evaluated and is not listed, src/colvarcomp_coordnums.h:256-261),
 //              then the survivors 32 at a time at full lane occupancy: value, own gradient, row.
-//   list step  row_walk_kernel, one warp per row chunk.
+//   list step  row_walk_kernel: one wave of CTAs, a warp per block of consecutive rows (rows.cu).
 // The listed set is: canonical row entries + extras; b200cv_pairlist_export maps it back to
 // canonical indices.
 #pragma once
