@@ -815,9 +815,9 @@ int b200cv_pairlist_reserve(b200cv_cvc *h, const double *d_pos1, const double *d
     h->pl_cap = want;
   }
   if (rows_usable(h) && sparse_list(h)) {
-    // the row form: two entries per listed pair, one chunk per atom and per ROW_BUF entries
-    // (every chunk padded to a multiple of 32 entries)
-    double const ent = headroom * 2.0 * (double)h->pl_n + 32.0 * (double)row_slots(h) + 65536.0;
+    // the row form: one entry per listed pair, one chunk per atom of group1 and per ROW_BUF
+    // entries (every chunk padded to a multiple of 32 entries)
+    double const ent = headroom * (double)h->pl_n + 32.0 * (double)row_slots(h) + 65536.0;
     double const chk = (double)row_slots(h) + headroom * ent / ROW_BUF + 4096.0;
     if ((unsigned)std::min(4.0e9, ent) > h->rows.cap_idx ||
         (unsigned)std::min(4.0e9, chk) > h->rows.cap_chunks) {
@@ -993,20 +993,15 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
     SortedGroup &I = h->self() ? J : B.side[0];
     unsigned counts[8];
     CUDA_OK(h, cudaMemcpy(counts, B.d_counts, sizeof(counts), cudaMemcpyDeviceToHost));
-    // valid slots: this rank's rows of each group, then the overflow chunks
+    // valid slots: this rank's rows, then the overflow chunks
     std::vector<int4> all((size_t)h->rows.cap_chunks), chunks;
     CUDA_OK(h, cudaMemcpy(all.data(), h->rows.d_chunks, sizeof(int4) * all.size(),
                           cudaMemcpyDeviceToHost));
     {
       size_t const slots = row_slots(h);
-      int const ns[2] = {I.n, h->self() ? 0 : J.n};
-      size_t base = 0;
-      for (int d = 0; d < 2; d++) {
-        size_t const r0 = (size_t)ns[d] * (size_t)h->rank / (size_t)h->world;
-        size_t const r1 = (size_t)ns[d] * ((size_t)h->rank + 1) / (size_t)h->world;
-        for (size_t r = r0; r < r1; r++) chunks.push_back(all[base + r]);
-        base += (size_t)ns[d];
-      }
+      size_t const r0 = (size_t)I.n * (size_t)h->rank / (size_t)h->world;
+      size_t const r1 = (size_t)I.n * ((size_t)h->rank + 1) / (size_t)h->world;
+      for (size_t r = r0; r < r1; r++) chunks.push_back(all[r]);
       size_t const extra = std::min<size_t>(counts[6], all.size() > slots ? all.size() - slots : 0);
       for (size_t x = 0; x < extra; x++) chunks.push_back(all[slots + x]);
     }
@@ -1026,14 +1021,11 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
       CUDA_OK(h, cudaMemcpy(idx.data(), h->rows.d_idx, sizeof(int) * used, cudaMemcpyDeviceToHost));
     }
     for (auto const &c : chunks) {
-      int const p = c.x, start = c.y, len = c.z, dir = c.w;
-      bool const self = h->self();
-      if (!self && dir != 0) continue;  // the rows of group2 repeat the pairs of group1's rows
+      int const p = c.x, start = c.y, len = c.z;
       if (len <= 0 || (size_t)start + (size_t)len > used) continue;
       for (int e = start; e < start + len; e++) {
         int const q = idx[(size_t)e];
-        if (q >= J.n) continue;        // padding (the far-away point, cellsort.cuh)
-        if (self && q <= p) continue;  // listed from the other atom's row
+        if (q >= J.n) continue;  // padding (the far-away point, cellsort.cuh)
         if (k >= count) return fail(h, B200CV_BUG_ERROR, "inconsistent row list");
         out[k++] = canonical((unsigned long long)oi[(size_t)p], (unsigned long long)oj[(size_t)q]);
       }

@@ -108,19 +108,19 @@ bool rebuild_with_rows(const b200cv_cvc *h, int flags)
          rows_usable(h) && h->pl_valid && !(h->gated) && sparse_list(h);
 }
 
-// chunk slots taken by the rows themselves (one per atom of both groups); overflow chunks follow
+// chunk slots taken by the rows themselves (one per atom of group1); overflow chunks follow
 unsigned row_slots(const b200cv_cvc *h)
 {
-  return (unsigned)h->g[0].n + (h->self() ? 0u : (unsigned)h->g[1].n);
+  return (unsigned)h->g[0].n;
 }
 
-// entries / chunks the rows of the next rebuild may need: two entries per listed pair (one per
-// direction), one chunk per atom plus one per ROW_BUF entries; a guess that turns out too small
-// costs one redo of the step
+// entries / chunks the rows of the next rebuild may need: one entry per listed pair, one chunk
+// per atom of group1 plus one per ROW_BUF entries; a guess that turns out too small costs one redo
+// of the step
 static void row_estimate(const b200cv_cvc *h, unsigned &entries, unsigned &chunks)
 {
-  unsigned long long const atoms = (unsigned long long)h->g[0].n + (h->self() ? 0ull : (unsigned long long)h->g[1].n);
-  unsigned long long const e = 2ull * h->pl_n + h->pl_n / 2ull + 32ull * atoms + 65536ull;  // chunks are padded to 32
+  unsigned long long const atoms = (unsigned long long)h->g[0].n;
+  unsigned long long const e = h->pl_n + h->pl_n / 4ull + 32ull * atoms + 65536ull;  // chunks are padded to 32
   unsigned long long const c = atoms + e / (unsigned long long)ROW_BUF + 4096ull;
   entries = (unsigned)std::min<unsigned long long>(e, 0xfffffff0ull);
   chunks = (unsigned)std::min<unsigned long long>(c, 0xfffffff0ull);
@@ -451,8 +451,10 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
     auto row_sides = [&](RowSideView &s1, RowSideView &s2) {
       SortedGroup &J = h->sort.side[1];
       SortedGroup &I = h->self() ? J : h->sort.side[0];
-      s1 = RowSideView{I.d_xs, I.d_ys, I.d_zs, I.d_sorted, I.d_cell_start, I.n, G1.d_grad, G1.stride};
-      s2 = RowSideView{J.d_xs, J.d_ys, J.d_zs, J.d_sorted, J.d_cell_start, J.n, G2.d_grad, G2.stride};
+      s1 = RowSideView{I.d_xs, I.d_ys, I.d_zs, I.d_sorted, I.d_cell_start, I.n, G1.d_grad, G1.stride,
+                       I.d_gs, I.gs_stride};
+      s2 = RowSideView{J.d_xs, J.d_ys, J.d_zs, J.d_sorted, J.d_cell_start, J.n, G2.d_grad, G2.stride,
+                       J.d_gs, J.gs_stride};
     };
     // exact-pair queue (and, on list steps, the extras) on the groups' own arrays: the rows queue
     // atom indices.  Partial sums of the exact kernel at `partials`.
@@ -464,6 +466,15 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       E.list = h->d_rare;
       E.count32 = h->rare_count();
       E.cap = h->rare_cap;
+      {
+        // what the rows added to their partners: group2 (selfCoordNum: the group) in cell order
+        SortedGroup const &J = h->sort.side[1];
+        E.gs = J.d_gs;
+        E.gs_stride = J.gs_stride;
+        E.gs_sorted = J.d_sorted;
+        E.gs_n = J.n;
+        E.gs_group = h->self() ? 1 : 2;
+      }
       if (walk) {
         E.list2 = h->d_pl;
         E.count2 = h->pl_count() + 1;  // persistent length of the extras
@@ -488,7 +499,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       h->launches++;
       return B200CV_OK;
     };
-    // rebuild.  Partial sums: [ROW_BLOCKS (| ROW_BLOCKS for the rows of group2) | EXACT_BLOCKS]
+    // rebuild.  Partial sums: [ROW_BLOCKS | EXACT_BLOCKS]
     auto enqueue_rows_build = [&](int build_flags, double *partials, const int *gate,
                                   int &nparts) -> int {
       CellSort &B = h->sort;
@@ -499,29 +510,25 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       h->launches++;
       RowSideView s1, s2;
       row_sides(s1, s2);
-      int const ndir = h->self() ? 1 : 2;
-      for (int dir = 0; dir < ndir; dir++) {
+      {
         RowBuildArgs T{};
-        T.own = dir == 0 ? s1 : s2;
-        T.nbr = (h->self() || dir == 1) ? s1 : s2;
+        T.own = s1;
+        T.nbr = h->self() ? s1 : s2;
         T.grid = B.d_grid;
         T.self = h->self() ? 1 : 0;
-        T.canonical = dir == 0 ? 1 : 0;
-        T.own_is_group1 = dir == 0 ? 1 : 0;
-        T.dir = dir;
         T.row_begin = (int)((long long)T.own.n * h->rank / h->world);
         T.row_end = (int)((long long)T.own.n * (h->rank + 1) / h->world);
         T.idx = h->rows.d_idx;
         T.cap_idx = h->rows.cap_idx;
         T.chunks = h->rows.d_chunks;
         T.cap_chunks = h->rows.cap_chunks;
-        T.chunk_base = dir == 0 ? 0u : (unsigned)s1.n;
+        T.chunk_base = 0u;
         T.chunk_extra = row_slots(h);
         T.counts = B.d_counts;
         T.rare = h->d_rare;
         T.rare_cap = h->rare_cap;
         T.rare_count = h->rare_count();
-        T.partials = partials + dir * ROW_BLOCKS;
+        T.partials = partials;
         T.want_grad = grad ? 1 : 0;
         cell_cutoffs(h, T.cut);
         for (int d = 0; d < 3; d++) T.cut[d] *= (1.0 + 1.0e-9);
@@ -532,8 +539,8 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       }
       h->pl_rows = true;
       h->pl_sorted = false;
-      nparts = ndir * ROW_BLOCKS + EXACT_BLOCKS;
-      return enqueue_row_exact(build_flags, false, partials + ndir * ROW_BLOCKS, nparts, gate, 1);
+      nparts = ROW_BLOCKS + EXACT_BLOCKS;
+      return enqueue_row_exact(build_flags, false, partials + ROW_BLOCKS, nparts, gate, 1);
     };
     // list step.  Partial sums: [ROW_BLOCKS | ROW_EXACT_BLOCKS]
     auto enqueue_rows_walk = [&](double *partials, const int *gate) -> int {
@@ -541,17 +548,16 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       CUDA_OK(h, cellsort_gather(B, x1, y1, z1, x2, y2, z2, gate, 0, stream));
       h->launches++;
       RowWalkArgs T{};
-      row_sides(T.side[0], T.side[1]);
+      RowSideView s1, s2;
+      row_sides(s1, s2);
+      T.own = s1;
+      T.nbr = h->self() ? s1 : s2;
       T.self = h->self() ? 1 : 0;
       T.idx = h->rows.d_idx;
       T.chunks = h->rows.d_chunks;
       T.cap_chunks = h->rows.cap_chunks;
-      for (int d = 0; d < 2; d++) {
-        int const n = T.side[d].n;
-        T.row_begin[d] = (int)((long long)n * h->rank / h->world);
-        T.row_end[d] = (int)((long long)n * (h->rank + 1) / h->world);
-      }
-      T.chunk_base1 = (unsigned)T.side[0].n;
+      T.row_begin = (int)((long long)T.own.n * h->rank / h->world);
+      T.row_end = (int)((long long)T.own.n * (h->rank + 1) / h->world);
       T.chunk_extra = row_slots(h);
       T.counts = B.d_counts;
       T.rare = h->d_rare;
@@ -573,7 +579,7 @@ int enqueue_calc(b200cv_cvc *h, int flags, cudaStream_t stream)
       int nparts = 0;
       int rc;
       if (rows_gated) {
-        static_assert(3 * ROW_BLOCKS + EXACT_BLOCKS + ROW_EXACT_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
+        static_assert(2 * ROW_BLOCKS + EXACT_BLOCKS + ROW_EXACT_BLOCKS <= PARTIALS_TAIL, "partials are sized for PARTIALS_TAIL");
         int nb = 0;
         rc = enqueue_rows_build(flags | B200CV_EF_REBUILD_PAIRLIST, h->d_partials, h->gate(), nb);
         if (rc) return rc;

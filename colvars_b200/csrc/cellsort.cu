@@ -159,8 +159,8 @@ __global__ void sort_gather_kernel(const double *__restrict__ x1, const double *
                                    int n1, double *xs1, double *ys1, double *zs1,
                                    const double *__restrict__ x2, const double *__restrict__ y2,
                                    const double *__restrict__ z2, const int *__restrict__ s2,
-                                   int n2, double *xs2, double *ys2, double *zs2,
-                                   int blocks1, const int *gate, int gate_on)
+                                   int n2, double *xs2, double *ys2, double *zs2, double *gs2,
+                                   size_t gs_stride2, int blocks1, const int *gate, int gate_on)
 {
   if (gate != nullptr && *gate != gate_on) return;
   if ((int)blockIdx.x < blocks1) {
@@ -173,8 +173,12 @@ __global__ void sort_gather_kernel(const double *__restrict__ x1, const double *
     zs1[p] = z1[i];
   } else {
     int const p = ((int)blockIdx.x - blocks1) * blockDim.x + threadIdx.x;
-    if (p == 0) xs2[n2] = ys2[n2] = zs2[n2] = SORT_FAR;
+    if (p == 0) {
+      xs2[n2] = ys2[n2] = zs2[n2] = SORT_FAR;
+      gs2[n2] = gs2[gs_stride2 + n2] = gs2[2 * gs_stride2 + n2] = 0.0;
+    }
     if (p >= n2) return;
+    gs2[p] = gs2[gs_stride2 + p] = gs2[2 * gs_stride2 + p] = 0.0;
     int const j = s2[p];
     xs2[p] = x2[j];
     ys2[p] = y2[j];
@@ -191,6 +195,7 @@ void side_free(SortedGroup &S)
   cudaFree(S.d_xs);
   cudaFree(S.d_ys);
   cudaFree(S.d_zs);
+  cudaFree(S.d_gs);
   S = SortedGroup();
 }
 
@@ -206,6 +211,9 @@ int side_setup(SortedGroup &S, int n, int cell_bits)
   if ((e = cudaMalloc(&S.d_xs, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&S.d_ys, nbd)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&S.d_zs, nbd)) != cudaSuccess) return (int)e;
+  S.gs_stride = ((size_t)std::max(n, 1) + 2) & ~(size_t)1;
+  if ((e = cudaMalloc(&S.d_gs, 3 * sizeof(double) * S.gs_stride)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemset(S.d_gs, 0, 3 * sizeof(double) * S.gs_stride)) != cudaSuccess) return (int)e;
   if ((e = cudaMalloc(&S.d_cell_start, sizeof(int) * (((size_t)1 << cell_bits) + 2))) != cudaSuccess) {
     return (int)e;
   }
@@ -296,7 +304,8 @@ int cellsort_gather(CellSort &B, const double *x1, const double *y1, const doubl
   int const b1 = B.self ? 0 : (I.n + 255) / 256, b2 = (J.n + 255) / 256;
   sort_gather_kernel<<<b1 + b2, 256, 0, stream>>>(x1, y1, z1, I.d_sorted, B.self ? 0 : I.n, I.d_xs,
                                                   I.d_ys, I.d_zs, x2, y2, z2, J.d_sorted, J.n,
-                                                  J.d_xs, J.d_ys, J.d_zs, b1, gate, gate_on);
+                                                  J.d_xs, J.d_ys, J.d_zs, J.d_gs, J.gs_stride, b1, gate,
+                                                  gate_on);
   note_launch();
   return (int)cudaGetLastError();
 }

@@ -48,6 +48,10 @@ struct SortedGroup {
   int *d_cell_start = nullptr;  // [2^cell_bits + 2]
   KeySort sort;
   double *d_xs = nullptr, *d_ys = nullptr, *d_zs = nullptr;  // coordinates in sorted order
+  // gradient contributions the rows of the OTHER atoms make to this group's atoms (rows.cuh):
+  // 3 planes of gs_stride in sorted order, unscaled (sum of gq * d), zeroed by the per-step gather
+  double *d_gs = nullptr;
+  size_t gs_stride = 0;
 };
 
 struct CellSort {

@@ -117,6 +117,21 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_kernel(const __grid_const
   }
   bool const grad = A.flags & EF_GRADIENTS;
   bool const rebuild = (A.flags & EF_REBUILD_PAIRLIST) && A.pl;
+  if (A.gs != nullptr && grad) {
+    // the partner shares of the neighbour rows (rows.cuh): cell order -> the group's gradient
+    double *const tx = A.gs_group == 1 ? A.g1x : A.g2x;
+    double *const ty = A.gs_group == 1 ? A.g1y : A.g2y;
+    double *const tz = A.gs_group == 1 ? A.g1z : A.g2z;
+    for (int p = blockIdx.x * EXACT_THREADS + threadIdx.x; p < A.gs_n; p += gridDim.x * EXACT_THREADS) {
+      double const sx = A.gs[p], sy = A.gs[A.gs_stride + p], sz = A.gs[2 * A.gs_stride + p];
+      if (sx != 0.0 || sy != 0.0 || sz != 0.0) {
+        int const atom = A.gs_sorted[p];
+        atomicAdd(&tx[atom], A.P.c_grad[0] * sx);
+        atomicAdd(&ty[atom], A.P.c_grad[1] * sy);
+        atomicAdd(&tz[atom], A.P.c_grad[2] * sz);
+      }
+    }
+  }
   double fsum = 0.0;
   // warp-uniform trip count: the group1 gradients of a warp's 32 entries are summed per run of
   // equal rows before they go to memory (a list rebuilt through the cell list is made of such

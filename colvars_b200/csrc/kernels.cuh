@@ -77,6 +77,13 @@ struct ExactArgs {
   const unsigned long long *list2;
   const unsigned long long *count2;
   unsigned long long cap2;
+  // row form of the list (rows.cuh): what the rows added to their partners, in cell order and
+  // unscaled -- added to the gradient of group `gs_group` (1 or 2) before anything else, or NULL
+  const double *gs;
+  size_t gs_stride;
+  const int *gs_sorted;                // atom at a sorted position
+  int gs_n;
+  int gs_group;
   double *partials;                    // one per CTA
   unsigned long long *pl;              // pair list to append to on rebuild (or NULL)
   unsigned long long pl_cap;

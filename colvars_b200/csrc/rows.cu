@@ -168,6 +168,11 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
     int const iz_hi = sort_cell(zo + A.cut[2], g.origin[2], g.inv_cell[2], g.dim[2]);
     int const nry = iy_hi - iy_lo + 1;
     int const nspan = nry * (iz_hi - iz_lo + 1);
+    // selfCoordNum: a pair belongs to the row of its atom that comes first in cell order, so
+    // only partners behind the own position are looked at (the rows of cells in front of the
+    // own one are skipped as a whole)
+    int const iy_own = sort_cell(yo, g.origin[1], g.inv_cell[1], g.dim[1]);
+    int const iz_own = sort_cell(zo, g.origin[2], g.inv_cell[2], g.dim[2]);
     double gx = 0.0, gy = 0.0, gz = 0.0;
     int nst = 0;        // staged partners (warp-uniform)
     int rlen = 0;       // buffered row entries (warp-uniform)
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
           for (int k = lane; k < plen; k += 32) A.idx[start + k] = k < rlen ? R[k] : A.nbr.n;
         }
         if (lane == 0 && c < A.cap_chunks) {
-          A.chunks[c] = make_int4(p, (int)start, fits ? plen : 0, A.dir);
+          A.chunks[c] = make_int4(p, (int)start, fits ? plen : 0, 0);
         }
         __syncwarp();
         rlen = 0;
@@ -207,16 +212,21 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       double F, gq;
       bool rare;
       row_pair<EXP, ANISO>(P, K, dx, dy, dz, valid ? -1 : 0, F, gq, rare);
-      fsum += F;  // both sides of a selfCoordNum pair: halved at the end
-      gx = fma(gq, dx, gx);
-      gy = fma(gq, dy, gy);
-      gz = fma(gq, dz, gz);
+      fsum += F;
+      double const tx = gq * dx, ty = gq * dy, tz = gq * dz;
+      gx += tx;
+      gy += ty;
+      gz += tz;
+      if (A.want_grad && valid) {
+        // the partner's share (unscaled, in cell order; exact_kernel adds it to the group)
+        atomicAdd(&A.nbr.gs[q], tx);
+        atomicAdd(&A.nbr.gs[A.nbr.gs_stride + q], ty);
+        atomicAdd(&A.nbr.gs[2 * A.nbr.gs_stride + q], tz);
+      }
       if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) {
-        // the canonical side hands the pair to exact_kernel
-        bool const mine = rare && (A.self ? (q > p) : (A.canonical != 0));
-        int const nbr_atom = mine ? A.nbr.sorted[q] : 0;
-        rare_push(RQ, nrq, mine, A.own_is_group1 ? own_atom : nbr_atom,
-                  A.own_is_group1 ? nbr_atom : own_atom, A.rare, A.rare_cap, A.rare_count, lane);
+        // pairs next to a threshold go to exact_kernel
+        int const nbr_atom = rare ? A.nbr.sorted[q] : 0;
+        rare_push(RQ, nrq, rare, own_atom, nbr_atom, A.rare, A.rare_cap, A.rare_count, lane);
       }
       // in the row: listed by the sign of the shifted function; pairs next to a threshold are
       // listed (or not) by exact_kernel and live in the extras
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       unsigned const ml = __ballot_sync(0xffffffffu, listed);
       if (listed) R[rlen + __popc(ml & lt)] = q;
       rlen += __popc(ml);
-      npairs += (listed && (!A.self || q > p)) ? 1ull : 0ull;  // the canonical side counts the pair
+      npairs += listed ? 1ull : 0ull;
       __syncwarp();
       if (rlen > ROW_BUF - 32) flush(false);
     };
@@ -253,6 +263,11 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
           int const row = (iz * g.dim[1] + iy) * g.dim[0];
           begin = A.nbr.cell_start[row + ix_lo];
           end = A.nbr.cell_start[row + ix_hi + 1];
+          if (A.self) {
+            bool const before = iz < iz_own || (iz == iz_own && iy < iy_own);
+            if (before) end = begin;
+            else if (iz == iz_own && iy == iy_own) begin = max(begin, p + 1);
+          }
         }
       }
       int const nsp = min(32, nspan - base);
@@ -274,8 +289,8 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
             ub = pair_l2<ANISO, BC_NONE>(P, dx, dy, dz);
             pb = true;
           }
-          pa = pa && (ua <= l2_pass) && !(A.self && qa == p);
-          pb = pb && (ub <= l2_pass) && !(A.self && qb == p);
+          pa = pa && (ua <= l2_pass);
+          pb = pb && (ub <= l2_pass);
           unsigned const ma = __ballot_sync(0xffffffffu, pa);
           unsigned const mb = __ballot_sync(0xffffffffu, pb);
           if ((ma | mb) == 0u) continue;
@@ -329,11 +344,8 @@ __global__ void __launch_bounds__(ROW_THREADS) row_build_kernel(const __grid_con
       s += red[w];
       np += redn[w];
     }
-    // selfCoordNum: every pair was seen from both of its atoms; coordNum: the scalar and the pair
-    // count belong to the rows of group1
-    bool const counts = A.self || A.canonical != 0;
-    A.partials[blockIdx.x] = A.self ? 0.5 * s : (counts ? s : 0.0);
-    if (np && counts) atomicAdd(reinterpret_cast<unsigned long long *>(A.counts + 4), np);
+    A.partials[blockIdx.x] = s;
+    if (np) atomicAdd(reinterpret_cast<unsigned long long *>(A.counts + 4), np);
   }
 }
 
@@ -394,15 +406,16 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
   }
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   PairParams const &P = A.P;
-  // work items: the rows of this rank (group1's, then group2's), then the overflow chunks; a
-  // warp takes a block of consecutive items (see row_build_kernel)
+  // work items: the rows of this rank, then the overflow chunks; a warp takes a block of
+  // consecutive items (see row_build_kernel)
   unsigned nextra = A.counts[6];
   if (A.chunk_extra + nextra > A.cap_chunks) {
     nextra = A.cap_chunks > A.chunk_extra ? A.cap_chunks - A.chunk_extra : 0u;
   }
-  unsigned const n0 = (unsigned)(A.row_end[0] - A.row_begin[0]);
-  unsigned const n1 = A.self ? 0u : (unsigned)(A.row_end[1] - A.row_begin[1]);
-  unsigned const total = n0 + n1 + nextra;
+  unsigned const n0 = (unsigned)(A.row_end - A.row_begin);
+  unsigned const total = n0 + nextra;
+  RowSideView const &O = A.own;
+  RowSideView const &N = A.nbr;
   double fsum = 0.0;
   unsigned const gwarp = blockIdx.x * WARPS + warp, nwarps = gridDim.x * WARPS;
   unsigned const per = (total + nwarps - 1) / nwarps;
@@ -421,9 +434,7 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
 
   auto header = [&](unsigned t) -> int4 {
     if (t >= t_last) return make_int4(0, 0, 0, 0);
-    unsigned const slot = t < n0 ? (unsigned)A.row_begin[0] + t
-                                 : (t < n0 + n1 ? A.chunk_base1 + (unsigned)A.row_begin[1] + (t - n0)
-                                                : A.chunk_extra + (t - n0 - n1));
+    unsigned const slot = t < n0 ? (unsigned)A.row_begin + t : A.chunk_extra + (t - n0);
     return A.chunks[slot];
   };
   // indices of a chunk into one of the warp's two buffers (asynchronously)
@@ -439,11 +450,10 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
   double nxo = 0.0, nyo = 0.0, nzo = 0.0;
   int nown = 0;
   if (t_first < t_last) {
-    RowSideView const &O1 = A.side[A.self ? 0 : h1.w];
-    nxo = O1.xs[h1.x];
-    nyo = O1.ys[h1.x];
-    nzo = O1.zs[h1.x];
-    nown = O1.sorted[h1.x];
+    nxo = O.xs[h1.x];
+    nyo = O.ys[h1.x];
+    nzo = O.zs[h1.x];
+    nown = O.sorted[h1.x];
   }
   for (unsigned t = t_first; t < t_last; t++) {
     int4 const ch = h1;
@@ -454,19 +464,18 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
     h2 = header(t + 2);
     prefetch(h1, buf ^ 1);  // (an empty group past the last row)
     if (t + 1 < t_last) {
-      RowSideView const &O1 = A.side[A.self ? 0 : h1.w];
-      nxo = O1.xs[h1.x];
-      nyo = O1.ys[h1.x];
-      nzo = O1.zs[h1.x];
-      nown = O1.sorted[h1.x];
+      nxo = O.xs[h1.x];
+      nyo = O.ys[h1.x];
+      nzo = O.zs[h1.x];
+      nown = O.sorted[h1.x];
     }
     cp_async_wait<1>();  // this row's indices have landed (the next row's may still be in flight)
     __syncwarp();
-    int const p = ch.x, len = min(ch.z, ROW_BUF), dir = ch.w;  // len: a multiple of 32
+    int const len = min(ch.z, ROW_BUF);  // a multiple of 32
     if (len > 0) {
-      RowSideView const &O = A.side[A.self ? 0 : dir];
-      RowSideView const &N = A.side[A.self ? 0 : 1 - dir];
       const double *const nx = N.xs, *const ny = N.ys, *const nz = N.zs;
+      double *const gsx = N.gs, *const gsy = N.gs + N.gs_stride, *const gsz = N.gs + 2 * N.gs_stride;
+      int const nbr_n = N.n;
       const int *const qp = sidx[warp][buf] + lane;
       double gx = 0.0, gy = 0.0, gz = 0.0, rsum = 0.0;
       auto load = [&](int k, double &x, double &y, double &z) {
@@ -475,22 +484,29 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
         y = ny[q];
         z = nz[q];
       };
-      auto eval = [&](double x, double y, double z, bool &rare) {
+      // one pair: the own atom's share stays in registers, the partner's (unscaled, in cell
+      // order; exact_kernel adds it to the group) goes out as three reductions
+      auto eval = [&](int k, double x, double y, double z, bool &rare) {
         double const dx = x - xo, dy = y - yo, dz = z - zo;
         double F, gq;
         row_pair<EXP, ANISO>(P, K, dx, dy, dz, -1, F, gq, rare);
         rsum += F;
-        gx = fma(gq, dx, gx);
-        gy = fma(gq, dy, gy);
-        gz = fma(gq, dz, gz);
+        double const tx = gq * dx, ty = gq * dy, tz = gq * dz;
+        gx += tx;
+        gy += ty;
+        gz += tz;
+        int const q = qp[k];
+        if (A.want_grad && q != nbr_n) {  // (not the padding: every row would add to one address)
+          atomicAdd(&gsx[q], tx);
+          atomicAdd(&gsy[q], ty);
+          atomicAdd(&gsz[q], tz);
+        }
       };
-      // the canonical side hands a pair next to a threshold to exact_kernel
+      // a pair next to a threshold goes to exact_kernel
       auto queue = [&](int k, bool rare) {
         int const q = qp[k];
-        bool const mine = rare && (A.self ? (q > p) : (dir == 0));
-        int const nbr_atom = mine ? N.sorted[q] : 0;
-        rare_push(RQ, nrq, mine, dir == 0 ? own_atom : nbr_atom, dir == 0 ? nbr_atom : own_atom,
-                  A.rare, A.rare_cap, A.rare_count, lane);
+        int const nbr_atom = rare ? N.sorted[q] : 0;
+        rare_push(RQ, nrq, rare, own_atom, nbr_atom, A.rare, A.rare_cap, A.rare_count, lane);
       };
       double ax0, ay0, az0, ax1 = 0.0, ay1 = 0.0, az1 = 0.0;
       load(0, ax0, ay0, az0);
@@ -501,8 +517,8 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
         if (k + 64 < len) load(k + 64, bx0, by0, bz0);
         if (k + 96 < len) load(k + 96, bx1, by1, bz1);
         bool r0, r1;
-        eval(ax0, ay0, az0, r0);
-        eval(ax1, ay1, az1, r1);
+        eval(k, ax0, ay0, az0, r0);
+        eval(k + 32, ax1, ay1, az1, r1);
         if (__builtin_expect(__any_sync(0xffffffffu, r0 || r1), 0)) {
           queue(k, r0);
           queue(k + 32, r1);
@@ -512,12 +528,10 @@ __global__ void __launch_bounds__(ROW_THREADS, B200CV_ROW_MINB) row_walk_kernel(
       }
       if (k < len) {
         bool r0;
-        eval(ax0, ay0, az0, r0);
+        eval(k, ax0, ay0, az0, r0);
         if (__builtin_expect(__any_sync(0xffffffffu, r0), 0)) queue(k, r0);
       }
-      // the scalar: both sides of a selfCoordNum pair are in rows (half each), a coordNum pair
-      // counts in the row of its group1 atom
-      fsum += A.self ? 0.5 * rsum : (dir == 0 ? rsum : 0.0);
+      fsum += rsum;
       if (A.want_grad) {
         double const g = warp_sum3(gx, gy, gz, lane);
         if ((lane & 7) == 0 && lane < 24) {

@@ -1,35 +1,40 @@
 // rows.cuh -- the pair list as neighbour ROWS (open systems; the sparse-list form).
 //
 // The reference keeps one bool per pair (src/colvarcomp_coordnums.cpp:147-151) and, between
-// rebuilds, evaluates exactly the pairs whose bool is set (:219-228).  Here every atom owns a row:
-// the sorted positions (cell order, cellsort.cuh) of ALL its listed partners, so a pair appears
-// twice, once in the row of each of its atoms (coordNum: rows of group1 atoms hold group2
-// partners and the other way round).  That doubles the pair evaluations of a list step and pays
-// for it several times over: a warp works on one row, 32 partners at a time, with coalesced index
-// loads, partner coordinates that sit next to each other in cell order, no mask (a row is padded
-// to whole steps with the index of a far-away point, cellsort.cuh) and -- because a row only
-// ever updates the gradient of its own atom -- no atomics and no shuffles in the pair loop: the
-// own gradient is a register sum, reduced once per row.
+// rebuilds, evaluates exactly the pairs whose bool is set (:219-228).  Here the listed pairs are
+// kept as rows: the atoms of group1 (selfCoordNum: of the group) each own the sorted positions
+// (cell order, cellsort.cuh) of their listed partners in group2 (selfCoordNum: of the partners
+// BEHIND them in cell order), so every listed pair is one entry of one row.  A warp works on one
+// row, 32 partners at a time, with coalesced index loads, partner coordinates that sit next to
+// each other in cell order and no mask (a row is padded to whole steps with the index of a
+// far-away point, cellsort.cuh).
 //
-//   value      one side of every pair is CANONICAL (selfCoordNum: the partner comes later in cell
-//              order; coordNum: the rows of group1): only there F is added to the scalar.
-//   gradient   own atom: -c_grad * gq * (x_partner - x_own), the same expression on both sides
+//   value      F of every entry.
+//   gradient   own atom: -c_grad * sum gq * (x_partner - x_own), a register sum reduced once per
+//              row; partner: + the same term, added (unscaled) to a gradient buffer in cell order
+//              (SortedGroup::d_gs, three reductions per entry that fall into a few sectors),
+//              which exact_kernel adds to the group's gradient afterwards
 //              (the reference's -G for group1 and +G for group2, src/colvarcomp_coordnums.h:267-277).
+//              [The first form of the rows kept every pair in the rows of BOTH its atoms -- no
+//              reductions in the pair loop, twice the entries, group2 rows as well; measured:
+//              the three reductions per pair cost less than the second evaluation, and the
+//              rebuild searches half the cells.]
 //   rare pairs next to a decision threshold (pair_is_rare, pair_math.cuh) contribute nothing in a
-//              row; the canonical side queues them (atom indices) for exact_kernel, which evaluates
-//              them in the reference's operation order and updates both atoms; they are never
-//              row entries.  |l2 - 1| < 2^-4 pairs are listed for certain (F ~ 1/2), pairs inside the
-//              window around tolerance_l2_max are listed by exact_kernel's own decision.  What
+//              row; they are queued (atom indices) for exact_kernel, which evaluates them in the
+//              reference's operation order and updates both atoms; they are never row entries.
+//              |l2 - 1| < 2^-4 pairs are listed for certain (F ~ 1/2), pairs inside the window
+//              around tolerance_l2_max are listed by exact_kernel's own decision.  What
 //              exact_kernel lists on a rebuild becomes the EXTRAS (packed (i << 32 | j) entries,
 //              atom indices), evaluated by every list step next to the rows.
 //   rebuild    row_build_kernel, one warp per atom: partners from the neighbouring rows of cells
-//              (x-range per row of cells from the distance of the atom to that row), first a
-//              cheap pass l2 <= tolerance_l2_max (everything else returns 0 in the reference
-//              before anything is evaluated and is not listed, src/colvarcomp_coordnums.h:256-261),
-//              then the survivors 32 at a time at full lane occupancy: value, own gradient, row.
+//              (x-range per row of cells from the distance of the atom to that row;
+//              selfCoordNum: only what lies behind the atom in cell order), first a cheap pass
+//              l2 <= tolerance_l2_max (everything else returns 0 in the reference before
+//              anything is evaluated and is not listed, src/colvarcomp_coordnums.h:256-261), then
+//              the survivors 32 at a time at full lane occupancy: value, gradients, row.
 //   list step  row_walk_kernel: one wave of CTAs, a warp per block of consecutive rows (rows.cu).
-// The listed set is: canonical row entries + extras; b200cv_pairlist_export maps it back to
-// canonical indices.
+// The listed set is: row entries + extras; b200cv_pairlist_export maps it back to canonical
+// indices.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -52,8 +57,8 @@ constexpr int ROW_BUF = 512;       // row entries buffered per warp before they 
 struct RowList {
   int *d_idx = nullptr;        // partner positions (cell order of the partner's group)
   unsigned cap_idx = 0;
-  // {own position, start, length, direction}: one slot per row -- group1's rows first, then
-  // group2's -- and behind them the overflow chunks of rows with more than ROW_BUF entries
+  // {own position, start, length, 0}: one slot per row and behind them the overflow chunks of
+  // rows with more than ROW_BUF entries
   int4 *d_chunks = nullptr;
   unsigned cap_chunks = 0;
   // counters live in CellSort::d_counts: [0] overflow chunks of this build, [3] entries of this
@@ -68,22 +73,21 @@ struct RowSideView {
   int n;
   double *grad;                // the group's gradient planes (atom order)
   size_t gstride;
+  double *gs;                  // partner shares in cell order (SortedGroup::d_gs), 3 planes
+  size_t gs_stride;
 };
 
 struct RowBuildArgs {
   RowSideView own, nbr;
   const SortGrid *grid;
-  int self;                    // own == nbr: skip the atom itself, canonical = partner later
-  int canonical;               // coordNum: 1 for the rows of group1, 0 for the rows of group2
-  int own_is_group1;           // rare-queue entries are (group1 atom << 32 | group2 atom)
-  int dir;                     // stored in the chunk: which way the walk reads own / nbr
+  int self;                    // own == nbr: partners behind the own position only
   int row_begin, row_end;      // rows (sorted positions of the own group) of this rank
   int *idx;
   unsigned cap_idx;
   int4 *chunks;
   unsigned cap_chunks;
-  unsigned chunk_base;         // slot of this group's row 0
-  unsigned chunk_extra;        // first overflow slot (= number of rows of both groups)
+  unsigned chunk_base;         // slot of row 0
+  unsigned chunk_extra;        // first overflow slot (= number of rows)
   unsigned *counts;            // CellSort::d_counts
   unsigned long long *rare;
   unsigned int rare_cap;
@@ -96,14 +100,13 @@ struct RowBuildArgs {
 };
 
 struct RowWalkArgs {
-  RowSideView side[2];         // [0] group1 (= the group of selfCoordNum), [1] group2
+  RowSideView own, nbr;        // group1 and group2 (selfCoordNum: the group, twice)
   int self;
   const int *idx;
   const int4 *chunks;
   unsigned cap_chunks;
-  int row_begin[2], row_end[2];  // this rank's rows of group1 / group2
-  unsigned chunk_base1;          // slot of group2's row 0 (= rows of group1)
-  unsigned chunk_extra;          // first overflow slot
+  int row_begin, row_end;      // this rank's rows
+  unsigned chunk_extra;        // first overflow slot
   unsigned *counts;
   unsigned long long *rare;
   unsigned int rare_cap;

@@ -260,8 +260,8 @@ int b200cv_pairlist_count(b200cv_cvc *h, size_t *count);
 int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *h_indices, size_t capacity);
 /* How the current list is kept: form 0 = packed (i, j) entries as the all-pairs sweep compacts
  * them, 1 = entries in cell order (cell-list rebuild, periodic cells), 2 = neighbour rows + a
- * few entries (open systems, sparse lists: every atom keeps all its partners, so a pair sits in
- * two rows), -1 = no rebuild yet; listed pairs, of them as packed entries, entries of all rows
+ * few entries (open systems, sparse lists: every group1 atom keeps its listed partners; for
+ * selfCoordNum those behind it in cell order), -1 = no rebuild yet; listed pairs, of them as packed entries, entries of all rows
  * (every row padded to a multiple of 32 entries), row chunks. */
 int b200cv_pairlist_stats(b200cv_cvc *h, int *form, size_t *pairs, size_t *entries,
                           size_t *row_entries, size_t *row_chunks);
