@@ -116,7 +116,7 @@ struct b200cv_cvc {
   bool sort_ready = false;
   b200cv::RowList rows;
   bool pl_rows = false;    // the current list is in row form
-  unsigned long long row_entries = 0;  // entries of all rows of this rank (both directions)
+  unsigned long long row_entries = 0;  // entries of all rows of this rank (padding included)
   // an evaluation has been enqueued whose queue counters / new list lengths the host has not
   // looked at yet (sync_and_check): the next call that builds on its result checks first
   bool unchecked = false;
