@@ -9,7 +9,13 @@ tests/test_oracle_ref_vectors.py):
 
 The arithmetic here is IEEE double without contraction; the kernel contracts the three dot
 products of step 3 into FMAs, which moves the candidates' scores by an ulp -- nine orders of
-magnitude below the margin."""
+magnitude below the margin.
+
+Since round 2 the kernel takes the DECISIONS (the integers of the fractional rounding, the image)
+in single precision with wider margins and does the arithmetic with the decided values in double
+precision in the reference's order (general_image: general_wrap-like steps 1-2, step 3);
+general_image_f32 below restates that with numpy float32 (no FMA: errors a little larger than
+the kernel's) and is held to the same two statements, also for vectors tens of cells long."""
 import ctypes as C
 
 import numpy as np
@@ -69,6 +75,80 @@ def general_image(bc, d):
     t = dx * s[:, 0] + dy * s[:, 1] + dz * s[:, 2]
     sgn = np.where(t > 0, -1.0, 1.0)
     return np.stack([dx + sgn * s[:, 0], dy + sgn * s[:, 1], dz + sgn * s[:, 2]], axis=1), ambiguous
+
+
+def general_image_f32(bc, d):
+    """general_image of pair_math.cuh, round 2: decisions in float32, arithmetic in float64"""
+    f32 = np.float32
+    cell, shift, n2, _ = tables(bc)
+    recip = np.array([list(v) for v in bc.reciprocal_cell])
+    max_n = max([v for v in n2 if v < 1e299], default=0.0)
+    marginf = f32(np.ldexp(max_n, -15))
+    n2f = np.minimum(n2, 3.0e38).astype(f32)
+    recipf, cell2f = recip.astype(f32), (2.0 * cell).astype(f32)
+    dx, dy, dz = d[:, 0].copy(), d[:, 1].copy(), d[:, 2].copy()
+    fx, fy, fz = dx.astype(f32), dy.astype(f32), dz.astype(f32)
+    amb = np.zeros(len(d), bool)
+    sh = []
+    with np.errstate(invalid="ignore", over="ignore"):
+        for a in range(3):
+            t0, t1, t2 = recipf[a, 0] * fx, recipf[a, 1] * fy, recipf[a, 2] * fz
+            u = (t0 + t1) + t2
+            mag = (np.abs(t0) + np.abs(t1)) + np.abs(t2)
+            r = np.rint(u)
+            dev = np.abs(u - r)
+            amb |= ~((mag * f32(2.0 ** -19) + dev) < f32(0.5))
+            sh.append(r.astype(np.float64))
+        dx = dx - ((sh[0] * cell[0, 0] + sh[1] * cell[1, 0]) + sh[2] * cell[2, 0])
+        dy = dy - ((sh[0] * cell[0, 1] + sh[1] * cell[1, 1]) + sh[2] * cell[2, 1])
+        dz = dz - ((sh[0] * cell[0, 2] + sh[1] * cell[1, 2]) + sh[2] * cell[2, 2])
+        gx, gy, gz = dx.astype(f32), dy.astype(f32), dz.astype(f32)
+        p = [(gx * cell2f[a, 0] + gy * cell2f[a, 1]) + gz * cell2f[a, 2] for a in range(3)]
+        pab, pamb = p[0] + p[1], p[0] - p[1]
+        q = np.stack([p[0], p[1], p[2], pab, pamb, p[0] + p[2], p[0] - p[2], p[1] + p[2],
+                      p[1] - p[2], pab + p[2], pab - p[2], pamb + p[2], pamb - p[2]])
+        v = n2f[:, None] - np.abs(q)
+        # the index rides in the four lowest mantissa bits
+        m = ((v.view(np.int32) & ~np.int32(15)) | np.arange(13, dtype=np.int32)[:, None]).view(f32)
+        best = m.min(axis=0)
+        cnt = (m < best + marginf).sum(axis=0)
+        shifted = best < marginf
+        amb |= (shifted & ((cnt >= 2) | (best > -marginf))) | np.isnan(best)
+        idx = np.where(shifted, best.view(np.int32) & 15, 13)
+    tab = np.concatenate([shift, np.zeros((1, 3))])
+    s = tab[idx]
+    t = dx * s[:, 0] + dy * s[:, 1] + dz * s[:, 2]
+    sgn = np.where(t > 0, -1.0, 1.0)
+    return np.stack([dx + sgn * s[:, 0], dy + sgn * s[:, 1], dz + sgn * s[:, 2]], axis=1), amb
+
+
+@pytest.mark.parametrize("span", [2.0, 40.0])
+@pytest.mark.parametrize("cell", list(CELLS))
+def test_single_precision_decisions_are_the_references_wherever_taken(cell, span):
+    """span: the atoms lie within +- span cells of the origin (40: unwrapped trajectories; the
+    margins grow with the size of the terms and hand more pairs over)"""
+    per, A, B, Cc = CELLS[cell]
+    L = 21.0
+    A, B, Cc = (L * np.array(v) for v in (A, B, Cc))
+    p = O.make_params(boundaries=(per, A, B, Cc))
+    lib = O.lib()
+    rng = np.random.default_rng(4242)
+    n = 60000
+    lat = np.array([A, B, Cc])
+    p1 = (rng.random((n, 3)) * 2 * span - span) @ lat
+    p2 = (rng.random((n, 3)) * 2 * span - span) @ lat
+    mine, ambiguous = general_image_f32(p.bc, p2 - p1)
+    ref = np.zeros((n, 3))
+    out = np.zeros(3)
+    dp = C.POINTER(C.c_double)
+    for k in range(n):
+        a, b = np.ascontiguousarray(p1[k]), np.ascontiguousarray(p2[k])
+        lib.cvo_position_distance(C.byref(p.bc), a.ctypes.data_as(dp), b.ctypes.data_as(dp),
+                                  out.ctypes.data_as(dp))
+        ref[k] = out
+    decided = ~ambiguous
+    assert ambiguous.mean() < (3e-3 if span < 10 else 2e-2), ambiguous.mean()
+    assert np.array_equal(mine[decided], ref[decided])
 
 
 @pytest.mark.parametrize("cell", list(CELLS))
