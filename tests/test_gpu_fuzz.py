@@ -99,3 +99,82 @@ def test_random_configuration_matches_the_oracle(seed):
     if use_pl and not centre:
         # list contents after the last rebuild, bit-exact canonical indices
         assert np.array_equal(np.sort(cv.pairlist()), np.flatnonzero(pl).astype(np.uint64)), cfg
+
+
+import os
+
+NSPARSE = int(os.environ.get("B200CV_FUZZ_SPARSE", "16"))
+
+
+def draw_sparse(seed):
+    """a system whose pair list is sparse (well below 2 % of the pairs), so that rebuilds after the
+    first go through the cell order: neighbour rows in an open system, cell-ordered entries in a
+    periodic cell"""
+    rng = np.random.default_rng(77000 + seed)
+    kind = str(rng.choice(["selfCoordNum", "coordNum"]))
+    if kind == "selfCoordNum":
+        n1, n2 = int(rng.integers(1500, 5000)), 0
+    else:
+        n1, n2 = int(rng.integers(40, 1200)), int(rng.integers(2500, 7000))
+    cfg = dict(kind=kind, n1=n1, n2=n2, seed=seed)
+    cfg["cutoff3"] = (3.5,) * 3 if rng.random() < 0.5 else tuple(rng.uniform(2.5, 4.0, 3))
+    cfg["tol"] = float(rng.choice([0.002, 0.01, 0.03]))
+    cfg["freq"] = int(rng.choice([1, 2, 3]))
+    cfg["cell"] = str(rng.choice(["none", "none", "ortho", "triclinic"]))
+    cfg["shape"] = str(rng.choice(["uniform", "blobs", "slab"]))
+    cfg["sigma"] = float(rng.choice([0.02, 0.1, 0.3]))
+    return cfg, rng
+
+
+@pytest.mark.parametrize("seed", range(NSPARSE))
+def test_random_sparse_pairlist_configuration_matches_the_oracle(seed):
+    cb = _cb()
+    cfg, rng = draw_sparse(seed)
+    kind, n1, n2 = cfg["kind"], cfg["n1"], cfg["n2"]
+    n = n1 + n2
+    L = 90.0
+    if cfg["shape"] == "uniform":
+        pos = rng.random((n, 3)) * L
+    elif cfg["shape"] == "blobs":
+        centres = rng.random((12, 3)) * L
+        pos = centres[rng.integers(12, size=n)] + rng.normal(0, 15.0, (n, 3))
+    else:
+        pos = rng.random((n, 3)) * np.array([L, L, 40.0])
+        pos[:, 2] += 0.25 * L
+    if kind == "coordNum":
+        rng.shuffle(pos)
+    cell = None
+    if cfg["cell"] == "ortho":
+        cell = ((1, 1, 1), (L, 0, 0), (0, L * 1.1, 0), (0, 0, L * 0.9))
+    elif cfg["cell"] == "triclinic":
+        cell = ((1, 1, 1), (L, 0, 0), (0.3 * L, L, 0), (0.1 * L, -0.2 * L, L))
+    i1 = np.arange(n1, dtype=np.int32)
+    i2 = np.arange(n1, n, dtype=np.int32) if n2 else None
+    cv = cb.CoordNum(kind, i1, i2, cutoff3=cfg["cutoff3"], tolerance=cfg["tol"],
+                     pairlist_freq=cfg["freq"])
+    if cell:
+        cv.set_boundaries(*cell)
+    p = O.make_params(cfg["cutoff3"], 6, 12, cfg["tol"], boundaries=cell)
+    npairs = n1 * (n1 - 1) // 2 if kind == "selfCoordNum" else n1 * n2
+    pl = np.ones(npairs, dtype=np.uint8)
+    for step in range(2 * cfg["freq"] + 2):
+        frame = np.ascontiguousarray(pos + rng.normal(0, cfg["sigma"], pos.shape) * step)
+        v = cv.calc_host(frame, step=step)
+        rebuild = step % cfg["freq"] == 0
+        if kind == "selfCoordNum":
+            ov, og1 = O.selfcoordnum(p, frame[i1], pairlist=pl, rebuild=rebuild)
+            og2 = None
+        else:
+            ov, og1, og2 = O.coordnum(p, frame[i1], frame[i2], pairlist=pl, rebuild=rebuild)
+        scale = max(abs(ov), 1e-9 * npairs)
+        assert abs(v - ov) <= RTOL * scale, (cfg, step, v, ov)
+        close_arr(cv.gradients(1), og1)
+        if og2 is not None:
+            close_arr(cv.gradients(2), og2)
+        if rebuild:
+            assert np.array_equal(np.sort(cv.pairlist()),
+                                  np.flatnonzero(pl).astype(np.uint64)), (cfg, step)
+    # the list was sparse, so the later rebuilds went through the cell order: neighbour rows (2) in
+    # an open system, cell-ordered entries (1) in a periodic cell
+    if pl.sum() * 64 < npairs:
+        assert cv.pairlist_stats()["form"] == (2 if cell is None else 1), (cfg, cv.pairlist_stats())

@@ -1,5 +1,3 @@
 #!/bin/bash
-# scratch: the GPU-box side of one gpurun call (edited per experiment)
 out=gpurun_out/$1; mkdir -p $out
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 1500 python -m pytest tests -x -q -m gpu > $out/tests.log 2>&1; tail -3 $out/tests.log
+B200CV_FUZZ_SPARSE=60 timeout 1700 python -m pytest tests/test_gpu_fuzz.py -q -m gpu -k sparse -x > $out/fuzz.log 2>&1; tail -15 $out/fuzz.log
