@@ -987,7 +987,7 @@ int b200cv_pairlist_export(b200cv_cvc *h, uint64_t *out, size_t capacity)
     return h->self() ? i * (2 * n1 - i - 1) / 2 + (j - i - 1) : i * n2 + j;
   };
   if (h->pl_rows) {
-    // row form (rows.cuh): the canonical side of every row chunk + the extras (atom indices)
+    // row form (rows.cuh): the entries of every row chunk + the extras (atom indices)
     CellSort &B = h->sort;
     SortedGroup &J = B.side[1];
     SortedGroup &I = h->self() ? J : B.side[0];

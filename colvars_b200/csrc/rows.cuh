@@ -62,7 +62,7 @@ struct RowList {
   int4 *d_chunks = nullptr;
   unsigned cap_chunks = 0;
   // counters live in CellSort::d_counts: [0] overflow chunks of this build, [3] entries of this
-  // build, [4..5] listed pairs in rows of this build (counted on the canonical side), [6] overflow chunks
+  // build, [4..5] listed pairs in rows of this build, [6] overflow chunks
   // of the current list
 };
 
