@@ -1,3 +1,7 @@
 #!/bin/bash
 out=gpurun_out/$1; mkdir -p $out
-B200CV_FUZZ_SPARSE=60 timeout 1700 python -m pytest tests/test_gpu_fuzz.py -q -m gpu -k sparse -x > $out/fuzz.log 2>&1; tail -15 $out/fuzz.log
+for v in "" _nored; do
+  echo "== variant '$v'"
+  B200CV_LIB=colvars_b200/libb200cv$v.so ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:row_walk -c 3 --csv --log-file $out/walk$v.csv python tools/exp_c3_steps.py 50000 14 > /dev/null 2>&1
+  grep row_walk $out/walk$v.csv | awk -F'","' '{print $(NF-2), $NF}' | tr -d '"' | tail -2
+done
